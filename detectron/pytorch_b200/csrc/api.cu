@@ -1,0 +1,129 @@
+// api.cu -- the extern "C" boundary of libb200_roi_ops.so (see include/b200_roi_ops.h).
+// Argument validation + dispatch only; kernels live in the per-op translation units.
+#include "common.cuh"
+
+namespace b200 {
+unsigned long long g_launch_count = 0;
+
+int roi_align_forward_generic(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, cudaStream_t);
+int roi_align_backward_generic(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, cudaStream_t);
+int roi_align_legacy_forward(const float*, float, int, int, int, int, int, int, int, const float*, float*, cudaStream_t);
+int roi_align_legacy_backward(const float*, float, int, int, int, int, int, int, int, const float*, float*, cudaStream_t);
+int roi_pool_forward(const float*, float, int, int, int, int, int, int, int, const float*, float*, int*, cudaStream_t);
+int roi_pool_backward(const float*, float, int, int, int, int, int, int, int, const float*, float*, const int*, cudaStream_t);
+int roi_crop_forward(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
+int roi_crop_backward(const float*, const float*, int, int, int, int, int, int, int, float*, float*, cudaStream_t);
+size_t nms_workspace_bytes(int);
+int nms(const float*, int, int, float, int*, int*, void*, size_t, cudaStream_t);
+
+static inline bool bad_dims(int N, int R, int H, int W, int C, int PH, int PW) {
+    return N < 0 || R < 0 || H <= 0 || W <= 0 || C < 0 || PH <= 0 || PW <= 0;
+}
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_roi_ops_abi_version(void) { return 1; }
+
+const char* b200_roi_ops_strerror(int status) {
+    if (status == B200_ROI_OK) return "success";
+    if (status == B200_ROI_EINVAL) return "b200_roi_ops: invalid argument (null pointer, negative or zero dimension)";
+    if (status == B200_ROI_EWORKSPACE) return "b200_roi_ops: workspace missing or smaller than b200_nms_workspace_bytes()";
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "b200_roi_ops: unknown status";
+}
+
+unsigned long long b200_roi_ops_launch_count(void) { return g_launch_count; }
+
+int b200_roi_align_forward(const float* bottom_data, float spatial_scale, int batch_size, int num_rois, int height,
+                           int width, int channels, int aligned_height, int aligned_width, int sampling_ratio,
+                           const float* bottom_rois, float* top_data, b200_stream_t stream) {
+    if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
+    if (num_rois > 0 && channels > 0 && (!bottom_data || !bottom_rois || !top_data)) return B200_ROI_EINVAL;
+    return roi_align_forward_generic(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
+                                     aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data,
+                                     (cudaStream_t)stream);
+}
+
+int b200_roi_align_backward(const float* top_diff, float spatial_scale, int batch_size, int num_rois, int height,
+                            int width, int channels, int aligned_height, int aligned_width, int sampling_ratio,
+                            const float* bottom_rois, float* bottom_diff, b200_stream_t stream) {
+    if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
+    if ((size_t)batch_size * channels == 0) return B200_ROI_OK;
+    if (!bottom_diff || (num_rois > 0 && (!top_diff || !bottom_rois))) return B200_ROI_EINVAL;
+    return roi_align_backward_generic(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
+                                      aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff,
+                                      (cudaStream_t)stream);
+}
+
+int b200_roi_align_legacy_forward(const float* bottom_data, float spatial_scale, int batch_size, int num_rois,
+                                  int height, int width, int channels, int aligned_height, int aligned_width,
+                                  const float* bottom_rois, float* top_data, b200_stream_t stream) {
+    if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
+    if (num_rois > 0 && channels > 0 && (!bottom_data || !bottom_rois || !top_data)) return B200_ROI_EINVAL;
+    return roi_align_legacy_forward(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
+                                    aligned_height, aligned_width, bottom_rois, top_data, (cudaStream_t)stream);
+}
+
+int b200_roi_align_legacy_backward(const float* top_diff, float spatial_scale, int batch_size, int num_rois,
+                                   int height, int width, int channels, int aligned_height, int aligned_width,
+                                   const float* bottom_rois, float* bottom_diff, b200_stream_t stream) {
+    if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
+    if ((size_t)batch_size * channels == 0) return B200_ROI_OK;
+    if (!bottom_diff || (num_rois > 0 && (!top_diff || !bottom_rois))) return B200_ROI_EINVAL;
+    return roi_align_legacy_backward(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
+                                     aligned_height, aligned_width, bottom_rois, bottom_diff, (cudaStream_t)stream);
+}
+
+int b200_roi_pool_forward(const float* bottom_data, float spatial_scale, int batch_size, int num_rois, int height,
+                          int width, int channels, int pooled_height, int pooled_width, const float* bottom_rois,
+                          float* top_data, int* argmax_data, b200_stream_t stream) {
+    if (bad_dims(batch_size, num_rois, height, width, channels, pooled_height, pooled_width)) return B200_ROI_EINVAL;
+    if (num_rois > 0 && channels > 0 && (!bottom_data || !bottom_rois || !top_data)) return B200_ROI_EINVAL;
+    return roi_pool_forward(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels, pooled_height,
+                            pooled_width, bottom_rois, top_data, argmax_data, (cudaStream_t)stream);
+}
+
+int b200_roi_pool_backward(const float* top_diff, float spatial_scale, int batch_size, int num_rois, int height,
+                           int width, int channels, int pooled_height, int pooled_width, const float* bottom_rois,
+                           float* bottom_diff, const int* argmax_data, b200_stream_t stream) {
+    if (bad_dims(batch_size, num_rois, height, width, channels, pooled_height, pooled_width)) return B200_ROI_EINVAL;
+    if ((size_t)batch_size * channels == 0) return B200_ROI_OK;
+    if (!bottom_diff || (num_rois > 0 && (!top_diff || !bottom_rois || !argmax_data))) return B200_ROI_EINVAL;
+    return roi_pool_backward(top_diff, spatial_scale, batch_size, num_rois, height, width, channels, pooled_height,
+                             pooled_width, bottom_rois, bottom_diff, argmax_data, (cudaStream_t)stream);
+}
+
+int b200_roi_crop_forward(const float* image, const float* grids, int batch_size, int channels, int height, int width,
+                          int num_rois, int out_height, int out_width, float* output, b200_stream_t stream) {
+    if (batch_size < 0 || channels < 0 || height <= 0 || width <= 0 || num_rois < 0 || out_height < 0 || out_width < 0)
+        return B200_ROI_EINVAL;
+    if ((size_t)num_rois * out_height * out_width * channels > 0 && (!image || !grids || !output)) return B200_ROI_EINVAL;
+    return roi_crop_forward(image, grids, batch_size, channels, height, width, num_rois, out_height, out_width, output,
+                            (cudaStream_t)stream);
+}
+
+int b200_roi_crop_backward(const float* grad_output, const float* grids, int batch_size, int channels, int height,
+                           int width, int num_rois, int out_height, int out_width, float* grad_image,
+                           float* grad_grids, b200_stream_t stream) {
+    if (batch_size < 0 || channels < 0 || height <= 0 || width <= 0 || num_rois < 0 || out_height < 0 || out_width < 0)
+        return B200_ROI_EINVAL;
+    if ((size_t)batch_size * channels == 0) return B200_ROI_OK;
+    if (!grad_image) return B200_ROI_EINVAL;
+    if ((size_t)num_rois * out_height * out_width > 0 && (!grad_output || !grids)) return B200_ROI_EINVAL;
+    return roi_crop_backward(grad_output, grids, batch_size, channels, height, width, num_rois, out_height, out_width,
+                             grad_image, grad_grids, (cudaStream_t)stream);
+}
+
+size_t b200_nms_workspace_bytes(int boxes_num) { return nms_workspace_bytes(boxes_num); }
+
+int b200_nms(const float* boxes_dev, int boxes_num, int boxes_dim, float nms_overlap_thresh, int* keep_out_dev,
+             int* num_out_dev, void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+    if (!num_out_dev || (boxes_num > 0 && (!boxes_dev || !keep_out_dev))) return B200_ROI_EINVAL;
+    return nms(boxes_dev, boxes_num, boxes_dim, nms_overlap_thresh, keep_out_dev, num_out_dev, workspace,
+               workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// common.cuh -- shared helpers for libb200_roi_ops.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../../include/b200_roi_ops.h"
+
+namespace b200 {
+
+// ---- launch accounting / error plumbing -------------------------------------------------------
+extern unsigned long long g_launch_count;   // defined in api.cu
+
+inline int finish_launch(int n_launches = 1) {
+    g_launch_count += (unsigned long long)n_launches;
+    cudaError_t err = cudaGetLastError();
+    return (err == cudaSuccess) ? B200_ROI_OK : (int)err;
+}
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+// ---- arithmetic that must round exactly like the reference kernels' SASS --------------------
+// All helpers use the _rn intrinsics, which nvcc never contracts or re-associates, so the
+// fusion pattern is exactly what is written here (see oracle/roi_ops_oracle.c for the recipes
+// and how they were read off `cuobjdump -sass` of the reference kernels built for sm_100a).
+
+// RoI geometry of the Caffe2-exact RoIAlign (reference roi_align_kernel.cu:75-98).
+struct XfromRoi {
+    int   batch;
+    float start_w, start_h, bin_w, bin_h;
+    int   grid_w, grid_h;
+};
+
+__device__ __forceinline__ XfromRoi xfrom_roi(const float* __restrict__ roi, float scale, int PH, int PW, int sr) {
+    XfromRoi g;
+    g.batch = (int)roi[0];
+    g.start_w = __fmul_rn(roi[1], scale);
+    g.start_h = __fmul_rn(roi[2], scale);
+    float rw = fmaxf(__fmaf_rn(roi[3], scale, -g.start_w), 1.f);
+    float rh = fmaxf(__fmaf_rn(roi[4], scale, -g.start_h), 1.f);
+    g.bin_h = __fdiv_rn(rh, (float)PH);
+    g.bin_w = __fdiv_rn(rw, (float)PW);
+    g.grid_h = (sr > 0) ? sr : (int)ceilf(g.bin_h);
+    g.grid_w = (sr > 0) ? sr : (int)ceilf(g.bin_w);
+    return g;
+}
+
+// sample coordinate: FADD(FFMA(p, bin, start), FMUL(i + .5, bin) / grid)   (:106-110)
+__device__ __forceinline__ float xfrom_coord(float start, float bin, int p, int i, int grid) {
+    float base = __fmaf_rn((float)p, bin, start);
+    float off = __fdiv_rn(__fmul_rn(__fadd_rn((float)i, .5f), bin), (float)grid);
+    return __fadd_rn(base, off);
+}
+
+// One axis of bilinear_interpolate (:19-52): low/high cell and the two weights (l = frac, h = 1-l).
+// valid == false  <=>  the reference's "outside the map" early-out for this axis.
+struct AxisTap {
+    int   low, high;
+    float l, h;
+    bool  valid;
+};
+
+__device__ __forceinline__ AxisTap xfrom_axis(float v, int size) {
+    AxisTap t;
+    t.valid = !(v < -1.0f || v > (float)size);
+    if (v <= 0.f) v = 0.f;
+    int low = (int)v;
+    if (low >= size - 1) {
+        t.low = t.high = size - 1;
+        v = (float)(size - 1);
+    } else {
+        t.low = low;
+        t.high = low + 1;
+    }
+    t.l = __fsub_rn(v, (float)t.low);
+    t.h = __fsub_rn(1.f, t.l);
+    return t;
+}
+
+}  // namespace b200

@@ -1,0 +1,152 @@
+// nms.cu -- proposal-layer NMS, everything on the device and on the caller's stream.
+//
+// Semantics: lib/model/nms/src/nms_cuda_kernel.cu (reference) devIoU :31-39, nms_kernel :41-85,
+// host greedy scan :123-144.  Kept indices are bit-exact with the reference because (a) the IoU
+// test reproduces the reference's SASS rounding recipe (row box = lower index: rounded area Sa;
+// column box area fused: FFMA(bw, bh, Sa); IEEE division; strict '>') and (b) the greedy scan is
+// the same integer logic -- box j is dropped iff a kept box i < j has bit (i, j) set.
+//
+// Differences in mechanism (not in results): only the upper triangle of 64x64 tiles is computed
+// (the reference commented its triangular skip out, :46, and did 2x the work); the suppression
+// scan runs on the GPU (one CTA; a warp resolves each 64-box diagonal block with shuffles, then
+// 1024 threads OR the kept rows into the running removal words) instead of a 4.5 MB blocking D2H
+// copy + single-threaded CPU loop + H2D; no cudaMalloc/cudaFree: scratch comes from the caller.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kNmsTile = 64;
+constexpr int kScanThreads = 1024;
+
+typedef unsigned long long u64;
+
+struct __align__(16) ColBox {
+    float x0, y0, x1, y1;
+};
+
+__device__ __forceinline__ bool nms_bit(float a0, float a1, float a2, float a3, float Sa,
+                                        float b0, float b1, float b2, float b3, float thresh) {
+    const float left = fmaxf(a0, b0), right = fminf(a2, b2);
+    const float top = fmaxf(a1, b1), bottom = fminf(a3, b3);
+    const float w = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+    const float h = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+    const float inter = __fmul_rn(w, h);
+    const float t = __fmaf_rn(__fadd_rn(__fsub_rn(b2, b0), 1.f), __fadd_rn(__fsub_rn(b3, b1), 1.f), Sa);
+    const float den = __fsub_rn(t, inter);
+    return __fdiv_rn(inter, den) > thresh;
+}
+
+// grid = (col_blocks, row_blocks); tiles below the diagonal exit immediately (their mask words
+// are never read by the scan).
+__global__ void __launch_bounds__(kNmsTile)
+nms_mask_kernel(const float* __restrict__ boxes, int n, int dim, float thresh, u64* __restrict__ mask) {
+    const int row_start = blockIdx.y, col_start = blockIdx.x;
+    if (row_start > col_start) return;
+    const int row_size = min(n - row_start * kNmsTile, kNmsTile);
+    const int col_size = min(n - col_start * kNmsTile, kNmsTile);
+    __shared__ ColBox cols[kNmsTile];
+    if ((int)threadIdx.x < col_size) {
+        const float* p = boxes + (size_t)(col_start * kNmsTile + threadIdx.x) * dim;
+        ColBox b; b.x0 = p[0]; b.y0 = p[1]; b.x1 = p[2]; b.y1 = p[3];
+        cols[threadIdx.x] = b;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < row_size) {
+        const int cur = row_start * kNmsTile + threadIdx.x;
+        const float* a = boxes + (size_t)cur * dim;
+        const float a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
+        const float Sa = __fmul_rn(__fadd_rn(__fsub_rn(a2, a0), 1.f), __fadd_rn(__fsub_rn(a3, a1), 1.f));
+        u64 t = 0;
+        const int start = (row_start == col_start) ? threadIdx.x + 1 : 0;
+        for (int i = start; i < col_size; ++i) {
+            const ColBox b = cols[i];
+            if (nms_bit(a0, a1, a2, a3, Sa, b.x0, b.y0, b.x1, b.y1, thresh)) t |= 1ULL << i;
+        }
+        const int col_blocks = (n + kNmsTile - 1) / kNmsTile;
+        mask[(size_t)cur * col_blocks + col_start] = t;
+    }
+}
+
+// Single-CTA greedy scan over the upper-triangular mask.  remv[] (one 64-bit word per column block)
+// lives in shared memory.
+__global__ void __launch_bounds__(kScanThreads)
+nms_scan_kernel(const u64* __restrict__ mask, int n, int col_blocks, int* __restrict__ keep_out, int* __restrict__ num_out) {
+    extern __shared__ u64 remv[];
+    __shared__ u64 s_kept;
+    __shared__ int s_count;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j = tid; j < col_blocks; j += kScanThreads) remv[j] = 0;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+
+    for (int b = 0; b < col_blocks; ++b) {
+        const int lim = min(kNmsTile, n - b * kNmsTile);
+        if (warp == 0) {
+            // lane l holds the diagonal words of rows b*64 + l and b*64 + 32 + l
+            const int r0 = b * kNmsTile + lane, r1 = r0 + 32;
+            const u64 d_lo = (r0 < n) ? mask[(size_t)r0 * col_blocks + b] : 0;
+            const u64 d_hi = (r1 < n) ? mask[(size_t)r1 * col_blocks + b] : 0;
+            u64 r = remv[b];
+            u64 kept = 0;
+#pragma unroll 8
+            for (int k = 0; k < kNmsTile; ++k) {
+                const u64 dk = __shfl_sync(0xffffffffu, (k < 32) ? d_lo : d_hi, k & 31);
+                if (k < lim && !((r >> k) & 1ULL)) { kept |= 1ULL << k; r |= dk; }
+            }
+            if (lane == 0) s_kept = kept;
+        }
+        __syncthreads();
+        const u64 kept = s_kept;
+        const int base = s_count;
+        if (tid < kNmsTile && ((kept >> tid) & 1ULL))
+            keep_out[base + __popcll(kept & ((1ULL << tid) - 1ULL))] = b * kNmsTile + tid;
+        // OR the mask rows of the kept boxes of block b into remv[j], j > b:
+        // thread = (k-group of 8, column word j); 128 column words per pass.
+        const int kg = tid >> 7;            // 0..7
+        for (int j = b + 1 + (tid & 127); j < col_blocks; j += 128) {
+            u64 acc = 0;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const int k = kg + 8 * kk;
+                if ((kept >> k) & 1ULL) acc |= mask[(size_t)(b * kNmsTile + k) * col_blocks + j];
+            }
+            if (acc) atomicOr(&remv[j], acc);
+        }
+        __syncthreads();
+        if (tid == 0) s_count = base + __popcll(kept);
+        // (next iteration's first __syncthreads publishes s_count / remv)
+    }
+    __syncthreads();
+    if (tid == 0) *num_out = s_count;
+}
+
+__global__ void nms_empty_kernel(int* num_out) { *num_out = 0; }
+
+size_t nms_workspace_bytes(int n) {
+    if (n <= 0) return 256;
+    const size_t cb = (size_t)(n + kNmsTile - 1) / kNmsTile;
+    return ((size_t)n * cb * sizeof(u64) + 255) / 256 * 256;
+}
+
+int nms(const float* boxes, int n, int dim, float thresh, int* keep_out, int* num_out, void* workspace,
+        size_t workspace_bytes, cudaStream_t stream) {
+    if (n < 0 || dim < 4) return B200_ROI_EINVAL;
+    if (n == 0) {
+        nms_empty_kernel<<<1, 1, 0, stream>>>(num_out);
+        return finish_launch();
+    }
+    if (workspace == nullptr || workspace_bytes < nms_workspace_bytes(n)) return B200_ROI_EWORKSPACE;
+    const int cb = (n + kNmsTile - 1) / kNmsTile;
+    u64* mask = (u64*)workspace;
+    dim3 grid(cb, cb);
+    nms_mask_kernel<<<grid, kNmsTile, 0, stream>>>(boxes, n, dim, thresh, mask);
+    const size_t smem = sizeof(u64) * (size_t)cb;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    nms_scan_kernel<<<1, kScanThreads, smem, stream>>>(mask, n, cb, keep_out, num_out);
+    return finish_launch(2);
+}
+
+}  // namespace b200

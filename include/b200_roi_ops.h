@@ -1,0 +1,127 @@
+/*
+ * b200_roi_ops.h -- C ABI of libb200_roi_ops.so: hand-written sm_100a CUDA replacements for the
+ * per-image detection hot path of roytseng-tw/Detectron.pytorch (RoIAlign fwd/bwd in both
+ * flavours, RoIPool, RoICrop, proposal NMS).
+ *
+ * The boundary mirrors the raw-pointer `extern "C"` launchers that sit under the reference's
+ * cffi/THC glue (the layer its `_ext` modules bind): plain device pointers, ints and floats, a
+ * CUDA stream, no torch types.  Each entry point cites the reference launcher it replaces
+ * (paths relative to the reference repository root).
+ *
+ * Conventions (all entry points)
+ *   - every pointer is a DEVICE pointer to dense, row-major ("contiguous") memory;
+ *   - features / gradients are fp32 NCHW; rois are fp32 (R,5) = [batch_idx, x1, y1, x2, y2] in
+ *     image pixels; boxes for NMS are fp32 (N,dim>=4) = [x1, y1, x2, y2, ...];
+ *   - work is enqueued on `stream` (pass torch's current stream); calls never synchronise unless
+ *     stated, keep no reference to caller memory after the enqueued work finishes, and are
+ *     re-entrant per device;
+ *   - outputs need NOT be pre-zeroed by the caller (the reference required `.zero_()`,
+ *     functions/roi_align.py:23,39-40): every call fully defines its output;
+ *   - return value: 0 = success; > 0 = a cudaError_t raised by the launch; < 0 = argument error
+ *     (B200_ROI_EINVAL, B200_ROI_EWORKSPACE).  The reference instead returned 1/0 and called
+ *     exit(-1) on a launch error (roi_align_kernel.cu:135-139); the Python layer turns a non-zero
+ *     status into RuntimeError.
+ */
+#ifndef B200_ROI_OPS_H_
+#define B200_ROI_OPS_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* b200_stream_t; /* == cudaStream_t */
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#define B200_ROI_OK 0
+#define B200_ROI_EINVAL (-1)
+#define B200_ROI_EWORKSPACE (-2)
+
+/* ABI version of this header (bumped on any signature change). */
+B200_API int b200_roi_ops_abi_version(void);
+/* Human-readable message for a status returned by any entry point. */
+B200_API const char* b200_roi_ops_strerror(int status);
+
+/* ---- RoIAlign, Caffe2/Detectron-exact variant (sampling_ratio) ---------------------------------
+ * replaces ROIAlignForwardLaucher / ROIAlignBackwardLaucher,
+ *   lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu:123-142, 272-290
+ *   (declared lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.h:13-27; bound through
+ *    roi_align_forward_cuda / roi_align_backward_cuda, src/roi_align_cuda.c:7-40, 42-76).
+ * Same argument meaning and order; `batch_size` is added to the forward (the reference only passed
+ * it to the backward) so that batch indices can be range-checked by the planner.
+ * top: (R, C, aligned_height, aligned_width).  bottom_diff: (batch_size, C, H, W), fully written. */
+B200_API int b200_roi_align_forward(const float* bottom_data, float spatial_scale, int batch_size, int num_rois,
+                           int height, int width, int channels, int aligned_height, int aligned_width,
+                           int sampling_ratio, const float* bottom_rois, float* top_data,
+                           b200_stream_t stream);
+B200_API int b200_roi_align_backward(const float* top_diff, float spatial_scale, int batch_size, int num_rois,
+                            int height, int width, int channels, int aligned_height, int aligned_width,
+                            int sampling_ratio, const float* bottom_rois, float* bottom_diff,
+                            b200_stream_t stream);
+
+/* ---- RoIAlign, legacy variant (one bilinear sample per lattice corner, fp64 interpolation) -----
+ * replaces ROIAlignForwardLaucher / ROIAlignBackwardLaucher,
+ *   lib/model/roi_align/src/roi_align_kernel.cu:73-91, 145-162 (header roi_align_kernel.h). */
+B200_API int b200_roi_align_legacy_forward(const float* bottom_data, float spatial_scale, int batch_size, int num_rois,
+                                  int height, int width, int channels, int aligned_height, int aligned_width,
+                                  const float* bottom_rois, float* top_data, b200_stream_t stream);
+B200_API int b200_roi_align_legacy_backward(const float* top_diff, float spatial_scale, int batch_size, int num_rois,
+                                   int height, int width, int channels, int aligned_height, int aligned_width,
+                                   const float* bottom_rois, float* bottom_diff, b200_stream_t stream);
+
+/* ---- RoIPool -----------------------------------------------------------------------------------
+ * replaces ROIPoolForwardLaucher / ROIPoolBackwardLaucher,
+ *   lib/model/roi_pooling/src/roi_pooling_kernel.cu:95-125, 205-234 (header roi_pooling_kernel.h:8-18).
+ * argmax_data: int32 (R, C, PH, PW), flat index into the WHOLE bottom tensor or -1; may be NULL in
+ * the forward.  The backward is deterministic and bit-identical to the reference's gather. */
+B200_API int b200_roi_pool_forward(const float* bottom_data, float spatial_scale, int batch_size, int num_rois,
+                          int height, int width, int channels, int pooled_height, int pooled_width,
+                          const float* bottom_rois, float* top_data, int* argmax_data, b200_stream_t stream);
+B200_API int b200_roi_pool_backward(const float* top_diff, float spatial_scale, int batch_size, int num_rois,
+                           int height, int width, int channels, int pooled_height, int pooled_width,
+                           const float* bottom_rois, float* bottom_diff, const int* argmax_data,
+                           b200_stream_t stream);
+
+/* ---- RoICrop (bilinear sampler from an explicit grid) -----------------------------------------
+ * replaces BilinearSamplerBHWD_updateOutput_cuda_kernel / _updateGradInput_cuda_kernel,
+ *   lib/model/roi_crop/src/roi_crop_cuda_kernel.cu:201-255, 257-326 (header roi_crop_cuda_kernel.h:6-32).
+ * image: (N, C, H, W); grids: (R, out_h, out_w, 2) with channel 0 = y, channel 1 = x in [-1, 1];
+ * output: (R, C, out_h, out_w).  RoI b samples image b / (R / N) (kernel :64, :217).  Dense tensors
+ * only (the reference took explicit strides; the Python layer makes inputs contiguous).
+ * grad_grids (same shape as grids) is zero-filled when non-NULL: the reference CUDA kernel never
+ * stores the grid gradient (:111-194), so the observable result is zeros. */
+B200_API int b200_roi_crop_forward(const float* image, const float* grids, int batch_size, int channels, int height,
+                          int width, int num_rois, int out_height, int out_width, float* output,
+                          b200_stream_t stream);
+B200_API int b200_roi_crop_backward(const float* grad_output, const float* grids, int batch_size, int channels,
+                           int height, int width, int num_rois, int out_height, int out_width,
+                           float* grad_image, float* grad_grids, b200_stream_t stream);
+
+/* ---- proposal NMS ------------------------------------------------------------------------------
+ * replaces nms_cuda_compute, lib/model/nms/src/nms_cuda_kernel.cu:87-161 (header nms_cuda_kernel.h:5-6;
+ * bound through nms_cuda, src/nms_cuda.c:8-19).
+ * boxes_dev: (boxes_num, boxes_dim) fp32, ALREADY sorted by score (the function never sorts).
+ * keep_out_dev: int32[boxes_num], receives the kept row indices in ascending order;
+ * num_out_dev: int32[1], receives their count.  Unlike the reference (cudaMalloc/cudaFree, four
+ * blocking memcpys, host-side greedy scan, legacy default stream) everything runs on `stream` with
+ * no host round trip; scratch comes from the caller: `workspace` must hold at least
+ * b200_nms_workspace_bytes(boxes_num) bytes (256-byte aligned). */
+B200_API size_t b200_nms_workspace_bytes(int boxes_num);
+B200_API int b200_nms(const float* boxes_dev, int boxes_num, int boxes_dim, float nms_overlap_thresh,
+             int* keep_out_dev, int* num_out_dev, void* workspace, size_t workspace_bytes,
+             b200_stream_t stream);
+
+/* ---- introspection used by the benchmark / tests (no compute) ----------------------------------
+ * Number of kernel launches the library has enqueued since load (all entry points). */
+B200_API unsigned long long b200_roi_ops_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_ROI_OPS_H_ */

@@ -1,0 +1,63 @@
+"""CPU-only: the C-ABI library builds for sm_100a, loads, exports every symbol include/*.h declares,
+and validates its arguments before touching CUDA (no compute calls here: there is no GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from detectron.pytorch_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200_roi_ops.h")).read()
+    return sorted(set(re.findall(r"B200_API[^;(]*?\b(b200_\w+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    path = build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 13
+    for name in declared:
+        assert hasattr(lib, name), "header declares %s but the library does not export it" % name
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared       # python binding covers exactly the header
+
+
+def test_sm100a_cubin_embedded():
+    import subprocess
+    path = build.build()
+    out = subprocess.run(["cuobjdump", "-lelf", path], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.load()
+    assert lib.b200_roi_ops_abi_version() == 1
+    EINVAL = -1
+    # negative / zero dimensions and null pointers are rejected before any CUDA call
+    assert lib.b200_roi_align_forward(None, 0.25, 1, 4, 0, 10, 3, 7, 7, 2, None, None, None) == EINVAL
+    assert lib.b200_roi_align_forward(None, 0.25, 1, 4, 10, 10, 3, 7, 7, 2, None, None, None) == EINVAL
+    assert lib.b200_roi_align_backward(None, 0.25, 1, 4, 10, 10, 3, 7, 7, 2, None, None, None) == EINVAL
+    assert lib.b200_roi_pool_forward(None, 0.25, 1, 4, 10, 10, 3, -7, 7, None, None, None, None) == EINVAL
+    assert lib.b200_roi_crop_forward(None, None, 1, 3, 10, 10, 2, 7, 7, None, None) == EINVAL
+    assert lib.b200_nms(None, 10, 5, 0.7, None, None, None, 0, None) == EINVAL
+    assert b"invalid argument" in lib.b200_roi_ops_strerror(EINVAL)
+    assert lib.b200_roi_ops_strerror(0) == b"success"
+    # workspace sizing is pure host arithmetic: n rows x ceil(n/64) 64-bit words
+    assert lib.b200_nms_workspace_bytes(6000) == 6000 * 94 * 8
+    assert lib.b200_nms_workspace_bytes(0) > 0
+    assert lib.b200_nms_workspace_bytes(64) == 64 * 8
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "detectron")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), fn
+                assert "liboracle" not in text and "oracle/_ref" not in text, fn

@@ -1,0 +1,244 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): the sm_100a kernels, called through the
+C ABI via the reference-shaped Python surface, against
+  (1) the CPU oracle (oracle/roi_ops_oracle.c) on the same seeded inputs,
+  (2) the reference's own CUDA kernels (oracle/_ref) when those .so files travelled along,
+  (3) the committed golden outputs of those kernels (tests/golden/*.npz),
+and, at BASELINE.json's full sizes, through size-independent properties.
+
+Tolerances: RoIAlign/legacy/crop forward, RoIPool fwd+bwd and NMS keep indices are BIT-EXACT
+(integer / identically-rounded fp32 work).  Gradients that the reference accumulates with fp32
+atomics are compared with |a-b| <= 1e-5 + 1e-5*|b| (north_star's 1e-5 fp32; summation order is
+undefined in the reference itself).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from detectron.pytorch_b200 import synthetic as S
+from detectron.pytorch_b200.model.nms.nms_gpu import nms_gpu
+from detectron.pytorch_b200.model.nms.nms_wrapper import nms as nms_wrapper
+from detectron.pytorch_b200.model.roi_align.functions.roi_align import RoIAlignFunction as LegacyRoIAlignFunction
+from detectron.pytorch_b200.model.roi_crop.functions.roi_crop import RoICropFunction
+from detectron.pytorch_b200.model.roi_pooling.functions.roi_pool import RoIPoolFunction
+from detectron.pytorch_b200.modeling.roi_xfrom.roi_align.functions.roi_align import RoIAlignFunction
+from detectron.pytorch_b200.modeling.roi_xfrom.roi_align.modules.roi_align import RoIAlignAvg, RoIAlignMax
+from oracle import cpu as O
+from oracle import gpu_ref as G
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+GRAD_TOL = dict(rtol=1e-5, atol=1e-5)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def run_fwd_bwd(fn, f, r, dy):
+    F = dev(f).requires_grad_(True)
+    out = fn(F, dev(r))
+    out.backward(dev(dy))
+    return out.detach().cpu().numpy(), F.grad.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------- RoIAlign
+@pytest.mark.parametrize("name", sorted(cases.ROI_CASES))
+def test_roi_align_vs_oracle(name):
+    c, f, r, dy = cases.roi_case(name)
+    P, s, sr = c["P"], c["scale"], c["sr"]
+    out, dx = run_fwd_bwd(RoIAlignFunction(P, P, s, sr), f, r, dy)
+    assert np.array_equal(out, O.roi_align_forward(f, r, P, P, s, sr))
+    np.testing.assert_allclose(dx, O.roi_align_backward(dy, r, c["shape"], P, P, s, sr, acc64=True), **GRAD_TOL)
+
+
+@pytest.mark.parametrize("name", sorted(cases.ROI_CASES))
+def test_roi_align_vs_reference_kernel(name):
+    if not G.available():
+        pytest.skip("oracle/_ref not built")
+    c, f, r, dy = cases.roi_case(name)
+    P, s, sr = c["P"], c["scale"], c["sr"]
+    out, dx = run_fwd_bwd(RoIAlignFunction(P, P, s, sr), f, r, dy)
+    ref_out = G.roi_align_forward(dev(f), dev(r), P, P, s, sr).cpu().numpy()
+    ref_dx = G.roi_align_backward(dev(dy), dev(r), c["shape"], P, P, s, sr).cpu().numpy()
+    assert np.array_equal(out, ref_out)
+    np.testing.assert_allclose(dx, ref_dx, **GRAD_TOL)
+
+
+@pytest.mark.parametrize("name", sorted(cases.ROI_CASES))
+def test_roi_align_vs_golden(name):
+    path = os.path.join(GOLDEN, "roi_align_xfrom_%s.npz" % name)
+    if not os.path.exists(path):
+        pytest.skip("golden not generated")
+    g = np.load(path)
+    c, f, r, dy = cases.roi_case(name)
+    out, dx = run_fwd_bwd(RoIAlignFunction(c["P"], c["P"], c["scale"], c["sr"]), f, r, dy)
+    assert np.array_equal(out, g["out"])
+    np.testing.assert_allclose(dx, g["dx"], **GRAD_TOL)
+
+
+def test_roi_align_baseline_cfg1_and_cfg2_full_size():
+    """BASELINE.json configs 1 and 2 at full size: forward bit-exact vs the oracle; backward within
+    1e-5; plus size-independent properties (adjointness, linearity, dX support)."""
+    for cfg in (S.CFG1, S.CFG2):
+        P, s, sr = cfg["pooled"], cfg["scale"], cfg["sampling_ratio"]
+        f = S.make_features(cfg["shape"]); r = S.make_rois(cfg["rois"], cfg["shape"], s)
+        dy = np.random.RandomState(1).standard_normal((cfg["rois"], cfg["shape"][1], P, P)).astype(np.float32)
+        out, dx = run_fwd_bwd(RoIAlignFunction(P, P, s, sr), f, r, dy)
+        assert np.array_equal(out, O.roi_align_forward(f, r, P, P, s, sr))
+        ref_dx = O.roi_align_backward(dy, r, cfg["shape"], P, P, s, sr, acc64=True)
+        np.testing.assert_allclose(dx, ref_dx, **GRAD_TOL)
+        # <out, dy> == <dx, f>
+        lhs = float(np.sum(out.astype(np.float64) * dy)); rhs = float(np.sum(dx.astype(np.float64) * f))
+        assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+        # cells no tap touches get exactly zero gradient
+        assert np.count_nonzero(np.abs(dx).sum(axis=(0, 1))) <= O.roi_align_touched_cells(r, cfg["shape"][0], cfg["shape"][2],
+                                                                                            cfg["shape"][3], P, P, s, sr)
+        if G.available():
+            assert np.array_equal(out, G.roi_align_forward(dev(f), dev(r), P, P, s, sr).cpu().numpy())
+
+
+def test_roi_align_forward_linearity_and_determinism():
+    cfg = S.CFG2
+    P, s, sr = cfg["pooled"], cfg["scale"], cfg["sampling_ratio"]
+    F1 = dev(S.make_features(cfg["shape"], seed=3)); F2 = dev(S.make_features(cfg["shape"], seed=4))
+    R = dev(S.make_rois(cfg["rois"], cfg["shape"], s, seed=5))
+    fn = RoIAlignFunction(P, P, s, sr)
+    a, b, ab = fn(F1, R), fn(F2, R), fn(F1 + F2, R)
+    torch.testing.assert_close(ab, a + b, rtol=1e-5, atol=1e-5)
+    assert torch.equal(fn(F1, R), a)                       # run-to-run bit-identical
+    assert torch.equal(fn(2 * F1, R), 2 * a)               # scaling by a power of two is exact
+
+
+def test_roi_align_empty_and_degenerate():
+    F = dev(S.make_features((1, 4, 10, 12)))
+    fn = RoIAlignFunction(7, 7, 0.25, 2)
+    out = fn(F, torch.zeros((0, 5), device="cuda"))
+    assert tuple(out.shape) == (0, 4, 7, 7)
+    Fg = F.clone().requires_grad_(True)
+    o = fn(Fg, torch.zeros((0, 5), device="cuda"))
+    o.sum().backward()
+    assert torch.count_nonzero(Fg.grad) == 0              # dX fully defined (zeros) with no RoIs
+    with pytest.raises(NotImplementedError):
+        fn(F.cpu(), torch.zeros((1, 5)))
+
+
+def test_roi_align_avg_max_modules():
+    c, f, r, _ = cases.roi_case("cfg1_small")
+    base = O.roi_align_forward(f, r, 8, 8, c["scale"], 2)
+    avg = RoIAlignAvg(7, 7, c["scale"], 2)(dev(f), dev(r)).cpu()
+    mx = RoIAlignMax(7, 7, c["scale"], 2)(dev(f), dev(r)).cpu()
+    tb = torch.from_numpy(base)
+    assert torch.equal(mx, torch.nn.functional.max_pool2d(tb, 2, 1))
+    torch.testing.assert_close(avg, torch.nn.functional.avg_pool2d(tb, 2, 1), rtol=1e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------- legacy RoIAlign, RoIPool
+@pytest.mark.parametrize("name", sorted(cases.ROI_CASES))
+def test_legacy_and_pool_vs_oracle_and_reference(name):
+    c, f, r, dy = cases.roi_case(name)
+    P, s = c["P"], c["scale"]
+    out, dx = run_fwd_bwd(LegacyRoIAlignFunction(P, P, s), f, r, dy)
+    assert np.array_equal(out, O.roi_align_legacy_forward(f, r, P, P, s))
+    np.testing.assert_allclose(dx, O.roi_align_legacy_backward(dy, r, c["shape"], P, P, s, acc64=True), **GRAD_TOL)
+    fn = RoIPoolFunction(P, P, s)
+    pout, pdx = run_fwd_bwd(fn, f, r, dy)
+    o_out, o_arg = O.roi_pool_forward(f, r, P, P, s)
+    assert np.array_equal(pout, o_out) and np.array_equal(fn.argmax.cpu().numpy(), o_arg)
+    assert np.array_equal(pdx, O.roi_pool_backward(dy, o_arg, r, c["shape"], P, P, s))
+    if G.available():
+        assert np.array_equal(out, G.roi_align_legacy_forward(dev(f), dev(r), P, P, s).cpu().numpy())
+        np.testing.assert_allclose(dx, G.roi_align_legacy_backward(dev(dy), dev(r), c["shape"], P, P, s).cpu().numpy(), **GRAD_TOL)
+        g_out, g_arg = G.roi_pool_forward(dev(f), dev(r), P, P, s)
+        assert np.array_equal(pout, g_out.cpu().numpy()) and np.array_equal(o_arg, g_arg.cpu().numpy())
+        assert np.array_equal(pdx, G.roi_pool_backward(dev(dy), g_arg, dev(r), c["shape"], P, P, s).cpu().numpy())
+    path = os.path.join(GOLDEN, "legacy_pool_%s.npz" % name)
+    if os.path.exists(path):
+        g = np.load(path)
+        assert np.array_equal(out, g["legacy_out"]) and np.array_equal(pout, g["pool_out"])
+        assert np.array_equal(pdx, g["pool_dx"])
+
+
+def test_pool_many_rois_chunked_list():
+    """> 512 overlapping RoIs on one tile exercises the chunked RoI list of the backward."""
+    shape = (1, 3, 20, 24)
+    f = S.make_features(shape)
+    r = S.make_rois(1400, shape, 0.25, seed=2, min_size=40, max_size=96)
+    fn = RoIPoolFunction(3, 3, 0.25)
+    dy = np.random.RandomState(1).standard_normal((1400, 3, 3, 3)).astype(np.float32)
+    pout, pdx = run_fwd_bwd(fn, f, r, dy)
+    o_out, o_arg = O.roi_pool_forward(f, r, 3, 3, 0.25)
+    assert np.array_equal(pout, o_out)
+    assert np.array_equal(pdx, O.roi_pool_backward(dy, o_arg, r, shape, 3, 3, 0.25))
+
+
+# ---------------------------------------------------------------------------------------- RoICrop
+def test_roi_crop_vs_oracle_reference_golden():
+    img, grid, go = cases.crop_case()
+    I = dev(img).requires_grad_(True); Gd = dev(grid).requires_grad_(True)
+    out = RoICropFunction()(I, Gd)
+    out.backward(dev(go))
+    o = out.detach().cpu().numpy(); gi = I.grad.cpu().numpy()
+    assert np.array_equal(o, O.roi_crop_forward(img, grid))
+    np.testing.assert_allclose(gi, O.roi_crop_backward(go, grid, img.shape, acc64=True), **GRAD_TOL)
+    assert torch.count_nonzero(Gd.grad) == 0
+    if G.available():
+        assert np.array_equal(o, G.roi_crop_forward(dev(img), dev(grid)).cpu().numpy())
+        rgi, rgg = G.roi_crop_backward(dev(img), dev(grid), dev(go))
+        np.testing.assert_allclose(gi, rgi.cpu().numpy(), **GRAD_TOL)
+        assert torch.count_nonzero(rgg) == 0
+    path = os.path.join(GOLDEN, "roi_crop.npz")
+    if os.path.exists(path):
+        assert np.array_equal(o, np.load(path)["out"])
+
+
+# -------------------------------------------------------------------------------------------- NMS
+@pytest.mark.parametrize("n", cases.NMS_SIZES)
+def test_nms_bit_exact(n):
+    b = cases.nms_case(n)
+    keep = nms_gpu(dev(b), 0.7)
+    assert keep.dtype == torch.int32 and keep.dim() == 2 and keep.size(1) == 1 and keep.is_cuda
+    k = keep.cpu().numpy().reshape(-1)
+    assert np.array_equal(k, O.nms_cuda(b, 0.7))
+    if G.available():
+        assert np.array_equal(k, G.nms_gpu(dev(b), 0.7).cpu().numpy().reshape(-1))
+    path = os.path.join(GOLDEN, "nms.npz")
+    if os.path.exists(path):
+        assert np.array_equal(k, np.load(path)["keep_%d" % n])
+
+
+@pytest.mark.parametrize("thresh", [0.3, 0.5, 0.9])
+def test_nms_thresholds_and_properties(thresh):
+    b = cases.nms_case(3000, seed=7)
+    k = nms_gpu(dev(b), thresh).cpu().numpy().reshape(-1)
+    assert np.array_equal(k, O.nms_cuda(b, thresh))
+    assert k[0] == 0 and np.all(np.diff(k) > 0)            # sorted, best box always kept
+    k2 = nms_gpu(dev(b[k]), thresh).cpu().numpy().reshape(-1)
+    assert np.array_equal(k2, np.arange(len(k)))            # idempotent
+
+
+def test_nms_edge_cases():
+    assert nms_wrapper(torch.zeros((0, 5), device="cuda"), 0.7) == []
+    one = dev(np.array([[0, 0, 10, 10, 0.5]], np.float32))
+    assert nms_gpu(one, 0.7).cpu().numpy().tolist() == [[0]]
+    dup = dev(np.tile(np.array([[5, 5, 50, 60, 0.9]], np.float32), (130, 1)))
+    assert nms_gpu(dup, 0.7).cpu().numpy().tolist() == [[0]]          # all duplicates collapse
+    # degenerate boxes: zero-area union -> 0/0 = NaN -> never suppressed (reference semantics)
+    deg = np.array([[10, 10, 9, 9, 0.9], [10, 10, 9, 9, 0.8], [0, 0, 5, 5, 0.7]], np.float32)
+    assert np.array_equal(nms_gpu(dev(deg), 0.7).cpu().numpy().reshape(-1), O.nms_cuda(deg, 0.7))
+    # extra columns are ignored, like boxes_dim in the reference
+    b6 = np.concatenate([cases.nms_case(500), np.ones((500, 1), np.float32)], axis=1)
+    assert np.array_equal(nms_gpu(dev(b6), 0.7).cpu().numpy().reshape(-1), O.nms_cuda(b6[:, :5], 0.7))
+
+
+def test_ops_honour_current_stream_and_noncontiguous_input():
+    c, f, r, _ = cases.roi_case("cfg1_small")
+    F = dev(np.transpose(f, (0, 1, 3, 2))).transpose(2, 3)   # non-contiguous view of the same values
+    assert not F.is_contiguous()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out = RoIAlignFunction(7, 7, c["scale"], 2)(F, dev(r))
+    s.synchronize()
+    assert np.array_equal(out.cpu().numpy(), O.roi_align_forward(f, r, 7, 7, c["scale"], 2))

@@ -1,0 +1,70 @@
+"""CPU-only: the reference-shaped Python surface (names, constructor signatures, call protocol,
+error behaviour) -- SURVEY.md 8(b)."""
+import inspect
+import sys
+
+import pytest
+import torch
+
+
+def test_reference_import_paths_and_signatures():
+    import detectron.pytorch_b200 as pkg
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("model", "modeling")}
+    try:
+        pkg.install_reference_aliases()
+        from modeling.roi_xfrom.roi_align.functions.roi_align import RoIAlignFunction          # model_builder.py:13
+        from modeling.roi_xfrom.roi_align.modules.roi_align import RoIAlign, RoIAlignAvg, RoIAlignMax
+        from model.roi_align.functions.roi_align import RoIAlignFunction as LegacyFn
+        from model.roi_align.modules.roi_align import RoIAlignAvg as LegacyAvg
+        from model.roi_pooling.functions.roi_pool import RoIPoolFunction                       # model_builder.py:11
+        from model.roi_pooling.modules.roi_pool import _RoIPooling
+        from model.roi_crop.functions.roi_crop import RoICropFunction                          # model_builder.py:12
+        from model.roi_crop.modules.roi_crop import _RoICrop
+        from model.nms.nms_gpu import nms_gpu
+        from model.nms.nms_wrapper import nms
+        assert list(inspect.signature(RoIAlignFunction.__init__).parameters)[1:] == ["aligned_height", "aligned_width", "spatial_scale", "sampling_ratio"]
+        assert list(inspect.signature(LegacyFn.__init__).parameters)[1:] == ["aligned_height", "aligned_width", "spatial_scale"]
+        assert list(inspect.signature(RoIPoolFunction.__init__).parameters)[1:] == ["pooled_height", "pooled_width", "spatial_scale"]
+        assert list(inspect.signature(nms_gpu).parameters) == ["dets", "thresh"]
+        assert list(inspect.signature(nms).parameters) == ["dets", "thresh", "force_cpu"]
+        f = RoIAlignFunction(7.0, 7, "0.25" and 0.25, 2)
+        assert (f.aligned_height, f.aligned_width, f.spatial_scale, f.sampling_ratio) == (7, 7, 0.25, 2)
+        assert f.rois is None and f.feature_size is None
+        for m in (RoIAlign(7, 7, 0.25, 2), RoIAlignAvg(7, 7, 0.25, 2), RoIAlignMax(7, 7, 0.25, 2), LegacyAvg(7, 7, 0.25),
+                  _RoIPooling(7, 7, 0.25), _RoICrop()):
+            assert isinstance(m, torch.nn.Module)
+        assert RoICropFunction().input1 is None
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("model", "modeling")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_cpu_tensors_are_rejected_like_the_reference():
+    from detectron.pytorch_b200.modeling.roi_xfrom.roi_align.functions.roi_align import RoIAlignFunction
+    from detectron.pytorch_b200.model.roi_align.functions.roi_align import RoIAlignFunction as LegacyFn
+    from detectron.pytorch_b200.model.roi_pooling.functions.roi_pool import RoIPoolFunction
+    from detectron.pytorch_b200.model.roi_crop.functions.roi_crop import RoICropFunction
+    from detectron.pytorch_b200.model.nms.nms_wrapper import nms
+    feats, rois = torch.zeros(1, 2, 8, 8), torch.zeros(3, 5)
+    with pytest.raises(NotImplementedError):        # functions/roi_align.py:28-29
+        RoIAlignFunction(7, 7, 0.25, 2)(feats, rois)
+    with pytest.raises(NotImplementedError):
+        LegacyFn(7, 7, 0.25)(feats, rois)
+    with pytest.raises(NotImplementedError):
+        RoIPoolFunction(7, 7, 0.25)(feats, rois)
+    with pytest.raises(NotImplementedError):
+        RoICropFunction()(feats, torch.zeros(1, 7, 7, 2))
+    assert nms(torch.zeros(0, 5), 0.7) == []        # nms_wrapper.py:13-14, before any device work
+    f = RoIAlignFunction(7, 7, 0.25, 2)
+    with pytest.raises(AssertionError):             # functions/roi_align.py:35 `assert ... grad_output.is_cuda`
+        f.backward(torch.zeros(3, 2, 7, 7))
+
+
+def test_no_silent_fallback_when_library_missing(monkeypatch, tmp_path):
+    from detectron.pytorch_b200 import _lib, build
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(build, "LIB_PATH", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(build, "find_nvcc", lambda: None)
+    with pytest.raises(ImportError):
+        _lib.load()
