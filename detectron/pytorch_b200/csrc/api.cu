@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" boundary of libb200_roi_ops.so (see include/b200_roi_ops.h).
 // Argument validation + dispatch only; kernels live in the per-op translation units.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace b200 {
 unsigned long long g_launch_count = 0;
@@ -14,6 +15,22 @@ int roi_pool_backward(const float*, float, int, int, int, int, int, int, int, co
 int roi_crop_forward(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int roi_crop_backward(const float*, const float*, int, int, int, int, int, int, int, float*, float*, cudaStream_t);
 size_t nms_workspace_bytes(int);
+size_t roi_align_tiled_workspace_bytes(int, int, int, int);
+int roi_align_forward_tiled(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, void*, size_t, cudaStream_t);
+
+// B200_ROI_ALIGN_PATH=generic|tiled|auto (default auto) -- test/benchmark override of the forward dispatch
+static int forward_path_mode() {
+    const char* e = getenv("B200_ROI_ALIGN_PATH");      // read per call: tests flip it at run time
+    if (e && e[0] == 'g') return 1;
+    if (e && e[0] == 't') return 2;
+    return 0;
+}
+
+static bool tiled_pays_off(int R, int C, int H, int W, int PH, int PW) {
+    // the tiled path stages whole tiles; it wins once the gather volume dwarfs the map itself
+    const long long taps = (long long)R * C * PH * PW;
+    return taps >= (1LL << 18) && (long long)H * W >= 1024;
+}
 int nms(const float*, int, int, float, int*, int*, void*, size_t, cudaStream_t);
 
 static inline bool bad_dims(int N, int R, int H, int W, int C, int PH, int PW) {
@@ -37,11 +54,48 @@ const char* b200_roi_ops_strerror(int status) {
 
 unsigned long long b200_roi_ops_launch_count(void) { return g_launch_count; }
 
+size_t b200_roi_align_workspace_bytes(int num_rois, int aligned_height, int aligned_width, int sampling_ratio) {
+    if (forward_path_mode() == 1) return 0;
+    return roi_align_tiled_workspace_bytes(num_rois, aligned_height, aligned_width, sampling_ratio);
+}
+
+int b200_roi_align_forward_ws(const float* bottom_data, float spatial_scale, int batch_size, int num_rois, int height,
+                              int width, int channels, int aligned_height, int aligned_width, int sampling_ratio,
+                              const float* bottom_rois, float* top_data, void* workspace, size_t workspace_bytes,
+                              b200_stream_t stream) {
+    if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
+    if (num_rois > 0 && channels > 0 && (!bottom_data || !bottom_rois || !top_data)) return B200_ROI_EINVAL;
+    const int mode = forward_path_mode();
+    if (mode != 1 && workspace != nullptr &&
+        (mode == 2 || tiled_pays_off(num_rois, channels, height, width, aligned_height, aligned_width))) {
+        const int rc = roi_align_forward_tiled(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
+                                               aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data,
+                                               workspace, workspace_bytes, (cudaStream_t)stream);
+        if (rc != 1000) return rc;
+    }
+    return roi_align_forward_generic(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
+                                     aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data,
+                                     (cudaStream_t)stream);
+}
+
 int b200_roi_align_forward(const float* bottom_data, float spatial_scale, int batch_size, int num_rois, int height,
                            int width, int channels, int aligned_height, int aligned_width, int sampling_ratio,
                            const float* bottom_rois, float* top_data, b200_stream_t stream) {
     if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
     if (num_rois > 0 && channels > 0 && (!bottom_data || !bottom_rois || !top_data)) return B200_ROI_EINVAL;
+    const int mode = forward_path_mode();
+    const size_t wsb = (mode == 1) ? 0 : roi_align_tiled_workspace_bytes(num_rois, aligned_height, aligned_width, sampling_ratio);
+    if (wsb > 0 && (mode == 2 || tiled_pays_off(num_rois, channels, height, width, aligned_height, aligned_width))) {
+        void* ws = nullptr;
+        if (cudaMallocAsync(&ws, wsb, (cudaStream_t)stream) == cudaSuccess) {
+            const int rc = b200_roi_align_forward_ws(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
+                                                     aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data, ws,
+                                                     wsb, stream);
+            cudaFreeAsync(ws, (cudaStream_t)stream);
+            return rc;
+        }
+        (void)cudaGetLastError();
+    }
     return roi_align_forward_generic(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
                                      aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data,
                                      (cudaStream_t)stream);

@@ -1,0 +1,337 @@
+// roi_align_tiled.cu -- Caffe2-exact RoIAlign FORWARD, feature-map-stationary ("tiled") fast path.
+//
+// Why: the RoI-centric gather (reference kernel, and our generic path) is bound by L1/L2
+// transactions, not HBM: every 4-byte tap costs a 32-byte sector slot (ncu, profiles/r01a:
+// 69.9 M L1 sectors for 3.29 M warp loads, l1tex 91 % busy, DRAM 6 %).  Here every feature byte
+// crosses L2 -> SM once (+ a 1-cell halo): a CTA owns a spatial tile x 32 channels, stages it into
+// shared memory TRANSPOSED to [cell][channel] (coalesced 128-byte row loads, conflict-free 128-bit
+// shared stores), and then serves every bilinear SAMPLE whose top-left tap lies in the tile with
+// conflict-free 128-bit shared loads: lane = (bin of a 4-bin group, 4-channel group), so one
+// LDS.128 fetches one tap for 4 bins x 32 channels.
+//
+// Work assignment is per sample, not per bin: a sample's 4 taps span 2x2 cells, so a 1-cell halo is
+// enough for ANY RoI size.  Bins whose samples fall into different tiles ("split" bins, ~1 in 5 at
+// BASELINE cfg2) are finished with red.global.add of the partial means; the prepass zero-fills
+// exactly those output elements.  Everything else is written once with plain stores, staged through
+// shared memory so that the lanes of a store are consecutive bins of one channel.
+//
+// Numerics: each lane evaluates the reference's rounding recipe in the reference's order
+// (oracle/roi_ops_oracle.c), so unsplit bins are bit-identical to the reference kernel; split bins
+// differ by the association of <= 4 partial sums (~1 ulp).
+//
+// Semantics: lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu (reference) :16-63, :65-121.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kTX = 32;                 // tile width in cells (one warp-wide row load)
+constexpr int kCG = 32;                 // channels per CTA
+constexpr int kCellWords = kCG + 4;     // 36 words = 144 B per cell: padding makes the transposing STS.128 conflict-free
+constexpr int kTiledThreads = 256;
+constexpr int kWarps = kTiledThreads / 32;
+constexpr int kAxisMax = 32;            // P * sampling_ratio per axis supported by the fast path
+constexpr int kListMax = 512;           // RoIs cached per pass of a CTA
+constexpr int kStageBins = 8;           // bins of one output row staged per flush
+constexpr int kStageWords = kStageBins + 1;
+
+struct __align__(16) AxisEntry {        // one bilinear sample along one axis (channel independent)
+    int   low;                          // low cell (clamped into the map even when invalid)
+    int   valid;                        // 0 <=> the reference's "outside the map" early-out
+    float l, h;                         // weights of the high / low cell
+};
+
+struct __align__(16) RoiHeader {
+    int batch;                          // -1 if the batch index is out of range
+    int y_min, y_max, x_min, x_max;     // range of `low` over the samples of each axis
+    int pad0, pad1, pad2;
+};
+
+struct TiledPlan {
+    int ny, nx;                         // samples per axis = P * sr
+    int core_h, core_w;                 // tile core (= tile - 1-cell halo)
+    int tile_h;                         // rows staged per tile
+    int tiles_y, tiles_x;
+    size_t smem_bytes;
+    size_t ws_hdr_off, ws_ytab_off, ws_xtab_off, ws_bytes;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// smem carve-up (bytes): [tile][roi list][per-warp axis tables][per-warp output staging][misc]
+__host__ __device__ inline size_t tiled_smem_bytes(int tile_h) {
+    return (size_t)kTX * tile_h * kCellWords * 4 + kListMax * 2 + (size_t)kWarps * 2 * kAxisMax * 16 +
+           (size_t)kWarps * kCG * kStageWords * 4 + 64;
+}
+
+bool roi_align_tiled_plan(int N, int R, int H, int W, int C, int PH, int PW, int sr, TiledPlan* p) {
+    if (sr < 1 || sr > 4 || PH * sr > kAxisMax || PW * sr > kAxisMax) return false;
+    if (R <= 0 || R > 65535 || C <= 0 || N <= 0) return false;
+    if ((long long)R * C * PH * PW >= (1LL << 31) || (long long)N * C * H * W >= (1LL << 31)) return false;
+    p->ny = PH * sr; p->nx = PW * sr;
+    // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
+    const size_t budget = 113 * 1024;
+    int th = 64;
+    while (th > 4 && tiled_smem_bytes(th) > budget) --th;
+    if (th <= 4) return false;
+    // do not stage rows a small map does not have; balance the rows over the tiles
+    int core_h = th - 1;
+    int tiles_y = (H + core_h - 1) / core_h;
+    core_h = (H + tiles_y - 1) / tiles_y;
+    p->core_h = core_h; p->tile_h = core_h + 1; p->tiles_y = tiles_y;
+    p->core_w = kTX - 1; p->tiles_x = (W + p->core_w - 1) / p->core_w;
+    p->smem_bytes = tiled_smem_bytes(p->tile_h);
+    p->ws_hdr_off = 0;
+    p->ws_ytab_off = align_up((size_t)R * sizeof(RoiHeader), 256);
+    p->ws_xtab_off = align_up(p->ws_ytab_off + (size_t)R * p->ny * sizeof(AxisEntry), 256);
+    p->ws_bytes = align_up(p->ws_xtab_off + (size_t)R * p->nx * sizeof(AxisEntry), 256);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prepass: per-RoI axis tables + header, and zero-fill of the outputs that will be accumulated
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int C, int H, int W, int PH, int PW, int sr,
+                     int ny, int nx, int core_h, int core_w, RoiHeader* __restrict__ hdr,
+                     AxisEntry* __restrict__ ytab, AxisEntry* __restrict__ xtab, float* __restrict__ out) {
+    __shared__ int s_ty[kAxisMax], s_tx[kAxisMax];
+    __shared__ int s_lo[2 * kAxisMax];
+    const int r = blockIdx.x;
+    const XfromRoi g = xfrom_roi(rois + 5 * (size_t)r, scale, PH, PW, sr);
+    const int t = threadIdx.x;
+    if (t < ny + nx) {
+        const bool isy = t < ny;
+        const int s = isy ? t : t - ny;
+        const int gsz = isy ? g.grid_h : g.grid_w;          // == sr on this path
+        const AxisTap a = isy ? xfrom_axis(xfrom_coord(g.start_h, g.bin_h, s / gsz, s % gsz, gsz), H)
+                              : xfrom_axis(xfrom_coord(g.start_w, g.bin_w, s / gsz, s % gsz, gsz), W);
+        AxisEntry e; e.low = a.low; e.valid = a.valid ? 1 : 0; e.l = a.l; e.h = a.h;
+        if (isy) { ytab[(size_t)r * ny + s] = e; s_ty[s] = a.low / core_h; }
+        else     { xtab[(size_t)r * nx + s] = e; s_tx[s] = a.low / core_w; }
+        s_lo[t] = a.low;
+    }
+    __syncthreads();
+    const bool batch_ok = g.batch >= 0 && g.batch < N;
+    if (t == 0) {
+        RoiHeader h;
+        h.batch = batch_ok ? g.batch : -1;
+        h.y_min = s_lo[0]; h.y_max = s_lo[ny - 1]; h.x_min = s_lo[ny]; h.x_max = s_lo[ny + nx - 1];
+        h.pad0 = h.pad1 = h.pad2 = 0;
+        hdr[r] = h;
+    }
+    // zero the outputs that the main kernel accumulates into (split bins), or never visits (bad batch index)
+    const int bins = PH * PW;
+    for (int idx = t; idx < C * bins; idx += blockDim.x) {
+        const int bin = idx % bins, ph = bin / PW, pw = bin % PW;
+        bool split = !batch_ok;
+        for (int i = 1; i < sr; ++i) split |= (s_ty[ph * sr + i] != s_ty[ph * sr]) || (s_tx[pw * sr + i] != s_tx[pw * sr]);
+        if (split) out[(size_t)r * C * bins + idx] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+__global__ void __launch_bounds__(kTiledThreads, 2)
+roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restrict__ hdr,
+                    const AxisEntry* __restrict__ g_ytab, const AxisEntry* __restrict__ g_xtab,
+                    float* __restrict__ out, int N, int R, int C, int H, int W, int PH, int PW, int sr,
+                    int ny, int nx, int core_h, int core_w, int tile_h, int tiles_x) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* tile = reinterpret_cast<float*>(smem_raw);
+    unsigned short* list = reinterpret_cast<unsigned short*>(smem_raw + (size_t)kTX * tile_h * kCellWords * 4);
+    AxisEntry* wtab_all = reinterpret_cast<AxisEntry*>(reinterpret_cast<unsigned char*>(list) + kListMax * 2);
+    float* stage_all = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wtab_all) + (size_t)kWarps * 2 * kAxisMax * 16);
+    int* misc = reinterpret_cast<int*>(stage_all + kWarps * kCG * kStageWords);   // [0]=list count, [1]=next item, [2..9]=warp counts
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
+    const int y0 = ty * core_h, x0 = tx * core_w;
+    const int c0 = blockIdx.y * kCG;
+    const int n = blockIdx.z;
+    const int y_end = y0 + core_h, x_end = x0 + core_w;      // core = [y0, y_end) x [x0, x_end)
+    const int bins = PH * PW;
+    const float count = (float)(sr * sr);
+
+    AxisEntry* wy = wtab_all + warp * 2 * kAxisMax;
+    AxisEntry* wx = wy + kAxisMax;
+    float* stage = stage_all + warp * kCG * kStageWords;
+
+    bool staged = false;
+    for (int r_base = 0; r_base < R; ) {
+        // ---- (1) compact the RoIs of image n whose sample range meets this tile's core (ascending order)
+        if (tid == 0) { misc[0] = 0; misc[1] = 0; }
+        __syncthreads();
+        int r_next = r_base;
+        while (r_next < R) {
+            const int r = r_next + tid;
+            bool hit = false;
+            if (r < R) {
+                const RoiHeader h = hdr[r];
+                hit = (h.batch == n) && h.y_max >= y0 && h.y_min < y_end && h.x_max >= x0 && h.x_min < x_end;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) misc[2 + warp] = __popc(m);
+            __syncthreads();
+            const int base_cnt = misc[0];
+            int before = base_cnt, chunk = 0;
+#pragma unroll
+            for (int k = 0; k < kWarps; ++k) { const int wc = misc[2 + k]; if (k < warp) before += wc; chunk += wc; }
+            if (base_cnt + chunk > kListMax) { __syncthreads(); break; }
+            if (hit) list[before + __popc(m & ((1u << lane) - 1u))] = (unsigned short)r;
+            __syncthreads();
+            if (tid == 0) misc[0] = base_cnt + chunk;
+            __syncthreads();
+            r_next += kTiledThreads;
+        }
+        r_base = r_next;
+        const int n_list = misc[0];
+        if (n_list == 0) continue;                       // uniform
+
+        // ---- (2) stage the tile once: rows [y0, y0+tile_h) x cols [x0, x0+32) x channels [c0, c0+32), zero outside the map
+        if (!staged) {
+            const size_t plane = (size_t)H * W;
+            const float* src = bottom + ((size_t)n * C + c0) * plane;
+            const int x = x0 + lane;
+            const bool x_ok = x < W;
+            const int items = tile_h * (kCG / 4);        // (row, channel quad) per warp-wide item
+#pragma unroll 4
+            for (int it = warp; it < items; it += kWarps) {
+                const int row = it >> 3, q = it & 7;
+                const int y = y0 + row;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (x_ok && y < H) {
+                    const float* p = src + (size_t)(4 * q) * plane + (size_t)y * W + x;
+                    const int cleft = C - c0 - 4 * q;
+                    if (cleft > 0) v.x = __ldg(p);
+                    if (cleft > 1) v.y = __ldg(p + plane);
+                    if (cleft > 2) v.z = __ldg(p + 2 * plane);
+                    if (cleft > 3) v.w = __ldg(p + 3 * plane);
+                }
+                *reinterpret_cast<float4*>(tile + (size_t)(row * kTX + lane) * kCellWords + 4 * q) = v;
+            }
+            staged = true;
+        }
+        __syncthreads();
+
+        // ---- (3) warps pull RoIs; lane = (q: bin of the 4-bin group, i: 4-channel group)
+        const int q = lane >> 3, i = lane & 7;
+        for (;;) {
+            int item = 0;
+            if (lane == 0) item = atomicAdd(&misc[1], 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= n_list) break;
+            const int r = list[item];
+            __syncwarp();
+            if (lane < ny) wy[lane] = g_ytab[(size_t)r * ny + lane];
+            if (lane < nx) wx[lane] = g_xtab[(size_t)r * nx + lane];
+            __syncwarp();
+            // samples of this RoI that live in this tile: contiguous index ranges [sy0, sy1) x [sx0, sx1)
+            const bool in_y = lane < ny && wy[lane].low >= y0 && wy[lane].low < y_end;
+            const bool in_x = lane < nx && wx[lane].low >= x0 && wx[lane].low < x_end;
+            const unsigned my = __ballot_sync(0xffffffffu, in_y), mx = __ballot_sync(0xffffffffu, in_x);
+            if (my == 0u || mx == 0u) continue;
+            const int sy0 = __ffs(my) - 1, sy1 = 32 - __clz(my);
+            const int sx0 = __ffs(mx) - 1, sx1 = 32 - __clz(mx);
+            const int ph0 = sy0 / sr, ph1 = (sy1 - 1) / sr + 1;
+            const int pw0 = sx0 / sr, pw1 = (sx1 - 1) / sr + 1;
+            float* out_r = out + (size_t)r * C * bins;
+
+            for (int ph = ph0; ph < ph1; ++ph) {
+                const bool row_whole = (ph * sr >= sy0) && (ph * sr + sr <= sy1);
+                for (int pwb = pw0; pwb < pw1; pwb += kStageBins) {
+                    const int npw = min(kStageBins, pw1 - pwb);
+                    // -- compute: groups of 4 bins (quarter-warp q takes bin pwb + 4*j + q)
+                    for (int j = 0; j * 4 < npw; ++j) {
+                        const int pwl = 4 * j + q;
+                        const int pw = pwb + pwl;
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                        if (pwl < npw) {
+                            for (int iy = 0; iy < sr; ++iy) {
+                                const int s_y = ph * sr + iy;
+                                if (s_y < sy0 || s_y >= sy1) continue;
+                                const AxisEntry ey = wy[s_y];
+                                if (!ey.valid) continue;
+                                const int row_off = ((ey.low - y0) * kTX - x0) * kCellWords + 4 * i;
+                                for (int ix = 0; ix < sr; ++ix) {
+                                    const int s_x = pw * sr + ix;
+                                    if (s_x < sx0 || s_x >= sx1) continue;
+                                    const AxisEntry ex = wx[s_x];
+                                    if (!ex.valid) continue;
+                                    const float w1 = __fmul_rn(ey.h, ex.h), w2 = __fmul_rn(ey.h, ex.l);
+                                    const float w3 = __fmul_rn(ey.l, ex.h), w4 = __fmul_rn(ey.l, ex.l);
+                                    const float* p = tile + (row_off + ex.low * kCellWords);
+                                    const float4 v1 = lds128(p), v2 = lds128(p + kCellWords);
+                                    const float4 v3 = lds128(p + kTX * kCellWords), v4 = lds128(p + (kTX + 1) * kCellWords);
+                                    a0 = __fadd_rn(a0, __fmaf_rn(v4.x, w4, __fmaf_rn(v3.x, w3, __fmaf_rn(v1.x, w1, __fmul_rn(v2.x, w2)))));
+                                    a1 = __fadd_rn(a1, __fmaf_rn(v4.y, w4, __fmaf_rn(v3.y, w3, __fmaf_rn(v1.y, w1, __fmul_rn(v2.y, w2)))));
+                                    a2 = __fadd_rn(a2, __fmaf_rn(v4.z, w4, __fmaf_rn(v3.z, w3, __fmaf_rn(v1.z, w1, __fmul_rn(v2.z, w2)))));
+                                    a3 = __fadd_rn(a3, __fmaf_rn(v4.w, w4, __fmaf_rn(v3.w, w3, __fmaf_rn(v1.w, w1, __fmul_rn(v2.w, w2)))));
+                                }
+                            }
+                            float* st = stage + (4 * i) * kStageWords + pwl;       // [channel][bin]
+                            st[0] = __fdiv_rn(a0, count);
+                            st[kStageWords] = __fdiv_rn(a1, count);
+                            st[2 * kStageWords] = __fdiv_rn(a2, count);
+                            st[3 * kStageWords] = __fdiv_rn(a3, count);
+                        }
+                    }
+                    __syncwarp();
+                    // -- flush: lanes = (channel within a group of 4, bin): runs of consecutive bins per channel
+                    const int cs = lane >> 3, b = lane & 7;
+                    if (b < npw) {
+                        const int pw = pwb + b;
+                        const bool whole = row_whole && (pw * sr >= sx0) && (pw * sr + sr <= sx1);
+#pragma unroll
+                        for (int cb = 0; cb < kCG / 4; ++cb) {
+                            const int c = cb * 4 + cs;
+                            if (c0 + c < C) {
+                                const float v = stage[c * kStageWords + b];
+                                float* dst = out_r + (size_t)(c0 + c) * bins + ph * PW + pw;
+                                if (whole) *dst = v; else atomicAdd(dst, v);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();       // the list is rebuilt by the next pass
+    }
+}
+
+size_t roi_align_tiled_workspace_bytes(int R, int PH, int PW, int sr) {
+    TiledPlan p;
+    // H, W, C, N do not enter the workspace size
+    if (!roi_align_tiled_plan(1, R, 64, 64, 1, PH, PW, sr, &p)) return 0;
+    return p.ws_bytes;
+}
+
+// returns B200_ROI_OK when the fast path ran; 1000 when it does not apply (caller falls back)
+int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int H, int W, int C, int PH, int PW, int sr,
+                            const float* rois, float* top, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    TiledPlan p;
+    if (!roi_align_tiled_plan(N, R, H, W, C, PH, PW, sr, &p)) return 1000;
+    if (workspace == nullptr || workspace_bytes < p.ws_bytes) return 1000;
+    unsigned char* ws = (unsigned char*)workspace;
+    RoiHeader* hdr = (RoiHeader*)(ws + p.ws_hdr_off);
+    AxisEntry* ytab = (AxisEntry*)(ws + p.ws_ytab_off);
+    AxisEntry* xtab = (AxisEntry*)(ws + p.ws_xtab_off);
+    static bool attr_set[64] = {false};     // per device: the attribute lives in the device's context
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1000;
+    if (!attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(roi_align_tiled_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set[dev] = true;
+    }
+    roi_align_tiled_prep<<<R, 128, 0, stream>>>(rois, scale, N, C, H, W, PH, PW, sr, p.ny, p.nx, p.core_h, p.core_w, hdr, ytab, xtab, top);
+    dim3 grid(p.tiles_x * p.tiles_y, (C + kCG - 1) / kCG, N);
+    roi_align_tiled_fwd<<<grid, kTiledThreads, p.smem_bytes, stream>>>(bottom, hdr, ytab, xtab, top, N, R, C, H, W, PH, PW, sr,
+                                                                       p.ny, p.nx, p.core_h, p.core_w, p.tile_h, p.tiles_x);
+    return finish_launch(2);
+}
+
+}  // namespace b200

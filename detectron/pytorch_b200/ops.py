@@ -39,10 +39,14 @@ def roi_align_forward(features, rois, aligned_height, aligned_width, spatial_sca
     N, C, H, W = features.shape
     R = rois.size(0)
     out = torch.empty((R, C, aligned_height, aligned_width), dtype=torch.float32, device=features.device)
+    lib = _lib.load()
+    ws_bytes = int(lib.b200_roi_align_workspace_bytes(R, aligned_height, aligned_width, sampling_ratio))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=features.device) if ws_bytes else None   # caching allocator, stream-ordered
     with torch.cuda.device(features.device):
-        _lib.check(_lib.load().b200_roi_align_forward(features.data_ptr(), spatial_scale, N, R, H, W, C, aligned_height,
-                                                      aligned_width, sampling_ratio, rois.data_ptr(), out.data_ptr(), _stream()),
-                   "b200_roi_align_forward")
+        _lib.check(lib.b200_roi_align_forward_ws(features.data_ptr(), spatial_scale, N, R, H, W, C, aligned_height,
+                                                 aligned_width, sampling_ratio, rois.data_ptr(), out.data_ptr(),
+                                                 ws.data_ptr() if ws is not None else None, ws_bytes, _stream()),
+                   "b200_roi_align_forward_ws")
     return out
 
 

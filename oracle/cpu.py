@@ -43,6 +43,10 @@ def set_fused(fused):
     lib().oracle_set_fused(int(bool(fused)))
 
 
+def set_threads(n):
+    lib().oracle_set_threads(int(n))
+
+
 def max_threads():
     return int(lib().oracle_max_threads())
 

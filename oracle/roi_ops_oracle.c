@@ -32,6 +32,14 @@
 
 #define ORACLE_API __attribute__((visibility("default")))
 
+ORACLE_API void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORACLE_API int oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
