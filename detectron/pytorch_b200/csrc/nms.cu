@@ -120,6 +120,85 @@ nms_scan_kernel(const u64* __restrict__ mask, int n, int col_blocks, int* __rest
     if (tid == 0) *num_out = s_count;
 }
 
+// Pipelined scan (default): the greedy chain only ever needs, for block b, the 64 mask rows of block b.
+// Those do not depend on the scan state, so they are prefetched -- all 64 rows, kept or not -- two blocks
+// ahead with cp.async into a shared-memory ring; the critical path per block is then: wait, 64-step
+// shuffle resolve of the diagonal word, OR of the kept rows out of shared memory.  The mask is read
+// exactly once (upper triangle), and no global-memory latency sits on the dependency chain.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kScanThreads)
+nms_scan_pipelined_kernel(const u64* __restrict__ mask, int n, int col_blocks, int* __restrict__ keep_out, int* __restrict__ num_out) {
+    extern __shared__ u64 sm[];
+    u64* remv = sm;                                   // [col_blocks]
+    u64* ring = sm + ((col_blocks + 1) & ~1);         // [2][64][col_blocks]
+    __shared__ u64 s_kept;
+    __shared__ int s_count;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t buf_words = (size_t)kNmsTile * col_blocks;
+
+    auto prefetch = [&](int b) {                      // rows of block b, columns [b, col_blocks)
+        if (b < col_blocks) {
+            u64* dst = ring + (size_t)(b & 1) * buf_words;
+            const int w = col_blocks - b, rows = min(kNmsTile, n - b * kNmsTile);
+            for (int e = tid; e < rows * w; e += kScanThreads) {
+                const int k = e / w, j = b + (e - k * w);
+                cp_async8(dst + (size_t)k * col_blocks + j, mask + (size_t)(b * kNmsTile + k) * col_blocks + j);
+            }
+        }
+        cp_async_commit();
+    };
+
+    for (int j = tid; j < col_blocks; j += kScanThreads) remv[j] = 0;
+    if (tid == 0) s_count = 0;
+    prefetch(0);
+    prefetch(1);
+    for (int b = 0; b < col_blocks; ++b) {
+        cp_async_wait<1>();                           // block b's rows have landed (block b+1 may be in flight)
+        __syncthreads();
+        const u64* rows = ring + (size_t)(b & 1) * buf_words;
+        const int lim = min(kNmsTile, n - b * kNmsTile);
+        if (warp == 0) {
+            const u64 d_lo = (lane < lim) ? rows[(size_t)lane * col_blocks + b] : 0;
+            const u64 d_hi = (lane + 32 < lim) ? rows[(size_t)(lane + 32) * col_blocks + b] : 0;
+            u64 r = remv[b];
+            u64 kept = 0;
+#pragma unroll 16
+            for (int k = 0; k < kNmsTile; ++k) {
+                const u64 dk = __shfl_sync(0xffffffffu, (k < 32) ? d_lo : d_hi, k & 31);
+                if (k < lim && !((r >> k) & 1ULL)) { kept |= 1ULL << k; r |= dk; }
+            }
+            if (lane == 0) s_kept = kept;
+        }
+        __syncthreads();
+        const u64 kept = s_kept;
+        const int base = s_count;
+        if (tid < kNmsTile && ((kept >> tid) & 1ULL))
+            keep_out[base + __popcll(kept & ((1ULL << tid) - 1ULL))] = b * kNmsTile + tid;
+        const int kg = tid >> 7;                      // 8 row groups x 128 column words per pass
+        for (int j = b + 1 + (tid & 127); j < col_blocks; j += 128) {
+            u64 acc = 0;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const int k = kg + 8 * kk;
+                if ((kept >> k) & 1ULL) acc |= rows[(size_t)k * col_blocks + j];
+            }
+            if (acc) atomicOr(&remv[j], acc);
+        }
+        __syncthreads();                              // ring[b & 1] is free again; remv is complete for block b+1
+        if (tid == 0) s_count = base + __popcll(kept);
+        prefetch(b + 2);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    if (tid == 0) *num_out = s_count;
+}
+
 __global__ void nms_empty_kernel(int* num_out) { *num_out = 0; }
 
 size_t nms_workspace_bytes(int n) {
@@ -140,6 +219,14 @@ int nms(const float* boxes, int n, int dim, float thresh, int* keep_out, int* nu
     u64* mask = (u64*)workspace;
     dim3 grid(cb, cb);
     nms_mask_kernel<<<grid, kNmsTile, 0, stream>>>(boxes, n, dim, thresh, mask);
+    const size_t smem_pipe = sizeof(u64) * (((size_t)cb + 1) / 2 * 2 + 2 * (size_t)kNmsTile * cb);
+    if (smem_pipe <= 220 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(nms_scan_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
+        if (e != cudaSuccess) return (int)e;
+        nms_scan_pipelined_kernel<<<1, kScanThreads, smem_pipe, stream>>>(mask, n, cb, keep_out, num_out);
+        return finish_launch(2);
+    }
+    // very large inputs (> ~14k boxes): the ring does not fit; fall back to the unpipelined scan
     const size_t smem = sizeof(u64) * (size_t)cb;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -96,15 +96,17 @@ roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int C, 
                      AxisEntry* __restrict__ ytab, AxisEntry* __restrict__ xtab, float* __restrict__ out) {
     __shared__ int s_ty[kAxisMax], s_tx[kAxisMax];
     __shared__ int s_lo[2 * kAxisMax];
+    __shared__ unsigned short s_split[kAxisMax * kAxisMax];
+    __shared__ int s_nsplit;
     const int r = blockIdx.x;
     const XfromRoi g = xfrom_roi(rois + 5 * (size_t)r, scale, PH, PW, sr);
     const int t = threadIdx.x;
+    if (t == 0) s_nsplit = 0;
     if (t < ny + nx) {
         const bool isy = t < ny;
         const int s = isy ? t : t - ny;
-        const int gsz = isy ? g.grid_h : g.grid_w;          // == sr on this path
-        const AxisTap a = isy ? xfrom_axis(xfrom_coord(g.start_h, g.bin_h, s / gsz, s % gsz, gsz), H)
-                              : xfrom_axis(xfrom_coord(g.start_w, g.bin_w, s / gsz, s % gsz, gsz), W);
+        const AxisTap a = isy ? xfrom_axis(xfrom_coord(g.start_h, g.bin_h, s / sr, s % sr, sr), H)
+                              : xfrom_axis(xfrom_coord(g.start_w, g.bin_w, s / sr, s % sr, sr), W);
         AxisEntry e; e.low = a.low; e.valid = a.valid ? 1 : 0; e.l = a.l; e.h = a.h;
         if (isy) { ytab[(size_t)r * ny + s] = e; s_ty[s] = a.low / core_h; }
         else     { xtab[(size_t)r * nx + s] = e; s_tx[s] = a.low / core_w; }
@@ -119,13 +121,20 @@ roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int C, 
         h.pad0 = h.pad1 = h.pad2 = 0;
         hdr[r] = h;
     }
-    // zero the outputs that the main kernel accumulates into (split bins), or never visits (bad batch index)
+    // bins the main kernel accumulates into (their samples straddle tiles) or never visits (bad batch index)
     const int bins = PH * PW;
-    for (int idx = t; idx < C * bins; idx += blockDim.x) {
-        const int bin = idx % bins, ph = bin / PW, pw = bin % PW;
+    for (int bin = t; bin < bins; bin += blockDim.x) {
+        const int ph = bin / PW, pw = bin % PW;
         bool split = !batch_ok;
         for (int i = 1; i < sr; ++i) split |= (s_ty[ph * sr + i] != s_ty[ph * sr]) || (s_tx[pw * sr + i] != s_tx[pw * sr]);
-        if (split) out[(size_t)r * C * bins + idx] = 0.f;
+        if (split) s_split[atomicAdd(&s_nsplit, 1)] = (unsigned short)bin;
+    }
+    __syncthreads();
+    const int nsplit = s_nsplit;
+    float* out_r = out + (size_t)r * C * bins;
+    for (int idx = t; idx < C * nsplit; idx += blockDim.x) {
+        const int c = idx / nsplit, k = idx - c * nsplit;
+        out_r[(size_t)c * bins + s_split[k]] = 0.f;
     }
 }
 
@@ -134,10 +143,11 @@ roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int C, 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+template <int SR>
 __global__ void __launch_bounds__(kTiledThreads, 2)
 roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restrict__ hdr,
                     const AxisEntry* __restrict__ g_ytab, const AxisEntry* __restrict__ g_xtab,
-                    float* __restrict__ out, int N, int R, int C, int H, int W, int PH, int PW, int sr,
+                    float* __restrict__ out, int N, int R, int C, int H, int W, int PH, int PW,
                     int ny, int nx, int core_h, int core_w, int tile_h, int tiles_x) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);
@@ -153,7 +163,8 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restric
     const int n = blockIdx.z;
     const int y_end = y0 + core_h, x_end = x0 + core_w;      // core = [y0, y_end) x [x0, x_end)
     const int bins = PH * PW;
-    const float count = (float)(sr * sr);
+    constexpr float kCount = (float)(SR * SR);
+    constexpr unsigned kFull = (1u << SR) - 1u;
 
     AxisEntry* wy = wtab_all + warp * 2 * kAxisMax;
     AxisEntry* wx = wy + kAxisMax;
@@ -218,6 +229,7 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restric
 
         // ---- (3) warps pull RoIs; lane = (q: bin of the 4-bin group, i: 4-channel group)
         const int q = lane >> 3, i = lane & 7;
+        const int cs = lane >> 3, bb = lane & 7;          // flush mapping: (channel within a group of 4, bin of the staged 8)
         for (;;) {
             int item = 0;
             if (lane == 0) item = atomicAdd(&misc[1], 1);
@@ -228,74 +240,78 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restric
             if (lane < ny) wy[lane] = g_ytab[(size_t)r * ny + lane];
             if (lane < nx) wx[lane] = g_xtab[(size_t)r * nx + lane];
             __syncwarp();
-            // samples of this RoI that live in this tile: contiguous index ranges [sy0, sy1) x [sx0, sx1)
-            const bool in_y = lane < ny && wy[lane].low >= y0 && wy[lane].low < y_end;
-            const bool in_x = lane < nx && wx[lane].low >= x0 && wx[lane].low < x_end;
+            // samples of this RoI that live in this tile: contiguous index ranges (bit masks my / mx);
+            // uy / ux additionally drop the samples the reference skips (outside the map)
+            bool in_y = false, in_x = false, ok_y = false, ok_x = false;
+            if (lane < ny) { const AxisEntry e = wy[lane]; in_y = e.low >= y0 && e.low < y_end; ok_y = in_y && e.valid; }
+            if (lane < nx) { const AxisEntry e = wx[lane]; in_x = e.low >= x0 && e.low < x_end; ok_x = in_x && e.valid; }
             const unsigned my = __ballot_sync(0xffffffffu, in_y), mx = __ballot_sync(0xffffffffu, in_x);
+            const unsigned uy = __ballot_sync(0xffffffffu, ok_y), ux = __ballot_sync(0xffffffffu, ok_x);
             if (my == 0u || mx == 0u) continue;
-            const int sy0 = __ffs(my) - 1, sy1 = 32 - __clz(my);
-            const int sx0 = __ffs(mx) - 1, sx1 = 32 - __clz(mx);
-            const int ph0 = sy0 / sr, ph1 = (sy1 - 1) / sr + 1;
-            const int pw0 = sx0 / sr, pw1 = (sx1 - 1) / sr + 1;
-            float* out_r = out + (size_t)r * C * bins;
+            const int ph0 = (__ffs(my) - 1) / SR, ph1 = (31 - __clz(my)) / SR + 1;
+            const int pw0 = (__ffs(mx) - 1) / SR, pw1 = (31 - __clz(mx)) / SR + 1;
+            const int npw = pw1 - pw0, nb = (ph1 - ph0) * npw;
+            const unsigned div_m = 65536u / (unsigned)npw + 1u;          // b / npw == (b * div_m) >> 16 for b < 4096
+            float* out_r = out + (size_t)r * C * bins + (size_t)c0 * bins;
 
-            for (int ph = ph0; ph < ph1; ++ph) {
-                const bool row_whole = (ph * sr >= sy0) && (ph * sr + sr <= sy1);
-                for (int pwb = pw0; pwb < pw1; pwb += kStageBins) {
-                    const int npw = min(kStageBins, pw1 - pwb);
-                    // -- compute: groups of 4 bins (quarter-warp q takes bin pwb + 4*j + q)
-                    for (int j = 0; j * 4 < npw; ++j) {
-                        const int pwl = 4 * j + q;
-                        const int pw = pwb + pwl;
-                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                        if (pwl < npw) {
-                            for (int iy = 0; iy < sr; ++iy) {
-                                const int s_y = ph * sr + iy;
-                                if (s_y < sy0 || s_y >= sy1) continue;
-                                const AxisEntry ey = wy[s_y];
-                                if (!ey.valid) continue;
-                                const int row_off = ((ey.low - y0) * kTX - x0) * kCellWords + 4 * i;
-                                for (int ix = 0; ix < sr; ++ix) {
-                                    const int s_x = pw * sr + ix;
-                                    if (s_x < sx0 || s_x >= sx1) continue;
-                                    const AxisEntry ex = wx[s_x];
-                                    if (!ex.valid) continue;
-                                    const float w1 = __fmul_rn(ey.h, ex.h), w2 = __fmul_rn(ey.h, ex.l);
-                                    const float w3 = __fmul_rn(ey.l, ex.h), w4 = __fmul_rn(ey.l, ex.l);
-                                    const float* p = tile + (row_off + ex.low * kCellWords);
-                                    const float4 v1 = lds128(p), v2 = lds128(p + kCellWords);
-                                    const float4 v3 = lds128(p + kTX * kCellWords), v4 = lds128(p + (kTX + 1) * kCellWords);
-                                    a0 = __fadd_rn(a0, __fmaf_rn(v4.x, w4, __fmaf_rn(v3.x, w3, __fmaf_rn(v1.x, w1, __fmul_rn(v2.x, w2)))));
-                                    a1 = __fadd_rn(a1, __fmaf_rn(v4.y, w4, __fmaf_rn(v3.y, w3, __fmaf_rn(v1.y, w1, __fmul_rn(v2.y, w2)))));
-                                    a2 = __fadd_rn(a2, __fmaf_rn(v4.z, w4, __fmaf_rn(v3.z, w3, __fmaf_rn(v1.z, w1, __fmul_rn(v2.z, w2)))));
-                                    a3 = __fadd_rn(a3, __fmaf_rn(v4.w, w4, __fmaf_rn(v3.w, w3, __fmaf_rn(v1.w, w1, __fmul_rn(v2.w, w2)))));
-                                }
-                            }
-                            float* st = stage + (4 * i) * kStageWords + pwl;       // [channel][bin]
-                            st[0] = __fdiv_rn(a0, count);
-                            st[kStageWords] = __fdiv_rn(a1, count);
-                            st[2 * kStageWords] = __fdiv_rn(a2, count);
-                            st[3 * kStageWords] = __fdiv_rn(a3, count);
-                        }
-                    }
-                    __syncwarp();
-                    // -- flush: lanes = (channel within a group of 4, bin): runs of consecutive bins per channel
-                    const int cs = lane >> 3, b = lane & 7;
-                    if (b < npw) {
-                        const int pw = pwb + b;
-                        const bool whole = row_whole && (pw * sr >= sx0) && (pw * sr + sr <= sx1);
+            for (int kb = 0; kb < nb; kb += kStageBins) {
 #pragma unroll
-                        for (int cb = 0; cb < kCG / 4; ++cb) {
-                            const int c = cb * 4 + cs;
-                            if (c0 + c < C) {
-                                const float v = stage[c * kStageWords + b];
-                                float* dst = out_r + (size_t)(c0 + c) * bins + ph * PW + pw;
-                                if (whole) *dst = v; else atomicAdd(dst, v);
+                for (int jj = 0; jj < kStageBins / 4; ++jj) {
+                    const int b = kb + jj * 4 + q;
+                    if (b < nb) {
+                        const int dph = (int)(((unsigned)b * div_m) >> 16);
+                        const int ph = ph0 + dph, pw = pw0 + (b - dph * npw);
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                        for (int iy = 0; iy < SR; ++iy) {
+                            const int s_y = ph * SR + iy;
+                            if (!((uy >> s_y) & 1u)) continue;
+                            const AxisEntry ey = wy[s_y];
+                            const int row_off = ((ey.low - y0) * kTX - x0) * kCellWords + 4 * i;
+#pragma unroll
+                            for (int ix = 0; ix < SR; ++ix) {
+                                const int s_x = pw * SR + ix;
+                                if (!((ux >> s_x) & 1u)) continue;
+                                const AxisEntry ex = wx[s_x];
+                                const float w1 = __fmul_rn(ey.h, ex.h), w2 = __fmul_rn(ey.h, ex.l);
+                                const float w3 = __fmul_rn(ey.l, ex.h), w4 = __fmul_rn(ey.l, ex.l);
+                                const float* p = tile + (row_off + ex.low * kCellWords);
+                                const float4 v1 = lds128(p), v2 = lds128(p + kCellWords);
+                                const float4 v3 = lds128(p + kTX * kCellWords), v4 = lds128(p + (kTX + 1) * kCellWords);
+                                a0 = __fadd_rn(a0, __fmaf_rn(v4.x, w4, __fmaf_rn(v3.x, w3, __fmaf_rn(v1.x, w1, __fmul_rn(v2.x, w2)))));
+                                a1 = __fadd_rn(a1, __fmaf_rn(v4.y, w4, __fmaf_rn(v3.y, w3, __fmaf_rn(v1.y, w1, __fmul_rn(v2.y, w2)))));
+                                a2 = __fadd_rn(a2, __fmaf_rn(v4.z, w4, __fmaf_rn(v3.z, w3, __fmaf_rn(v1.z, w1, __fmul_rn(v2.z, w2)))));
+                                a3 = __fadd_rn(a3, __fmaf_rn(v4.w, w4, __fmaf_rn(v3.w, w3, __fmaf_rn(v1.w, w1, __fmul_rn(v2.w, w2)))));
                             }
                         }
+                        if (SR == 3) {        // count 9: a true division, like the reference's `output_val /= count`
+                            a0 = __fdiv_rn(a0, kCount); a1 = __fdiv_rn(a1, kCount); a2 = __fdiv_rn(a2, kCount); a3 = __fdiv_rn(a3, kCount);
+                        } else {              // count 1 / 4 / 16: multiplying by the reciprocal is exact
+                            a0 = __fmul_rn(a0, 1.f / kCount); a1 = __fmul_rn(a1, 1.f / kCount);
+                            a2 = __fmul_rn(a2, 1.f / kCount); a3 = __fmul_rn(a3, 1.f / kCount);
+                        }
+                        float* st = stage + (4 * i) * kStageWords + jj * 4 + q;       // [channel][bin]
+                        st[0] = a0; st[kStageWords] = a1; st[2 * kStageWords] = a2; st[3 * kStageWords] = a3;
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
+                // -- flush 8 bins x 32 channels: lanes = (channel within a group of 4, bin)
+                const int b = kb + bb;
+                if (b < nb) {
+                    const int dph = (int)(((unsigned)b * div_m) >> 16);
+                    const int ph = ph0 + dph, pw = pw0 + (b - dph * npw);
+                    const bool whole = (((my >> (ph * SR)) & kFull) == kFull) && (((mx >> (pw * SR)) & kFull) == kFull);
+                    float* dst = out_r + ph * PW + pw;
+#pragma unroll
+                    for (int cb = 0; cb < kCG / 4; ++cb) {
+                        const int c = cb * 4 + cs;
+                        if (c0 + c < C) {
+                            const float v = stage[c * kStageWords + bb];
+                            if (whole) dst[(size_t)c * bins] = v; else atomicAdd(dst + (size_t)c * bins, v);
+                        }
+                    }
+                }
+                __syncwarp();
             }
         }
         __syncthreads();       // the list is rebuilt by the next pass
@@ -323,14 +339,25 @@ int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int 
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1000;
     if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(roi_align_tiled_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(roi_align_tiled_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_tiled_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_tiled_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_tiled_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         if (e != cudaSuccess) return (int)e;
         attr_set[dev] = true;
     }
     roi_align_tiled_prep<<<R, 128, 0, stream>>>(rois, scale, N, C, H, W, PH, PW, sr, p.ny, p.nx, p.core_h, p.core_w, hdr, ytab, xtab, top);
     dim3 grid(p.tiles_x * p.tiles_y, (C + kCG - 1) / kCG, N);
-    roi_align_tiled_fwd<<<grid, kTiledThreads, p.smem_bytes, stream>>>(bottom, hdr, ytab, xtab, top, N, R, C, H, W, PH, PW, sr,
-                                                                       p.ny, p.nx, p.core_h, p.core_w, p.tile_h, p.tiles_x);
+#define B200_LAUNCH_TILED(SRV)                                                                                              \
+    roi_align_tiled_fwd<SRV><<<grid, kTiledThreads, p.smem_bytes, stream>>>(bottom, hdr, ytab, xtab, top, N, R, C, H, W, PH, \
+                                                                            PW, p.ny, p.nx, p.core_h, p.core_w, p.tile_h, p.tiles_x)
+    switch (sr) {
+        case 1: B200_LAUNCH_TILED(1); break;
+        case 2: B200_LAUNCH_TILED(2); break;
+        case 3: B200_LAUNCH_TILED(3); break;
+        default: B200_LAUNCH_TILED(4); break;
+    }
+#undef B200_LAUNCH_TILED
     return finish_launch(2);
 }
 

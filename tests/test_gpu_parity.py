@@ -255,6 +255,12 @@ def test_nms_thresholds_and_properties(thresh):
     assert np.array_equal(k2, np.arange(len(k)))            # idempotent
 
 
+def test_nms_large_input_uses_fallback_scan():
+    b = cases.nms_case(15000, seed=3)       # > 14k boxes: the shared-memory ring does not fit
+    k = nms_gpu(dev(b), 0.7).cpu().numpy().reshape(-1)
+    assert np.array_equal(k, O.nms_cuda(b, 0.7))
+
+
 def test_nms_edge_cases():
     assert nms_wrapper(torch.zeros((0, 5), device="cuda"), 0.7) == []
     one = dev(np.array([[0, 0, 10, 10, 0.5]], np.float32))

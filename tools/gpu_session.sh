@@ -21,6 +21,7 @@ if [ "$MODE" = "full" ]; then
   python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference.json" 2>> "$OUT/bench.err"; echo "bench-ref rc=$?" | tee -a "$OUT/status.txt"
   cat "$OUT/bench_reference.json"
 fi
+echo "== ubench"; [ -x tools/ubench_red ] && timeout 120 tools/ubench_red > "$OUT/ubench_red.txt" 2>&1; cat "$OUT/ubench_red.txt"
 echo "== ncu launch list"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" \
     python bench.py --steps 4 --warmup 3 --no-graph > "$OUT/ncu_launches.log" 2>&1; echo "ncu-list rc=$?" | tee -a "$OUT/status.txt"
