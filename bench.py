@@ -174,9 +174,13 @@ def main():
                                                  outs[i].data_ptr(), wss[i].data_ptr() if ws_bytes else None, ws_bytes,
                                                  torch.cuda.current_stream().cuda_stream), "fwd")
 
+    bws_bytes = int(lib.b200_roi_align_backward_workspace_bytes(N, C, H, W))
+    bws = torch.empty((max(bws_bytes, 1),), dtype=torch.uint8, device=device)     # one scratch image, reused every step
+
     def bwd(i):
-        _lib.check(lib.b200_roi_align_backward(dys[i].data_ptr(), scale, N, R, H, W, C, P, P, sr, rois[i].data_ptr(),
-                                               dxs[i].data_ptr(), torch.cuda.current_stream().cuda_stream), "bwd")
+        _lib.check(lib.b200_roi_align_backward_ws(dys[i].data_ptr(), scale, N, R, H, W, C, P, P, sr, rois[i].data_ptr(),
+                                                  dxs[i].data_ptr(), bws.data_ptr() if bws_bytes else None, bws_bytes,
+                                                  torch.cuda.current_stream().cuda_stream), "bwd")
 
     def step(i):
         fwd(i % nsets); bwd(i % nsets)

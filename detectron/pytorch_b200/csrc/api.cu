@@ -32,6 +32,23 @@ static bool tiled_pays_off(int R, int C, int H, int W, int PH, int PW) {
     return taps >= (1LL << 18) && (long long)H * W >= 1024;
 }
 int nms(const float*, int, int, float, int*, int*, void*, size_t, cudaStream_t);
+size_t roi_align_bwd_nhwc_workspace_bytes(int, int, int, int);
+int roi_align_backward_nhwc(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, void*, size_t, cudaStream_t);
+
+// B200_ROI_ALIGN_BWD_PATH=generic|nhwc|auto
+static int backward_path_mode() {
+    const char* e = getenv("B200_ROI_ALIGN_BWD_PATH");
+    if (e && e[0] == 'g') return 1;
+    if (e && e[0] == 'n') return 2;
+    return 0;
+}
+
+static bool nhwc_pays_off(int N, int R, int C, int H, int W, int PH, int PW, int sr) {
+    // fixed cost: zero + transpose the whole map; gain: 4x fewer L2 reduction ops
+    if (sr < 1 || (C & 3)) return false;
+    const long long taps = (long long)R * C * PH * PW * sr * sr * 4;
+    return taps >= 2LL * N * C * H * W;
+}
 
 static inline bool bad_dims(int N, int R, int H, int W, int C, int PH, int PW) {
     return N < 0 || R < 0 || H <= 0 || W <= 0 || C < 0 || PH <= 0 || PW <= 0;
@@ -101,12 +118,51 @@ int b200_roi_align_forward(const float* bottom_data, float spatial_scale, int ba
                                      (cudaStream_t)stream);
 }
 
+size_t b200_roi_align_backward_workspace_bytes(int batch_size, int channels, int height, int width) {
+    if (backward_path_mode() == 1 || batch_size <= 0 || channels <= 0 || height <= 0 || width <= 0) return 0;
+    return roi_align_bwd_nhwc_workspace_bytes(batch_size, channels, height, width);
+}
+
+int b200_roi_align_backward_ws(const float* top_diff, float spatial_scale, int batch_size, int num_rois, int height,
+                               int width, int channels, int aligned_height, int aligned_width, int sampling_ratio,
+                               const float* bottom_rois, float* bottom_diff, void* workspace, size_t workspace_bytes,
+                               b200_stream_t stream) {
+    if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
+    if ((size_t)batch_size * channels == 0) return B200_ROI_OK;
+    if (!bottom_diff || (num_rois > 0 && (!top_diff || !bottom_rois))) return B200_ROI_EINVAL;
+    const int mode = backward_path_mode();
+    if (mode != 1 && workspace != nullptr && num_rois > 0 &&
+        (mode == 2 || nhwc_pays_off(batch_size, num_rois, channels, height, width, aligned_height, aligned_width, sampling_ratio))) {
+        const int rc = roi_align_backward_nhwc(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
+                                               aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff,
+                                               workspace, workspace_bytes, (cudaStream_t)stream);
+        if (rc != 1000) return rc;
+    }
+    return roi_align_backward_generic(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
+                                      aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff,
+                                      (cudaStream_t)stream);
+}
+
 int b200_roi_align_backward(const float* top_diff, float spatial_scale, int batch_size, int num_rois, int height,
                             int width, int channels, int aligned_height, int aligned_width, int sampling_ratio,
                             const float* bottom_rois, float* bottom_diff, b200_stream_t stream) {
     if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
     if ((size_t)batch_size * channels == 0) return B200_ROI_OK;
     if (!bottom_diff || (num_rois > 0 && (!top_diff || !bottom_rois))) return B200_ROI_EINVAL;
+    const int mode = backward_path_mode();
+    if (mode != 1 && num_rois > 0 &&
+        (mode == 2 || nhwc_pays_off(batch_size, num_rois, channels, height, width, aligned_height, aligned_width, sampling_ratio))) {
+        const size_t wsb = roi_align_bwd_nhwc_workspace_bytes(batch_size, channels, height, width);
+        void* ws = nullptr;
+        if (cudaMallocAsync(&ws, wsb, (cudaStream_t)stream) == cudaSuccess) {
+            const int rc = b200_roi_align_backward_ws(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
+                                                      aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff,
+                                                      ws, wsb, stream);
+            cudaFreeAsync(ws, (cudaStream_t)stream);
+            return rc;
+        }
+        (void)cudaGetLastError();
+    }
     return roi_align_backward_generic(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
                                       aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff,
                                       (cudaStream_t)stream);

@@ -230,16 +230,31 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restric
         // ---- (3) warps pull RoIs; lane = (q: bin of the 4-bin group, i: 4-channel group)
         const int q = lane >> 3, i = lane & 7;
         const int cs = lane >> 3, bb = lane & 7;          // flush mapping: (channel within a group of 4, bin of the staged 8)
-        for (;;) {
-            int item = 0;
+        // the axis tables of the NEXT RoI are fetched into registers while the current one is processed
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&misc[1], 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        AxisEntry pre_y, pre_x;
+        pre_y.low = pre_x.low = 0; pre_y.valid = pre_x.valid = 0; pre_y.l = pre_y.h = pre_x.l = pre_x.h = 0.f;
+        int r = 0;
+        if (item < n_list) {
+            r = list[item];
+            if (lane < ny) pre_y = g_ytab[(size_t)r * ny + lane];
+            if (lane < nx) pre_x = g_xtab[(size_t)r * nx + lane];
+        }
+        while (item < n_list) {
+            __syncwarp();
+            if (lane < ny) wy[lane] = pre_y;
+            if (lane < nx) wx[lane] = pre_x;
+            __syncwarp();
+            const int r_cur = r;
             if (lane == 0) item = atomicAdd(&misc[1], 1);
             item = __shfl_sync(0xffffffffu, item, 0);
-            if (item >= n_list) break;
-            const int r = list[item];
-            __syncwarp();
-            if (lane < ny) wy[lane] = g_ytab[(size_t)r * ny + lane];
-            if (lane < nx) wx[lane] = g_xtab[(size_t)r * nx + lane];
-            __syncwarp();
+            if (item < n_list) {
+                r = list[item];
+                if (lane < ny) pre_y = g_ytab[(size_t)r * ny + lane];
+                if (lane < nx) pre_x = g_xtab[(size_t)r * nx + lane];
+            }
             // samples of this RoI that live in this tile: contiguous index ranges (bit masks my / mx);
             // uy / ux additionally drop the samples the reference skips (outside the map)
             bool in_y = false, in_x = false, ok_y = false, ok_x = false;
@@ -252,7 +267,7 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restric
             const int pw0 = (__ffs(mx) - 1) / SR, pw1 = (31 - __clz(mx)) / SR + 1;
             const int npw = pw1 - pw0, nb = (ph1 - ph0) * npw;
             const unsigned div_m = 65536u / (unsigned)npw + 1u;          // b / npw == (b * div_m) >> 16 for b < 4096
-            float* out_r = out + (size_t)r * C * bins + (size_t)c0 * bins;
+            float* out_r = out + (size_t)r_cur * C * bins + (size_t)c0 * bins;
 
             for (int kb = 0; kb < nb; kb += kStageBins) {
 #pragma unroll

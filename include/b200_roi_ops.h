@@ -78,6 +78,17 @@ B200_API int b200_roi_align_forward_ws(const float* bottom_data, float spatial_s
                               int sampling_ratio, const float* bottom_rois, float* top_data,
                               void* workspace, size_t workspace_bytes, b200_stream_t stream);
 
+/* Workspace variant of the backward: the vector-reduction path accumulates into a channel-innermost
+ * scratch image of dX and transposes it back; it needs
+ * b200_roi_align_backward_workspace_bytes(batch_size, channels, height, width) bytes (= sizeof dX).
+ * NULL / too small -> the scalar-atomic kernel runs.  The plain b200_roi_align_backward obtains the
+ * scratch with cudaMallocAsync/cudaFreeAsync on `stream`. */
+B200_API size_t b200_roi_align_backward_workspace_bytes(int batch_size, int channels, int height, int width);
+B200_API int b200_roi_align_backward_ws(const float* top_diff, float spatial_scale, int batch_size, int num_rois,
+                               int height, int width, int channels, int aligned_height, int aligned_width,
+                               int sampling_ratio, const float* bottom_rois, float* bottom_diff,
+                               void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
 /* ---- RoIAlign, legacy variant (one bilinear sample per lattice corner, fp64 interpolation) -----
  * replaces ROIAlignForwardLaucher / ROIAlignBackwardLaucher,
  *   lib/model/roi_align/src/roi_align_kernel.cu:73-91, 145-162 (header roi_align_kernel.h). */

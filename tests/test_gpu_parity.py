@@ -39,8 +39,11 @@ def dev(a):
 
 @pytest.fixture(params=["generic", "tiled"])
 def fwd_path(request, monkeypatch):
-    """Force the RoIAlign forward dispatch (B200_ROI_ALIGN_PATH is read per call by the library)."""
+    """Force the RoIAlign forward AND backward dispatch (the env vars are read per call by the library):
+    generic = RoI-centric kernels (scalar atomics in the backward), tiled = feature-map-stationary
+    forward + vector-reduction (NHWC scratch) backward."""
     monkeypatch.setenv("B200_ROI_ALIGN_PATH", request.param)
+    monkeypatch.setenv("B200_ROI_ALIGN_BWD_PATH", "generic" if request.param == "generic" else "nhwc")
     return request.param
 
 
@@ -140,12 +143,22 @@ def test_roi_align_many_rois_multi_image_partial_channels(fwd_path):
     f = S.make_features(shape, seed=5)
     r = S.make_rois(1500, shape, 0.125, seed=6, min_size=64, max_size=500)
     r[7, 0] = 5.0                       # batch index out of range
-    for P, sr in ((7, 2), (14, 2), (3, 1), (6, 4)):
-        out = RoIAlignFunction(P, P, 0.125, sr)(dev(f), dev(r)).cpu().numpy()
+    for P, sr in ((7, 2), (14, 2), (3, 1), (6, 4), (5, 3)):
+        dy = np.random.RandomState(P).standard_normal((1500, 40, P, P)).astype(np.float32)
+        out, dx = run_fwd_bwd(RoIAlignFunction(P, P, 0.125, sr), f, r, dy)
         rr = r.copy(); rr[7, 0] = 0
         ref = O.roi_align_forward(f, rr, P, P, 0.125, sr)
         ref[7] = 0
         assert_fwd_matches(out, ref, fwd_path)
+        dyr = dy.copy(); dyr[7] = 0          # the RoI with the bad batch index contributes nothing
+        np.testing.assert_allclose(dx, O.roi_align_backward(dyr, rr, shape, P, P, 0.125, sr, acc64=True), rtol=1e-5, atol=2e-5)
+    # C = 6 (not a multiple of 4): the vector path must fall back to scalar reductions per channel
+    shape6 = (2, 6, 30, 34)
+    f6 = S.make_features(shape6, seed=8); r6 = S.make_rois(64, shape6, 0.25, seed=9)
+    dy6 = np.random.RandomState(3).standard_normal((64, 6, 7, 7)).astype(np.float32)
+    out6, dx6 = run_fwd_bwd(RoIAlignFunction(7, 7, 0.25, 2), f6, r6, dy6)
+    assert_fwd_matches(out6, O.roi_align_forward(f6, r6, 7, 7, 0.25, 2), fwd_path)
+    np.testing.assert_allclose(dx6, O.roi_align_backward(dy6, r6, shape6, 7, 7, 0.25, 2, acc64=True), **GRAD_TOL)
 
 
 def test_roi_align_empty_and_degenerate():
