@@ -141,7 +141,16 @@ roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int C, 
 // ------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2).  Each half is an independent IEEE-754 RN
+// operation, so results are bit-identical to the scalar _rn intrinsics; it halves the issue slots of
+// the interpolation, which is issue-bound, not FLOP-bound.
+typedef unsigned long long u64x;
+__device__ __forceinline__ u64x pack2(float lo, float hi) { u64x r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64x v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64x fma2(u64x a, u64x b, u64x c) { u64x d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64x mul2(u64x a, u64x b) { u64x d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64x add2(u64x a, u64x b) { u64x d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ ulonglong2 lds128(const float* p) { return *reinterpret_cast<const ulonglong2*>(p); }
 
 template <int SR>
 __global__ void __launch_bounds__(kTiledThreads, 2)
@@ -203,25 +212,39 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restric
 
         // ---- (2) stage the tile once: rows [y0, y0+tile_h) x cols [x0, x0+32) x channels [c0, c0+32), zero outside the map
         if (!staged) {
+            // warp w stages channel quad w of every tile row; loads are branch-free (addresses clamped into
+            // the tensor, invalid lanes zeroed afterwards) and issued kRowsPerBatch rows = 4*kRowsPerBatch
+            // independent 128-byte-coalesced loads at a time, so ~28 loads per thread are in flight.
+            constexpr int kRowsPerBatch = 7;
             const size_t plane = (size_t)H * W;
-            const float* src = bottom + ((size_t)n * C + c0) * plane;
             const int x = x0 + lane;
             const bool x_ok = x < W;
-            const int items = tile_h * (kCG / 4);        // (row, channel quad) per warp-wide item
-#pragma unroll 4
-            for (int it = warp; it < items; it += kWarps) {
-                const int row = it >> 3, q = it & 7;
-                const int y = y0 + row;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (x_ok && y < H) {
-                    const float* p = src + (size_t)(4 * q) * plane + (size_t)y * W + x;
-                    const int cleft = C - c0 - 4 * q;
-                    if (cleft > 0) v.x = __ldg(p);
-                    if (cleft > 1) v.y = __ldg(p + plane);
-                    if (cleft > 2) v.z = __ldg(p + 2 * plane);
-                    if (cleft > 3) v.w = __ldg(p + 3 * plane);
+            const int cq = c0 + 4 * warp;
+            const bool ch0 = cq < C, ch1 = cq + 1 < C, ch2 = cq + 2 < C, ch3 = cq + 3 < C;
+            const float* base = bottom + (size_t)n * C * plane + min(x, W - 1);
+            const float* p0 = base + (size_t)min(cq, C - 1) * plane;
+            const float* p1 = base + (size_t)min(cq + 1, C - 1) * plane;
+            const float* p2 = base + (size_t)min(cq + 2, C - 1) * plane;
+            const float* p3 = base + (size_t)min(cq + 3, C - 1) * plane;
+            float* dst = tile + (size_t)lane * kCellWords + 4 * warp;
+            for (int k0 = 0; k0 < tile_h; k0 += kRowsPerBatch) {
+                float4 v[kRowsPerBatch];
+#pragma unroll
+                for (int bq = 0; bq < kRowsPerBatch; ++bq) {
+                    const size_t off = (size_t)min(y0 + k0 + bq, H - 1) * W;
+                    v[bq].x = __ldg(p0 + off); v[bq].y = __ldg(p1 + off); v[bq].z = __ldg(p2 + off); v[bq].w = __ldg(p3 + off);
                 }
-                *reinterpret_cast<float4*>(tile + (size_t)(row * kTX + lane) * kCellWords + 4 * q) = v;
+#pragma unroll
+                for (int bq = 0; bq < kRowsPerBatch; ++bq) {
+                    const int row = k0 + bq;
+                    if (row < tile_h) {
+                        const bool ok = x_ok && (y0 + row < H);
+                        float4 o;
+                        o.x = (ok && ch0) ? v[bq].x : 0.f; o.y = (ok && ch1) ? v[bq].y : 0.f;
+                        o.z = (ok && ch2) ? v[bq].z : 0.f; o.w = (ok && ch3) ? v[bq].w : 0.f;
+                        *reinterpret_cast<float4*>(dst + (size_t)row * kTX * kCellWords) = o;
+                    }
+                }
             }
             staged = true;
         }
@@ -276,7 +299,7 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restric
                     if (b < nb) {
                         const int dph = (int)(((unsigned)b * div_m) >> 16);
                         const int ph = ph0 + dph, pw = pw0 + (b - dph * npw);
-                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                        u64x acc_lo = 0ull, acc_hi = 0ull;           // channels (0,1) and (2,3) of this lane's group
 #pragma unroll
                         for (int iy = 0; iy < SR; ++iy) {
                             const int s_y = ph * SR + iy;
@@ -290,15 +313,17 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restric
                                 const AxisEntry ex = wx[s_x];
                                 const float w1 = __fmul_rn(ey.h, ex.h), w2 = __fmul_rn(ey.h, ex.l);
                                 const float w3 = __fmul_rn(ey.l, ex.h), w4 = __fmul_rn(ey.l, ex.l);
+                                const u64x W1 = pack2(w1, w1), W2 = pack2(w2, w2), W3 = pack2(w3, w3), W4 = pack2(w4, w4);
                                 const float* p = tile + (row_off + ex.low * kCellWords);
-                                const float4 v1 = lds128(p), v2 = lds128(p + kCellWords);
-                                const float4 v3 = lds128(p + kTX * kCellWords), v4 = lds128(p + (kTX + 1) * kCellWords);
-                                a0 = __fadd_rn(a0, __fmaf_rn(v4.x, w4, __fmaf_rn(v3.x, w3, __fmaf_rn(v1.x, w1, __fmul_rn(v2.x, w2)))));
-                                a1 = __fadd_rn(a1, __fmaf_rn(v4.y, w4, __fmaf_rn(v3.y, w3, __fmaf_rn(v1.y, w1, __fmul_rn(v2.y, w2)))));
-                                a2 = __fadd_rn(a2, __fmaf_rn(v4.z, w4, __fmaf_rn(v3.z, w3, __fmaf_rn(v1.z, w1, __fmul_rn(v2.z, w2)))));
-                                a3 = __fadd_rn(a3, __fmaf_rn(v4.w, w4, __fmaf_rn(v3.w, w3, __fmaf_rn(v1.w, w1, __fmul_rn(v2.w, w2)))));
+                                const ulonglong2 v1 = lds128(p), v2 = lds128(p + kCellWords);
+                                const ulonglong2 v3 = lds128(p + kTX * kCellWords), v4 = lds128(p + (kTX + 1) * kCellWords);
+                                // val = FFMA(v4,w4, FFMA(v3,w3, FFMA(v1,w1, FMUL(v2,w2))));  acc += val   (reference order)
+                                acc_lo = add2(acc_lo, fma2(v4.x, W4, fma2(v3.x, W3, fma2(v1.x, W1, mul2(v2.x, W2)))));
+                                acc_hi = add2(acc_hi, fma2(v4.y, W4, fma2(v3.y, W3, fma2(v1.y, W1, mul2(v2.y, W2)))));
                             }
                         }
+                        float a0, a1, a2, a3;
+                        unpack2(acc_lo, a0, a1); unpack2(acc_hi, a2, a3);
                         if (SR == 3) {        // count 9: a true division, like the reference's `output_val /= count`
                             a0 = __fdiv_rn(a0, kCount); a1 = __fdiv_rn(a1, kCount); a2 = __fdiv_rn(a2, kCount); a3 = __fdiv_rn(a3, kCount);
                         } else {              // count 1 / 4 / 16: multiplying by the reciprocal is exact

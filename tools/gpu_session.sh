@@ -22,10 +22,11 @@ if [ "$MODE" = "full" ]; then
   cat "$OUT/bench_reference.json"
 fi
 echo "== ubench"; [ -x tools/ubench_red ] && timeout 120 tools/ubench_red > "$OUT/ubench_red.txt" 2>&1; cat "$OUT/ubench_red.txt"
+echo "== ncu nms"; ncu --set full --clock-control none --import-source on -k regex:nms_scan -s 2 -c 1 -o "$OUT/prof_nms" -f python tools/nms_probe.py > "$OUT/ncu_nms.log" 2>&1; tail -2 "$OUT/ncu_nms.log"
 echo "== ncu launch list"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" \
     python bench.py --steps 4 --warmup 3 --no-graph > "$OUT/ncu_launches.log" 2>&1; echo "ncu-list rc=$?" | tee -a "$OUT/status.txt"
 echo "== ncu full (our kernels)"
-ncu --set full --clock-control none --import-source on -k regex:'roi_align|nms_' -s 8 -c 6 -o "$OUT/prof" -f \
+ncu --set full --clock-control none --import-source on -k regex:'roi_align|nms_scan|nhwc' -s 10 -c 8 -o "$OUT/prof" -f \
     python bench.py --steps 4 --warmup 3 --no-graph > "$OUT/ncu_full.log" 2>&1; echo "ncu-full rc=$?" | tee -a "$OUT/status.txt"
 ls -la "$OUT"
