@@ -164,15 +164,20 @@ nms_scan_pipelined_kernel(const u64* __restrict__ mask, int n, int col_blocks, i
         const u64* rows = ring + (size_t)(b & 1) * buf_words;
         const int lim = min(kNmsTile, n - b * kNmsTile);
         if (warp == 0) {
-            const u64 d_lo = (lane < lim) ? rows[(size_t)lane * col_blocks + b] : 0;
-            const u64 d_hi = (lane + 32 < lim) ? rows[(size_t)(lane + 32) * col_blocks + b] : 0;
+            // Serial greedy resolve of the 64 boxes of block b.  Branch-free and fully unrolled: the diagonal
+            // words come from shared memory (broadcast loads that do not depend on the running state, so they
+            // are issued ahead), and the dependent chain per box is one bit test + one predicated OR.
             u64 r = remv[b];
             u64 kept = 0;
-#pragma unroll 16
+            const u64* diag = rows + b;
+#pragma unroll
             for (int k = 0; k < kNmsTile; ++k) {
-                const u64 dk = __shfl_sync(0xffffffffu, (k < 32) ? d_lo : d_hi, k & 31);
-                if (k < lim && !((r >> k) & 1ULL)) { kept |= 1ULL << k; r |= dk; }
+                const u64 dk = (k < lim) ? diag[(size_t)k * col_blocks] : 0ULL;
+                const bool alive = ((r >> k) & 1ULL) == 0ULL;
+                kept |= alive ? (1ULL << k) : 0ULL;
+                r |= alive ? dk : 0ULL;
             }
+            if (lim < kNmsTile) kept &= (1ULL << lim) - 1ULL;
             if (lane == 0) s_kept = kept;
         }
         __syncthreads();
