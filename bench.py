@@ -166,7 +166,7 @@ def main():
     dxs = [torch.empty(shape, device=device) for _ in range(nsets)]
     stream = torch.cuda.current_stream()
 
-    ws_bytes = int(lib.b200_roi_align_workspace_bytes(R, P, P, sr))
+    ws_bytes = int(lib.b200_roi_align_workspace_bytes(N, R, H, W, P, P, sr))
     wss = [torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=device) for _ in range(nsets)]
 
     def fwd(i):

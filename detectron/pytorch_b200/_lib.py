@@ -21,7 +21,7 @@ _SIGNATURES = {
     "b200_roi_ops_launch_count": (ctypes.c_ulonglong, []),
     # (bottom, scale, N, R, H, W, C, PH, PW, sr, rois, top, stream)
     "b200_roi_align_forward": (ctypes.c_int, [_c_float_p, ctypes.c_float] + [ctypes.c_int] * 8 + [_c_float_p, _c_float_p, _stream_t]),
-    "b200_roi_align_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 4),
+    "b200_roi_align_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 7),
     # (bottom, scale, N, R, H, W, C, PH, PW, sr, rois, top, workspace, workspace_bytes, stream)
     "b200_roi_align_forward_ws": (ctypes.c_int, [_c_float_p, ctypes.c_float] + [ctypes.c_int] * 8 +
                                   [_c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t, _stream_t]),

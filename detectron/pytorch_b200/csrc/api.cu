@@ -15,7 +15,7 @@ int roi_pool_backward(const float*, float, int, int, int, int, int, int, int, co
 int roi_crop_forward(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int roi_crop_backward(const float*, const float*, int, int, int, int, int, int, int, float*, float*, cudaStream_t);
 size_t nms_workspace_bytes(int);
-size_t roi_align_tiled_workspace_bytes(int, int, int, int);
+size_t roi_align_tiled_workspace_bytes(int, int, int, int, int, int, int);
 int roi_align_forward_tiled(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, void*, size_t, cudaStream_t);
 
 // B200_ROI_ALIGN_PATH=generic|tiled|auto (default auto) -- test/benchmark override of the forward dispatch
@@ -71,9 +71,10 @@ const char* b200_roi_ops_strerror(int status) {
 
 unsigned long long b200_roi_ops_launch_count(void) { return g_launch_count; }
 
-size_t b200_roi_align_workspace_bytes(int num_rois, int aligned_height, int aligned_width, int sampling_ratio) {
+size_t b200_roi_align_workspace_bytes(int batch_size, int num_rois, int height, int width, int aligned_height,
+                                      int aligned_width, int sampling_ratio) {
     if (forward_path_mode() == 1) return 0;
-    return roi_align_tiled_workspace_bytes(num_rois, aligned_height, aligned_width, sampling_ratio);
+    return roi_align_tiled_workspace_bytes(batch_size, num_rois, height, width, aligned_height, aligned_width, sampling_ratio);
 }
 
 int b200_roi_align_forward_ws(const float* bottom_data, float spatial_scale, int batch_size, int num_rois, int height,
@@ -101,7 +102,8 @@ int b200_roi_align_forward(const float* bottom_data, float spatial_scale, int ba
     if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
     if (num_rois > 0 && channels > 0 && (!bottom_data || !bottom_rois || !top_data)) return B200_ROI_EINVAL;
     const int mode = forward_path_mode();
-    const size_t wsb = (mode == 1) ? 0 : roi_align_tiled_workspace_bytes(num_rois, aligned_height, aligned_width, sampling_ratio);
+    const size_t wsb = (mode == 1) ? 0 : roi_align_tiled_workspace_bytes(batch_size, num_rois, height, width, aligned_height,
+                                                                         aligned_width, sampling_ratio);
     if (wsb > 0 && (mode == 2 || tiled_pays_off(num_rois, channels, height, width, aligned_height, aligned_width))) {
         void* ws = nullptr;
         if (cudaMallocAsync(&ws, wsb, (cudaStream_t)stream) == cudaSuccess) {

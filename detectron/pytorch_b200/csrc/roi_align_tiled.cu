@@ -3,11 +3,11 @@
 // Why: the RoI-centric gather (reference kernel, and our generic path) is bound by L1/L2
 // transactions, not HBM: every 4-byte tap costs a 32-byte sector slot (ncu, profiles/r01a:
 // 69.9 M L1 sectors for 3.29 M warp loads, l1tex 91 % busy, DRAM 6 %).  Here every feature byte
-// crosses L2 -> SM once (+ a 1-cell halo): a CTA owns a spatial tile x 32 channels, stages it into
+// crosses L2 -> SM once (+ a 1-cell halo): a work item = spatial tile x 32 channels is staged into
 // shared memory TRANSPOSED to [cell][channel] (coalesced 128-byte row loads, conflict-free 128-bit
-// shared stores), and then serves every bilinear SAMPLE whose top-left tap lies in the tile with
+// shared stores) and then serves every bilinear SAMPLE whose top-left tap lies in the tile with
 // conflict-free 128-bit shared loads: lane = (bin of a 4-bin group, 4-channel group), so one
-// LDS.128 fetches one tap for 4 bins x 32 channels.
+// LDS.128 fetches one tap for 4 bins x 32 channels; the interpolation runs on packed FFMA2.
 //
 // Work assignment is per sample, not per bin: a sample's 4 taps span 2x2 cells, so a 1-cell halo is
 // enough for ANY RoI size.  Bins whose samples fall into different tiles ("split" bins, ~1 in 5 at
@@ -15,87 +15,30 @@
 // exactly those output elements.  Everything else is written once with plain stores, staged through
 // shared memory so that the lanes of a store are consecutive bins of one channel.
 //
+// The prepass (one CTA per RoI) does everything that is channel independent exactly once: the
+// per-axis sample tables (all IEEE divisions), and the list of RoIs per tile (global atomics), so the
+// main kernel neither computes coordinates nor scans RoIs.  The main kernel is persistent (two CTAs
+// per SM pulling (tile, channel group) items from a global counter), which removes the per-CTA launch
+// cost and lets the two co-resident CTAs drift apart so one stages while the other computes.
+//
 // Numerics: each lane evaluates the reference's rounding recipe in the reference's order
 // (oracle/roi_ops_oracle.c), so unsplit bins are bit-identical to the reference kernel; split bins
 // differ by the association of <= 4 partial sums (~1 ulp).
 //
 // Semantics: lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu (reference) :16-63, :65-121.
-#include "common.cuh"
+#include "roi_align_tiled.cuh"
 
 namespace b200 {
 
-constexpr int kTX = 32;                 // tile width in cells (one warp-wide row load)
-constexpr int kCG = 32;                 // channels per CTA
-constexpr int kCellWords = kCG + 4;     // 36 words = 144 B per cell: padding makes the transposing STS.128 conflict-free
-constexpr int kTiledThreads = 256;
-constexpr int kWarps = kTiledThreads / 32;
-constexpr int kAxisMax = 32;            // P * sampling_ratio per axis supported by the fast path
-constexpr int kListMax = 512;           // RoIs cached per pass of a CTA
-constexpr int kStageBins = 8;           // bins of one output row staged per flush
-constexpr int kStageWords = kStageBins + 1;
-
-struct __align__(16) AxisEntry {        // one bilinear sample along one axis (channel independent)
-    int   low;                          // low cell (clamped into the map even when invalid)
-    int   valid;                        // 0 <=> the reference's "outside the map" early-out
-    float l, h;                         // weights of the high / low cell
-};
-
-struct __align__(16) RoiHeader {
-    int batch;                          // -1 if the batch index is out of range
-    int y_min, y_max, x_min, x_max;     // range of `low` over the samples of each axis
-    int pad0, pad1, pad2;
-};
-
-struct TiledPlan {
-    int ny, nx;                         // samples per axis = P * sr
-    int core_h, core_w;                 // tile core (= tile - 1-cell halo)
-    int tile_h;                         // rows staged per tile
-    int tiles_y, tiles_x;
-    size_t smem_bytes;
-    size_t ws_hdr_off, ws_ytab_off, ws_xtab_off, ws_bytes;
-};
-
-static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-// smem carve-up (bytes): [tile][roi list][per-warp axis tables][per-warp output staging][misc]
-__host__ __device__ inline size_t tiled_smem_bytes(int tile_h) {
-    return (size_t)kTX * tile_h * kCellWords * 4 + kListMax * 2 + (size_t)kWarps * 2 * kAxisMax * 16 +
-           (size_t)kWarps * kCG * kStageWords * 4 + 64;
-}
-
-bool roi_align_tiled_plan(int N, int R, int H, int W, int C, int PH, int PW, int sr, TiledPlan* p) {
-    if (sr < 1 || sr > 4 || PH * sr > kAxisMax || PW * sr > kAxisMax) return false;
-    if (R <= 0 || R > 65535 || C <= 0 || N <= 0) return false;
-    if ((long long)R * C * PH * PW >= (1LL << 31) || (long long)N * C * H * W >= (1LL << 31)) return false;
-    p->ny = PH * sr; p->nx = PW * sr;
-    // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
-    const size_t budget = 113 * 1024;
-    int th = 64;
-    while (th > 4 && tiled_smem_bytes(th) > budget) --th;
-    if (th <= 4) return false;
-    // do not stage rows a small map does not have; balance the rows over the tiles
-    int core_h = th - 1;
-    int tiles_y = (H + core_h - 1) / core_h;
-    core_h = (H + tiles_y - 1) / tiles_y;
-    p->core_h = core_h; p->tile_h = core_h + 1; p->tiles_y = tiles_y;
-    p->core_w = kTX - 1; p->tiles_x = (W + p->core_w - 1) / p->core_w;
-    p->smem_bytes = tiled_smem_bytes(p->tile_h);
-    p->ws_hdr_off = 0;
-    p->ws_ytab_off = align_up((size_t)R * sizeof(RoiHeader), 256);
-    p->ws_xtab_off = align_up(p->ws_ytab_off + (size_t)R * p->ny * sizeof(AxisEntry), 256);
-    p->ws_bytes = align_up(p->ws_xtab_off + (size_t)R * p->nx * sizeof(AxisEntry), 256);
-    return true;
-}
-
 // ------------------------------------------------------------------------------------------------
-// prepass: per-RoI axis tables + header, and zero-fill of the outputs that will be accumulated
+// prepass
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int C, int H, int W, int PH, int PW, int sr,
-                     int ny, int nx, int core_h, int core_w, RoiHeader* __restrict__ hdr,
-                     AxisEntry* __restrict__ ytab, AxisEntry* __restrict__ xtab, float* __restrict__ out) {
+roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int R, int C, int H, int W, int PH, int PW, int sr,
+                     int ny, int nx, int core_h, int core_w, int tiles_y, int tiles_x,
+                     RoiHeader* __restrict__ hdr, AxisEntry* __restrict__ ytab, AxisEntry* __restrict__ xtab,
+                     int* __restrict__ tile_count, unsigned short* __restrict__ tile_list, float* __restrict__ out) {
     __shared__ int s_ty[kAxisMax], s_tx[kAxisMax];
-    __shared__ int s_lo[2 * kAxisMax];
     __shared__ unsigned short s_split[kAxisMax * kAxisMax];
     __shared__ int s_nsplit;
     const int r = blockIdx.x;
@@ -105,21 +48,28 @@ roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int C, 
     if (t < ny + nx) {
         const bool isy = t < ny;
         const int s = isy ? t : t - ny;
-        const AxisTap a = isy ? xfrom_axis(xfrom_coord(g.start_h, g.bin_h, s / sr, s % sr, sr), H)
-                              : xfrom_axis(xfrom_coord(g.start_w, g.bin_w, s / sr, s % sr, sr), W);
-        AxisEntry e; e.low = a.low; e.valid = a.valid ? 1 : 0; e.l = a.l; e.h = a.h;
-        if (isy) { ytab[(size_t)r * ny + s] = e; s_ty[s] = a.low / core_h; }
-        else     { xtab[(size_t)r * nx + s] = e; s_tx[s] = a.low / core_w; }
-        s_lo[t] = a.low;
+        const AxisEntry e = tiled_axis_entry(g, isy, s, sr, H, W);
+        if (isy) { ytab[(size_t)r * ny + s] = e; s_ty[s] = e.low / core_h; }
+        else     { xtab[(size_t)r * nx + s] = e; s_tx[s] = e.low / core_w; }
     }
     __syncthreads();
     const bool batch_ok = g.batch >= 0 && g.batch < N;
+    // sample lows are monotone along an axis, so the tiles of this RoI form the rectangle below
+    const int ty0 = s_ty[0], ty1 = s_ty[ny - 1], tx0 = s_tx[0], tx1 = s_tx[nx - 1];
     if (t == 0) {
         RoiHeader h;
         h.batch = batch_ok ? g.batch : -1;
-        h.y_min = s_lo[0]; h.y_max = s_lo[ny - 1]; h.x_min = s_lo[ny]; h.x_max = s_lo[ny + nx - 1];
+        h.y_min = ty0; h.y_max = ty1; h.x_min = tx0; h.x_max = tx1;
         h.pad0 = h.pad1 = h.pad2 = 0;
         hdr[r] = h;
+    }
+    if (batch_ok) {
+        const int nty = ty1 - ty0 + 1, ntx = tx1 - tx0 + 1;
+        for (int k = t; k < nty * ntx; k += blockDim.x) {
+            const int tile = (g.batch * tiles_y + ty0 + k / ntx) * tiles_x + tx0 + k % ntx;
+            const int pos = atomicAdd(&tile_count[tile], 1);
+            tile_list[(size_t)tile * R + pos] = (unsigned short)r;
+        }
     }
     // bins the main kernel accumulates into (their samples straddle tiles) or never visits (bad batch index)
     const int bins = PH * PW;
@@ -139,84 +89,53 @@ roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int C, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// main kernel
+// main kernel (persistent)
 // ------------------------------------------------------------------------------------------------
-// Packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2).  Each half is an independent IEEE-754 RN
-// operation, so results are bit-identical to the scalar _rn intrinsics; it halves the issue slots of
-// the interpolation, which is issue-bound, not FLOP-bound.
-typedef unsigned long long u64x;
-__device__ __forceinline__ u64x pack2(float lo, float hi) { u64x r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void unpack2(u64x v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64x fma2(u64x a, u64x b, u64x c) { u64x d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ u64x mul2(u64x a, u64x b) { u64x d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ u64x add2(u64x a, u64x b) { u64x d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ ulonglong2 lds128(const float* p) { return *reinterpret_cast<const ulonglong2*>(p); }
-
 template <int SR>
 __global__ void __launch_bounds__(kTiledThreads, 2)
-roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restrict__ hdr,
-                    const AxisEntry* __restrict__ g_ytab, const AxisEntry* __restrict__ g_xtab,
-                    float* __restrict__ out, int N, int R, int C, int H, int W, int PH, int PW,
-                    int ny, int nx, int core_h, int core_w, int tile_h, int tiles_x) {
+roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restrict__ g_ytab, const AxisEntry* __restrict__ g_xtab,
+                    int* __restrict__ work_counter, const int* __restrict__ tile_count,
+                    const unsigned short* __restrict__ tile_list, float* __restrict__ out,
+                    int N, int R, int C, int H, int W, int PH, int PW, int ny, int nx,
+                    int core_h, int core_w, int tile_h, int tiles_y, int tiles_x, int n_cgroups, int n_work) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);
-    unsigned short* list = reinterpret_cast<unsigned short*>(smem_raw + (size_t)kTX * tile_h * kCellWords * 4);
-    AxisEntry* wtab_all = reinterpret_cast<AxisEntry*>(reinterpret_cast<unsigned char*>(list) + kListMax * 2);
+    AxisEntry* wtab_all = reinterpret_cast<AxisEntry*>(smem_raw + (size_t)kTX * tile_h * kCellWords * 4);
     float* stage_all = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wtab_all) + (size_t)kWarps * 2 * kAxisMax * 16);
-    int* misc = reinterpret_cast<int*>(stage_all + kWarps * kCG * kStageWords);   // [0]=list count, [1]=next item, [2..9]=warp counts
+    int* misc = reinterpret_cast<int*>(stage_all + kWarps * kCG * kStageWords);   // [0]=work item, [1]=next RoI of the list
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
-    const int y0 = ty * core_h, x0 = tx * core_w;
-    const int c0 = blockIdx.y * kCG;
-    const int n = blockIdx.z;
-    const int y_end = y0 + core_h, x_end = x0 + core_w;      // core = [y0, y_end) x [x0, x_end)
     const int bins = PH * PW;
     constexpr float kCount = (float)(SR * SR);
     constexpr unsigned kFull = (1u << SR) - 1u;
-
     AxisEntry* wy = wtab_all + warp * 2 * kAxisMax;
     AxisEntry* wx = wy + kAxisMax;
     float* stage = stage_all + warp * kCG * kStageWords;
+    const int q = lane >> 3, i = lane & 7;                // compute mapping: (bin of the 4-bin group, 4-channel group)
+    const int cs = lane >> 3, bb = lane & 7;              // flush mapping:   (channel within a group of 4, staged bin)
+    const size_t plane = (size_t)H * W;
 
-    bool staged = false;
-    for (int r_base = 0; r_base < R; ) {
-        // ---- (1) compact the RoIs of image n whose sample range meets this tile's core (ascending order)
-        if (tid == 0) { misc[0] = 0; misc[1] = 0; }
+    for (;;) {
+        __syncthreads();                                  // previous item fully consumed (tile, misc)
+        if (tid == 0) { misc[0] = atomicAdd(work_counter, 1); misc[1] = 0; }
         __syncthreads();
-        int r_next = r_base;
-        while (r_next < R) {
-            const int r = r_next + tid;
-            bool hit = false;
-            if (r < R) {
-                const RoiHeader h = hdr[r];
-                hit = (h.batch == n) && h.y_max >= y0 && h.y_min < y_end && h.x_max >= x0 && h.x_min < x_end;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) misc[2 + warp] = __popc(m);
-            __syncthreads();
-            const int base_cnt = misc[0];
-            int before = base_cnt, chunk = 0;
-#pragma unroll
-            for (int k = 0; k < kWarps; ++k) { const int wc = misc[2 + k]; if (k < warp) before += wc; chunk += wc; }
-            if (base_cnt + chunk > kListMax) { __syncthreads(); break; }
-            if (hit) list[before + __popc(m & ((1u << lane) - 1u))] = (unsigned short)r;
-            __syncthreads();
-            if (tid == 0) misc[0] = base_cnt + chunk;
-            __syncthreads();
-            r_next += kTiledThreads;
-        }
-        r_base = r_next;
-        const int n_list = misc[0];
-        if (n_list == 0) continue;                       // uniform
+        const int work = misc[0];
+        if (work >= n_work) break;
+        const int tile_id = work / n_cgroups;             // consecutive items share a tile (same list, tables hit L2)
+        const int c0 = (work - tile_id * n_cgroups) * kCG;
+        const int n_list = tile_count[tile_id];
+        if (n_list == 0) continue;                        // uniform
+        const unsigned short* list = tile_list + (size_t)tile_id * R;
+        const int tx = tile_id % tiles_x, ty = (tile_id / tiles_x) % tiles_y, n = tile_id / (tiles_x * tiles_y);
+        const int y0 = ty * core_h, x0 = tx * core_w;
+        const int y_end = y0 + core_h, x_end = x0 + core_w;      // core = [y0, y_end) x [x0, x_end)
 
-        // ---- (2) stage the tile once: rows [y0, y0+tile_h) x cols [x0, x0+32) x channels [c0, c0+32), zero outside the map
-        if (!staged) {
-            // warp w stages channel quad w of every tile row; loads are branch-free (addresses clamped into
-            // the tensor, invalid lanes zeroed afterwards) and issued kRowsPerBatch rows = 4*kRowsPerBatch
-            // independent 128-byte-coalesced loads at a time, so ~28 loads per thread are in flight.
+        // ---- stage the tile: rows [y0, y0+tile_h) x cols [x0, x0+32) x channels [c0, c0+32), zero outside the map.
+        // Warp w stages channel quad w of every row; loads are branch-free (addresses clamped into the tensor,
+        // invalid lanes zeroed afterwards) and issued kRowsPerBatch rows = 4*kRowsPerBatch independent
+        // 128-byte-coalesced loads at a time, so ~28 loads per thread are in flight.
+        {
             constexpr int kRowsPerBatch = 7;
-            const size_t plane = (size_t)H * W;
             const int x = x0 + lane;
             const bool x_ok = x < W;
             const int cq = c0 + 4 * warp;
@@ -246,14 +165,11 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restric
                     }
                 }
             }
-            staged = true;
         }
         __syncthreads();
 
-        // ---- (3) warps pull RoIs; lane = (q: bin of the 4-bin group, i: 4-channel group)
-        const int q = lane >> 3, i = lane & 7;
-        const int cs = lane >> 3, bb = lane & 7;          // flush mapping: (channel within a group of 4, bin of the staged 8)
-        // the axis tables of the NEXT RoI are fetched into registers while the current one is processed
+        // ---- warps pull RoIs of this tile; the axis tables of the NEXT RoI are fetched into registers
+        //      while the current one is processed
         int item = 0;
         if (lane == 0) item = atomicAdd(&misc[1], 1);
         item = __shfl_sync(0xffffffffu, item, 0);
@@ -289,7 +205,7 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restric
             const int ph0 = (__ffs(my) - 1) / SR, ph1 = (31 - __clz(my)) / SR + 1;
             const int pw0 = (__ffs(mx) - 1) / SR, pw1 = (31 - __clz(mx)) / SR + 1;
             const int npw = pw1 - pw0, nb = (ph1 - ph0) * npw;
-            const unsigned div_m = 65536u / (unsigned)npw + 1u;          // b / npw == (b * div_m) >> 16 for b < 4096
+            const unsigned div_m = 65536u / (unsigned)npw + 1u;          // b / npw == (b * div_m) >> 16 for b < 1024
             float* out_r = out + (size_t)r_cur * C * bins + (size_t)c0 * bins;
 
             for (int kb = 0; kb < nb; kb += kStageBins) {
@@ -354,14 +270,12 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const RoiHeader* __restric
                 __syncwarp();
             }
         }
-        __syncthreads();       // the list is rebuilt by the next pass
     }
 }
 
-size_t roi_align_tiled_workspace_bytes(int R, int PH, int PW, int sr) {
+size_t roi_align_tiled_workspace_bytes(int N, int R, int H, int W, int PH, int PW, int sr) {
     TiledPlan p;
-    // H, W, C, N do not enter the workspace size
-    if (!roi_align_tiled_plan(1, R, 64, 64, 1, PH, PW, sr, &p)) return 0;
+    if (!roi_align_tiled_plan(N, R, H, W, 1, PH, PW, sr, false, &p)) return 0;
     return p.ws_bytes;
 }
 
@@ -369,13 +283,19 @@ size_t roi_align_tiled_workspace_bytes(int R, int PH, int PW, int sr) {
 int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int H, int W, int C, int PH, int PW, int sr,
                             const float* rois, float* top, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     TiledPlan p;
-    if (!roi_align_tiled_plan(N, R, H, W, C, PH, PW, sr, &p)) return 1000;
+    if (!roi_align_tiled_plan(N, R, H, W, C, PH, PW, sr, false, &p)) return 1000;
     if (workspace == nullptr || workspace_bytes < p.ws_bytes) return 1000;
     unsigned char* ws = (unsigned char*)workspace;
-    RoiHeader* hdr = (RoiHeader*)(ws + p.ws_hdr_off);
-    AxisEntry* ytab = (AxisEntry*)(ws + p.ws_ytab_off);
-    AxisEntry* xtab = (AxisEntry*)(ws + p.ws_xtab_off);
+    RoiHeader* hdr = (RoiHeader*)(ws + p.hdr_off);
+    AxisEntry* ytab = (AxisEntry*)(ws + p.ytab_off);
+    AxisEntry* xtab = (AxisEntry*)(ws + p.xtab_off);
+    int* zero = (int*)(ws + p.zero_off);
+    int* work_counter = zero;
+    int* tile_count = zero + 4;
+    unsigned short* tile_list = (unsigned short*)(ws + p.tile_list_off);
+
     static bool attr_set[64] = {false};     // per device: the attribute lives in the device's context
+    static int sm_count[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1000;
     if (!attr_set[dev]) {
@@ -383,14 +303,20 @@ int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int 
         if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_tiled_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_tiled_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_tiled_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
         attr_set[dev] = true;
     }
-    roi_align_tiled_prep<<<R, 128, 0, stream>>>(rois, scale, N, C, H, W, PH, PW, sr, p.ny, p.nx, p.core_h, p.core_w, hdr, ytab, xtab, top);
-    dim3 grid(p.tiles_x * p.tiles_y, (C + kCG - 1) / kCG, N);
+    cudaError_t err = cudaMemsetAsync(zero, 0, p.zero_bytes, stream);
+    if (err != cudaSuccess) return (int)err;
+    roi_align_tiled_prep<<<R, 128, 0, stream>>>(rois, scale, N, R, C, H, W, PH, PW, sr, p.ny, p.nx, p.core_h, p.core_w,
+                                               p.tiles_y, p.tiles_x, hdr, ytab, xtab, tile_count, tile_list, top);
+    const int n_cgroups = (C + kCG - 1) / kCG;
+    const int n_work = p.tiles_total * n_cgroups;
+    const int grid = n_work < 2 * sm_count[dev] ? n_work : 2 * sm_count[dev];      // persistent: two CTAs per SM
 #define B200_LAUNCH_TILED(SRV)                                                                                              \
-    roi_align_tiled_fwd<SRV><<<grid, kTiledThreads, p.smem_bytes, stream>>>(bottom, hdr, ytab, xtab, top, N, R, C, H, W, PH, \
-                                                                            PW, p.ny, p.nx, p.core_h, p.core_w, p.tile_h, p.tiles_x)
+    roi_align_tiled_fwd<SRV><<<grid, kTiledThreads, p.smem_bytes, stream>>>(bottom, ytab, xtab, work_counter, tile_count,   \
+        tile_list, top, N, R, C, H, W, PH, PW, p.ny, p.nx, p.core_h, p.core_w, p.tile_h, p.tiles_y, p.tiles_x, n_cgroups, n_work)
     switch (sr) {
         case 1: B200_LAUNCH_TILED(1); break;
         case 2: B200_LAUNCH_TILED(2); break;

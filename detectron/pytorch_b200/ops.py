@@ -40,7 +40,7 @@ def roi_align_forward(features, rois, aligned_height, aligned_width, spatial_sca
     R = rois.size(0)
     out = torch.empty((R, C, aligned_height, aligned_width), dtype=torch.float32, device=features.device)
     lib = _lib.load()
-    ws_bytes = int(lib.b200_roi_align_workspace_bytes(R, aligned_height, aligned_width, sampling_ratio))
+    ws_bytes = int(lib.b200_roi_align_workspace_bytes(N, R, H, W, aligned_height, aligned_width, sampling_ratio))
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=features.device) if ws_bytes else None   # caching allocator, stream-ordered
     with torch.cuda.device(features.device):
         _lib.check(lib.b200_roi_align_forward_ws(features.data_ptr(), spatial_scale, N, R, H, W, C, aligned_height,

@@ -66,13 +66,14 @@ B200_API int b200_roi_align_backward(const float* top_diff, float spatial_scale,
                             b200_stream_t stream);
 
 /* Workspace variant of the forward: the feature-map-stationary fast path needs
- * b200_roi_align_workspace_bytes(num_rois, aligned_height, aligned_width, sampling_ratio) bytes of
- * device scratch (per-RoI sample tables; 256-byte aligned; 0 = fast path not applicable to these
- * parameters).  The Python layer takes it from torch's caching allocator.  The plain
+ * b200_roi_align_workspace_bytes(batch_size, num_rois, height, width, aligned_height, aligned_width,
+ * sampling_ratio) bytes of device scratch (per-RoI sample tables + per-tile RoI lists; 256-byte
+ * aligned; 0 = fast path not applicable to these parameters).  The Python layer takes it from torch's caching allocator.  The plain
  * b200_roi_align_forward obtains the same scratch with cudaMallocAsync/cudaFreeAsync on `stream`.
  * With workspace == NULL (or too small) the shape-generic kernel runs.  Results are identical
  * either way up to ~1 ulp on bins whose samples straddle two tiles. */
-B200_API size_t b200_roi_align_workspace_bytes(int num_rois, int aligned_height, int aligned_width, int sampling_ratio);
+B200_API size_t b200_roi_align_workspace_bytes(int batch_size, int num_rois, int height, int width,
+                                               int aligned_height, int aligned_width, int sampling_ratio);
 B200_API int b200_roi_align_forward_ws(const float* bottom_data, float spatial_scale, int batch_size, int num_rois,
                               int height, int width, int channels, int aligned_height, int aligned_width,
                               int sampling_ratio, const float* bottom_rois, float* top_data,
