@@ -142,13 +142,14 @@ nms_scan_pipelined_kernel(const u64* __restrict__ mask, int n, int col_blocks, i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t buf_words = (size_t)kNmsTile * col_blocks;
 
-    auto prefetch = [&](int b) {                      // rows of block b, columns [b, col_blocks)
+    auto prefetch = [&](int b) {                      // rows of block b, columns [b, col_blocks): warp -> rows, lanes -> columns
         if (b < col_blocks) {
             u64* dst = ring + (size_t)(b & 1) * buf_words;
-            const int w = col_blocks - b, rows = min(kNmsTile, n - b * kNmsTile);
-            for (int e = tid; e < rows * w; e += kScanThreads) {
-                const int k = e / w, j = b + (e - k * w);
-                cp_async8(dst + (size_t)k * col_blocks + j, mask + (size_t)(b * kNmsTile + k) * col_blocks + j);
+            const int rows = min(kNmsTile, n - b * kNmsTile);
+            for (int k = warp; k < rows; k += kScanThreads / 32) {
+                const u64* src = mask + (size_t)(b * kNmsTile + k) * col_blocks;
+                u64* d = dst + (size_t)k * col_blocks;
+                for (int j = b + lane; j < col_blocks; j += 32) cp_async8(d + j, src + j);
             }
         }
         cp_async_commit();
@@ -185,15 +186,15 @@ nms_scan_pipelined_kernel(const u64* __restrict__ mask, int n, int col_blocks, i
         const int base = s_count;
         if (tid < kNmsTile && ((kept >> tid) & 1ULL))
             keep_out[base + __popcll(kept & ((1ULL << tid) - 1ULL))] = b * kNmsTile + tid;
-        const int kg = tid >> 7;                      // 8 row groups x 128 column words per pass
-        for (int j = b + 1 + (tid & 127); j < col_blocks; j += 128) {
-            u64 acc = 0;
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-                const int k = kg + 8 * kk;
-                if ((kept >> k) & 1ULL) acc |= rows[(size_t)k * col_blocks + j];
+        // one thread per later column word: OR the rows of the kept boxes (no atomics: single writer per word)
+        for (int j = b + 1 + tid; j < col_blocks; j += kScanThreads) {
+            u64 acc = 0, kk = kept;
+            while (kk) {
+                const int k = __ffsll((long long)kk) - 1;
+                kk &= kk - 1;
+                acc |= rows[(size_t)k * col_blocks + j];
             }
-            if (acc) atomicOr(&remv[j], acc);
+            remv[j] |= acc;
         }
         __syncthreads();                              // ring[b & 1] is free again; remv is complete for block b+1
         if (tid == 0) s_count = base + __popcll(kept);

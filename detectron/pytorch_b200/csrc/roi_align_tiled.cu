@@ -115,16 +115,22 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
     const int cs = lane >> 3, bb = lane & 7;              // flush mapping:   (channel within a group of 4, staged bin)
     const size_t plane = (size_t)H * W;
 
+    if (tid == 0) misc[0] = atomicAdd(work_counter, 1);
     for (;;) {
-        __syncthreads();                                  // previous item fully consumed (tile, misc)
-        if (tid == 0) { misc[0] = atomicAdd(work_counter, 1); misc[1] = 0; }
-        __syncthreads();
+        __syncthreads();                                  // misc[0] published; previous item fully consumed
         const int work = misc[0];
         if (work >= n_work) break;
+        // the NEXT item is claimed now, so the global atomic's latency hides behind this item
+        int next_work = 0;
+        if (tid == 0) { next_work = atomicAdd(work_counter, 1); misc[1] = 0; }
         const int tile_id = work / n_cgroups;             // consecutive items share a tile (same list, tables hit L2)
         const int c0 = (work - tile_id * n_cgroups) * kCG;
         const int n_list = tile_count[tile_id];
-        if (n_list == 0) continue;                        // uniform
+        if (n_list == 0) {                                // uniform: nothing samples this tile
+            __syncthreads();
+            if (tid == 0) misc[0] = next_work;
+            continue;
+        }
         const unsigned short* list = tile_list + (size_t)tile_id * R;
         const int tx = tile_id % tiles_x, ty = (tile_id / tiles_x) % tiles_y, n = tile_id / (tiles_x * tiles_y);
         const int y0 = ty * core_h, x0 = tx * core_w;
@@ -270,6 +276,8 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
                 __syncwarp();
             }
         }
+        __syncthreads();                                  // every warp has read misc[0] and is done with the tile
+        if (tid == 0) misc[0] = next_work;
     }
 }
 
