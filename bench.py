@@ -146,7 +146,8 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     lib = _lib.load()
 
     cfg = S.CFG2
@@ -190,8 +191,10 @@ def main():
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
-    def timed(fn_iter, n, graph=False):
-        """device time (ms) of n calls fn_iter(i), CUDA events on the launching stream."""
+    def timed(fn_iter, n, graph=False, collective=True):
+        """device time (ms) of n calls fn_iter(i), CUDA events on the launching stream.  `collective=False`
+        for measurements only some ranks take (no barrier: a rank-local barrier would deadlock the others)."""
+        sync = barrier if collective else torch.cuda.synchronize
         g = None
         if graph:
             side = torch.cuda.Stream()
@@ -205,7 +208,7 @@ def main():
                 for i in range(n):
                     fn_iter(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
+        sync()
         e0.record()
         if g is not None:
             g.replay()
@@ -215,7 +218,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        barrier()
+        sync()
         return ms
 
     # ---- warm-up (untimed)
@@ -241,8 +244,8 @@ def main():
 
     # ---- per-kernel launch times (rank-local, device-resident, rotating sets), for the roofline
     n_k = max(20, min(200, K))
-    ms_fwd = timed(lambda i: fwd(i % nsets), n_k, graph=use_graph) / n_k
-    ms_bwd = timed(lambda i: bwd(i % nsets), n_k, graph=use_graph) / n_k
+    ms_fwd = timed(lambda i: fwd(i % nsets), n_k, graph=use_graph, collective=False) / n_k
+    ms_bwd = timed(lambda i: bwd(i % nsets), n_k, graph=use_graph, collective=False) / n_k
     peak_gbs, peak_src = load_peaks()
     touched = benchutil.roi_align_touched_cells(rois_np[0], N, H, W, P, P, scale, sr)
     bts = benchutil.roi_align_bytes(shape, R, P, P, touched_cells=touched)
@@ -272,7 +275,7 @@ def main():
     try:
         nms_boxes = [torch.from_numpy(S.make_nms_boxes(S.CFG3["boxes"], seed=i)).to(device) for i in range(4)]
         ops.nms_raw(nms_boxes[0], S.CFG3["thresh"])
-        ms_nms = timed(lambda i: ops.nms_raw(nms_boxes[i % 4], S.CFG3["thresh"]), 40) / 40
+        ms_nms = timed(lambda i: ops.nms_raw(nms_boxes[i % 4], S.CFG3["thresh"]), 40, collective=False) / 40
         kept = int(ops.nms_raw(nms_boxes[0], S.CFG3["thresh"])[1].item())
         kernels["nms_6000"] = {"ms": ms_nms, "boxes_per_s": S.CFG3["boxes"] / (ms_nms * 1e-3), "kept": kept,
                                "informational_bytes": benchutil.nms_bytes(S.CFG3["boxes"], kept)}
@@ -291,8 +294,9 @@ def main():
                 for i in range(3):
                     ref_step(i)
                 n_r = max(10, min(50, K))
-                ms_ref = timed(ref_step, n_r) / n_r
-                ms_ref_f = timed(lambda i: G.roi_align_forward(feats[i % nsets], rois[i % nsets], P, P, scale, sr), n_r) / n_r
+                ms_ref = timed(ref_step, n_r, collective=False) / n_r
+                ms_ref_f = timed(lambda i: G.roi_align_forward(feats[i % nsets], rois[i % nsets], P, P, scale, sr), n_r,
+                                 collective=False) / n_r
                 G.nms_gpu(nms_boxes[0], S.CFG3["thresh"])
                 t0 = time.perf_counter()
                 for i in range(10):

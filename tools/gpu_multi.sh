@@ -4,16 +4,9 @@ set -u
 N=${1:-2}; TAG=${2:-multi}
 OUT=gpurun_out/$TAG; mkdir -p "$OUT"
 nvidia-smi -L > "$OUT/gpus.txt" 2>&1
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
     bench.py --gpus $N --steps 100 --warmup 5 > "$OUT/bench_n$N.json" 2> "$OUT/bench_n$N.err"; echo "bench N=$N rc=$?" | tee "$OUT/status.txt"
-cat "$OUT/bench_n$N.json" | cut -c1-700; tail -5 "$OUT/bench_n$N.err"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 \
+tail -1 "$OUT/bench_n$N.json" | cut -c1-900; tail -3 "$OUT/bench_n$N.err"
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 \
     bench.py --impl reference --gpus $N --steps 2 --warmup 1 > "$OUT/bench_ref_n$N.json" 2>> "$OUT/bench_n$N.err"; echo "bench-ref N=$N rc=$?" | tee -a "$OUT/status.txt"
-cat "$OUT/bench_ref_n$N.json" | cut -c1-300
-python bench.py --steps 100 --warmup 5 > "$OUT/bench_n1.json" 2>> "$OUT/bench_n$N.err"; echo "bench N=1 rc=$?" | tee -a "$OUT/status.txt"
-python -c "
-import json
-a=json.load(open('$OUT/bench_n1.json')); b=json.load(open('$OUT/bench_n$N.json'))
-print('N=1', a['value'], 'N=$N', b['value'], 'ratio', b['value']/a['value'])
-print('fwd', a['kernels']['fwd']['ms'], 'bwd', a['kernels']['bwd']['ms'], 'nms', a['kernels']['nms_6000'])
-"
+tail -1 "$OUT/bench_ref_n$N.json" | cut -c1-300
