@@ -188,9 +188,25 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
             if (lane < nx) pre_x = g_xtab[(size_t)r * nx + lane];
         }
         while (item < n_list) {
+            // Tile-local tables of this RoI: every lane converts its own axis sample into
+            // {shared-memory offset of the low cell (words), weight of the high cell, weight of the low cell};
+            // samples that are not this tile's (low cell outside the core) or that the reference skips (outside
+            // the map) get offset 0 and zero weights, so the inner loop needs no checks: they contribute +0.
+            bool in_y = false, in_x = false;
+            AxisEntry ty_e, tx_e;
+            ty_e.low = 0; ty_e.valid = 0; ty_e.l = 0.f; ty_e.h = 0.f;
+            tx_e = ty_e;
+            if (lane < ny) {
+                in_y = pre_y.low >= y0 && pre_y.low < y_end;
+                if (in_y && pre_y.valid) { ty_e.low = (pre_y.low - y0) * (kTX * kCellWords); ty_e.l = pre_y.l; ty_e.h = pre_y.h; }
+            }
+            if (lane < nx) {
+                in_x = pre_x.low >= x0 && pre_x.low < x_end;
+                if (in_x && pre_x.valid) { tx_e.low = (pre_x.low - x0) * kCellWords; tx_e.l = pre_x.l; tx_e.h = pre_x.h; }
+            }
             __syncwarp();
-            if (lane < ny) wy[lane] = pre_y;
-            if (lane < nx) wx[lane] = pre_x;
+            if (lane < ny) wy[lane] = ty_e;
+            if (lane < nx) wx[lane] = tx_e;
             __syncwarp();
             const int r_cur = r;
             if (lane == 0) item = atomicAdd(&misc[1], 1);
@@ -200,58 +216,50 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
                 if (lane < ny) pre_y = g_ytab[(size_t)r * ny + lane];
                 if (lane < nx) pre_x = g_xtab[(size_t)r * nx + lane];
             }
-            // samples of this RoI that live in this tile: contiguous index ranges (bit masks my / mx);
-            // uy / ux additionally drop the samples the reference skips (outside the map)
-            bool in_y = false, in_x = false, ok_y = false, ok_x = false;
-            if (lane < ny) { const AxisEntry e = wy[lane]; in_y = e.low >= y0 && e.low < y_end; ok_y = in_y && e.valid; }
-            if (lane < nx) { const AxisEntry e = wx[lane]; in_x = e.low >= x0 && e.low < x_end; ok_x = in_x && e.valid; }
+            // samples of this RoI whose low cell lies in this tile's core: contiguous index ranges (bit masks)
             const unsigned my = __ballot_sync(0xffffffffu, in_y), mx = __ballot_sync(0xffffffffu, in_x);
-            const unsigned uy = __ballot_sync(0xffffffffu, ok_y), ux = __ballot_sync(0xffffffffu, ok_x);
             if (my == 0u || mx == 0u) continue;
             const int ph0 = (__ffs(my) - 1) / SR, ph1 = (31 - __clz(my)) / SR + 1;
             const int pw0 = (__ffs(mx) - 1) / SR, pw1 = (31 - __clz(mx)) / SR + 1;
             const int npw = pw1 - pw0, nb = (ph1 - ph0) * npw;
             const unsigned div_m = 65536u / (unsigned)npw + 1u;          // b / npw == (b * div_m) >> 16 for b < 1024
             float* out_r = out + (size_t)r_cur * C * bins + (size_t)c0 * bins;
+            const float* tbase = tile + 4 * i;
 
             for (int kb = 0; kb < nb; kb += kStageBins) {
 #pragma unroll
                 for (int jj = 0; jj < kStageBins / 4; ++jj) {
                     const int b = kb + jj * 4 + q;
+                    const int bc = min(b, nb - 1);                   // lanes past the end recompute the last bin, unstored
+                    const int dph = (int)(((unsigned)bc * div_m) >> 16);
+                    const int sy = (ph0 + dph) * SR, sx = (pw0 + (bc - dph * npw)) * SR;
+                    u64x acc_lo = 0ull, acc_hi = 0ull;               // channels (0,1) and (2,3) of this lane's group
+#pragma unroll
+                    for (int iy = 0; iy < SR; ++iy) {
+                        const AxisEntry ey = wy[sy + iy];
+#pragma unroll
+                        for (int ix = 0; ix < SR; ++ix) {
+                            const AxisEntry ex = wx[sx + ix];
+                            const float w1 = __fmul_rn(ey.h, ex.h), w2 = __fmul_rn(ey.h, ex.l);
+                            const float w3 = __fmul_rn(ey.l, ex.h), w4 = __fmul_rn(ey.l, ex.l);
+                            const u64x W1 = pack2(w1, w1), W2 = pack2(w2, w2), W3 = pack2(w3, w3), W4 = pack2(w4, w4);
+                            const float* p = tbase + (ey.low + ex.low);
+                            const ulonglong2 v1 = lds128(p), v2 = lds128(p + kCellWords);
+                            const ulonglong2 v3 = lds128(p + kTX * kCellWords), v4 = lds128(p + (kTX + 1) * kCellWords);
+                            // val = FFMA(v4,w4, FFMA(v3,w3, FFMA(v1,w1, FMUL(v2,w2))));  acc += val   (reference order)
+                            acc_lo = add2(acc_lo, fma2(v4.x, W4, fma2(v3.x, W3, fma2(v1.x, W1, mul2(v2.x, W2)))));
+                            acc_hi = add2(acc_hi, fma2(v4.y, W4, fma2(v3.y, W3, fma2(v1.y, W1, mul2(v2.y, W2)))));
+                        }
+                    }
+                    float a0, a1, a2, a3;
+                    unpack2(acc_lo, a0, a1); unpack2(acc_hi, a2, a3);
+                    if (SR == 3) {        // count 9: a true division, like the reference's `output_val /= count`
+                        a0 = __fdiv_rn(a0, kCount); a1 = __fdiv_rn(a1, kCount); a2 = __fdiv_rn(a2, kCount); a3 = __fdiv_rn(a3, kCount);
+                    } else {              // count 1 / 4 / 16: multiplying by the reciprocal is exact
+                        a0 = __fmul_rn(a0, 1.f / kCount); a1 = __fmul_rn(a1, 1.f / kCount);
+                        a2 = __fmul_rn(a2, 1.f / kCount); a3 = __fmul_rn(a3, 1.f / kCount);
+                    }
                     if (b < nb) {
-                        const int dph = (int)(((unsigned)b * div_m) >> 16);
-                        const int ph = ph0 + dph, pw = pw0 + (b - dph * npw);
-                        u64x acc_lo = 0ull, acc_hi = 0ull;           // channels (0,1) and (2,3) of this lane's group
-#pragma unroll
-                        for (int iy = 0; iy < SR; ++iy) {
-                            const int s_y = ph * SR + iy;
-                            if (!((uy >> s_y) & 1u)) continue;
-                            const AxisEntry ey = wy[s_y];
-                            const int row_off = ((ey.low - y0) * kTX - x0) * kCellWords + 4 * i;
-#pragma unroll
-                            for (int ix = 0; ix < SR; ++ix) {
-                                const int s_x = pw * SR + ix;
-                                if (!((ux >> s_x) & 1u)) continue;
-                                const AxisEntry ex = wx[s_x];
-                                const float w1 = __fmul_rn(ey.h, ex.h), w2 = __fmul_rn(ey.h, ex.l);
-                                const float w3 = __fmul_rn(ey.l, ex.h), w4 = __fmul_rn(ey.l, ex.l);
-                                const u64x W1 = pack2(w1, w1), W2 = pack2(w2, w2), W3 = pack2(w3, w3), W4 = pack2(w4, w4);
-                                const float* p = tile + (row_off + ex.low * kCellWords);
-                                const ulonglong2 v1 = lds128(p), v2 = lds128(p + kCellWords);
-                                const ulonglong2 v3 = lds128(p + kTX * kCellWords), v4 = lds128(p + (kTX + 1) * kCellWords);
-                                // val = FFMA(v4,w4, FFMA(v3,w3, FFMA(v1,w1, FMUL(v2,w2))));  acc += val   (reference order)
-                                acc_lo = add2(acc_lo, fma2(v4.x, W4, fma2(v3.x, W3, fma2(v1.x, W1, mul2(v2.x, W2)))));
-                                acc_hi = add2(acc_hi, fma2(v4.y, W4, fma2(v3.y, W3, fma2(v1.y, W1, mul2(v2.y, W2)))));
-                            }
-                        }
-                        float a0, a1, a2, a3;
-                        unpack2(acc_lo, a0, a1); unpack2(acc_hi, a2, a3);
-                        if (SR == 3) {        // count 9: a true division, like the reference's `output_val /= count`
-                            a0 = __fdiv_rn(a0, kCount); a1 = __fdiv_rn(a1, kCount); a2 = __fdiv_rn(a2, kCount); a3 = __fdiv_rn(a3, kCount);
-                        } else {              // count 1 / 4 / 16: multiplying by the reciprocal is exact
-                            a0 = __fmul_rn(a0, 1.f / kCount); a1 = __fmul_rn(a1, 1.f / kCount);
-                            a2 = __fmul_rn(a2, 1.f / kCount); a3 = __fmul_rn(a3, 1.f / kCount);
-                        }
                         float* st = stage + (4 * i) * kStageWords + jj * 4 + q;       // [channel][bin]
                         st[0] = a0; st[kStageWords] = a1; st[2 * kStageWords] = a2; st[3 * kStageWords] = a3;
                     }
@@ -263,14 +271,17 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
                     const int dph = (int)(((unsigned)b * div_m) >> 16);
                     const int ph = ph0 + dph, pw = pw0 + (b - dph * npw);
                     const bool whole = (((my >> (ph * SR)) & kFull) == kFull) && (((mx >> (pw * SR)) & kFull) == kFull);
-                    float* dst = out_r + ph * PW + pw;
+                    float* dst = out_r + ph * PW + pw + (size_t)cs * bins;
+                    const float* src = stage + cs * kStageWords + bb;
+                    const int cmax = C - c0 - cs;                   // channel c = 4*cb + cs is real iff 4*cb < cmax
+                    if (whole) {
 #pragma unroll
-                    for (int cb = 0; cb < kCG / 4; ++cb) {
-                        const int c = cb * 4 + cs;
-                        if (c0 + c < C) {
-                            const float v = stage[c * kStageWords + bb];
-                            if (whole) dst[(size_t)c * bins] = v; else atomicAdd(dst + (size_t)c * bins, v);
-                        }
+                        for (int cb = 0; cb < kCG / 4; ++cb)
+                            if (4 * cb < cmax) dst[(size_t)(4 * cb) * bins] = src[4 * cb * kStageWords];
+                    } else {
+#pragma unroll
+                        for (int cb = 0; cb < kCG / 4; ++cb)
+                            if (4 * cb < cmax) atomicAdd(dst + (size_t)(4 * cb) * bins, src[4 * cb * kStageWords]);
                     }
                 }
                 __syncwarp();
