@@ -186,15 +186,26 @@ nms_scan_pipelined_kernel(const u64* __restrict__ mask, int n, int col_blocks, i
         const int base = s_count;
         if (tid < kNmsTile && ((kept >> tid) & 1ULL))
             keep_out[base + __popcll(kept & ((1ULL << tid) - 1ULL))] = b * kNmsTile + tid;
-        // one thread per later column word: OR the rows of the kept boxes (no atomics: single writer per word)
-        for (int j = b + 1 + tid; j < col_blocks; j += kScanThreads) {
-            u64 acc = 0, kk = kept;
-            while (kk) {
-                const int k = __ffsll((long long)kk) - 1;
-                kk &= kk - 1;
-                acc |= rows[(size_t)k * col_blocks + j];
+        // OR the rows of the kept boxes into the later column words.  lane = (column of a group of 4, row group of 8):
+        // every lane ORs <= 8 rows of its residue class, the 8 partials of a column are combined with shuffles,
+        // and one lane updates remv[j] (single writer per word, no atomics).  32 warps cover 128 columns per pass.
+        {
+            const int kg = lane & 7, jl = lane >> 3;
+            for (int j0 = b + 1 + warp * 4; j0 < col_blocks; j0 += (kScanThreads / 32) * 4) {
+                const int j = j0 + jl;
+                u64 acc = 0;
+                if (j < col_blocks) {
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const int k = kg + 8 * kk;
+                        if ((kept >> k) & 1ULL) acc |= rows[(size_t)k * col_blocks + j];
+                    }
+                }
+                acc |= __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc |= __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc |= __shfl_xor_sync(0xffffffffu, acc, 4);
+                if (kg == 0 && j < col_blocks && acc) remv[j] |= acc;
             }
-            remv[j] |= acc;
         }
         __syncthreads();                              // ring[b & 1] is free again; remv is complete for block b+1
         if (tid == 0) s_count = base + __popcll(kept);

@@ -101,15 +101,15 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);
     AxisEntry* wtab_all = reinterpret_cast<AxisEntry*>(smem_raw + (size_t)kTX * tile_h * kCellWords * 4);
-    float* stage_all = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wtab_all) + (size_t)kWarps * 2 * kAxisMax * 16);
+    float* stage_all = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wtab_all) + (size_t)kWarps * (ny + nx) * 16);
     int* misc = reinterpret_cast<int*>(stage_all + kWarps * kCG * kStageWords);   // [0]=work item, [1]=next RoI of the list
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bins = PH * PW;
     constexpr float kCount = (float)(SR * SR);
     constexpr unsigned kFull = (1u << SR) - 1u;
-    AxisEntry* wy = wtab_all + warp * 2 * kAxisMax;
-    AxisEntry* wx = wy + kAxisMax;
+    AxisEntry* wy = wtab_all + warp * (ny + nx);
+    AxisEntry* wx = wy + ny;
     float* stage = stage_all + warp * kCG * kStageWords;
     const int q = lane >> 3, i = lane & 7;                // compute mapping: (bin of the 4-bin group, 4-channel group)
     const int cs = lane >> 3, bb = lane & 7;              // flush mapping:   (channel within a group of 4, staged bin)
@@ -137,31 +137,32 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
         const int y_end = y0 + core_h, x_end = x0 + core_w;      // core = [y0, y_end) x [x0, x_end)
 
         // ---- stage the tile: rows [y0, y0+tile_h) x cols [x0, x0+32) x channels [c0, c0+32), zero outside the map.
-        // Warp w stages channel quad w of every row; loads are branch-free (addresses clamped into the tensor,
-        // invalid lanes zeroed afterwards) and issued kRowsPerBatch rows = 4*kRowsPerBatch independent
-        // 128-byte-coalesced loads at a time, so ~28 loads per thread are in flight.
+        // Loads are branch-free (addresses clamped into the tensor, invalid lanes zeroed afterwards) and issued
+        // kRowsPerBatch rows = 4*kRowsPerBatch independent 128-byte-coalesced loads at a time (20 per thread,
+        // x 1024 resident threads per SM in flight).
         {
-            constexpr int kRowsPerBatch = 7;
+            // 16 warps: warp w stages channel quad (w & 7) of the rows of parity (w >> 3)
+            constexpr int kRowsPerBatch = 5;
             const int x = x0 + lane;
             const bool x_ok = x < W;
-            const int cq = c0 + 4 * warp;
+            const int cq = c0 + 4 * (warp & 7);
             const bool ch0 = cq < C, ch1 = cq + 1 < C, ch2 = cq + 2 < C, ch3 = cq + 3 < C;
             const float* base = bottom + (size_t)n * C * plane + min(x, W - 1);
             const float* p0 = base + (size_t)min(cq, C - 1) * plane;
             const float* p1 = base + (size_t)min(cq + 1, C - 1) * plane;
             const float* p2 = base + (size_t)min(cq + 2, C - 1) * plane;
             const float* p3 = base + (size_t)min(cq + 3, C - 1) * plane;
-            float* dst = tile + (size_t)lane * kCellWords + 4 * warp;
-            for (int k0 = 0; k0 < tile_h; k0 += kRowsPerBatch) {
+            float* dst = tile + (size_t)lane * kCellWords + 4 * (warp & 7);
+            for (int k0 = (warp >> 3); k0 < tile_h; k0 += 2 * kRowsPerBatch) {
                 float4 v[kRowsPerBatch];
 #pragma unroll
                 for (int bq = 0; bq < kRowsPerBatch; ++bq) {
-                    const size_t off = (size_t)min(y0 + k0 + bq, H - 1) * W;
+                    const size_t off = (size_t)min(y0 + k0 + 2 * bq, H - 1) * W;
                     v[bq].x = __ldg(p0 + off); v[bq].y = __ldg(p1 + off); v[bq].z = __ldg(p2 + off); v[bq].w = __ldg(p3 + off);
                 }
 #pragma unroll
                 for (int bq = 0; bq < kRowsPerBatch; ++bq) {
-                    const int row = k0 + bq;
+                    const int row = k0 + 2 * bq;
                     if (row < tile_h) {
                         const bool ok = x_ok && (y0 + row < H);
                         float4 o;

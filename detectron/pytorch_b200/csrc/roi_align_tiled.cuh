@@ -9,7 +9,7 @@ namespace b200 {
 constexpr int kTX = 32;                 // tile width in cells (one warp-wide row access)
 constexpr int kCG = 32;                 // channels per work item
 constexpr int kCellWords = kCG + 4;     // 36 words = 144 B per cell: the pad makes the transposing 128-bit shared accesses conflict-free
-constexpr int kTiledThreads = 256;
+constexpr int kTiledThreads = 512;      // 16 warps; two CTAs per SM = 32 resident warps (<= 64 registers / thread)
 constexpr int kWarps = kTiledThreads / 32;
 constexpr int kAxisMax = 32;            // P * sampling_ratio per axis supported by the tiled paths
 constexpr int kStageBins = 8;           // bins staged per warp between compute and global memory
@@ -45,9 +45,9 @@ struct TiledPlan {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// shared memory of a work item: [tile][per-warp axis tables][per-warp staging][misc]
-__host__ __device__ inline size_t tiled_smem_bytes(int tile_h) {
-    return (size_t)kTX * tile_h * kCellWords * 4 + (size_t)kWarps * 2 * kAxisMax * 16 +
+// shared memory of a work item: [tile][per-warp axis tables (ny + nx entries)][per-warp staging][misc]
+__host__ __device__ inline size_t tiled_smem_bytes(int tile_h, int ny, int nx) {
+    return (size_t)kTX * tile_h * kCellWords * 4 + (size_t)kWarps * (ny + nx) * 16 +
            (size_t)kWarps * kCG * kStageWords * 4 + 64;
 }
 
@@ -59,7 +59,7 @@ static inline bool roi_align_tiled_plan(int N, int R, int H, int W, int C, int P
     p->ny = PH * sr; p->nx = PW * sr;
     const size_t budget = 113 * 1024;               // two work items resident per SM: (228 KB - 2 x 1 KB) / 2
     int th = 64;
-    while (th > 4 && tiled_smem_bytes(th) > budget) --th;
+    while (th > 4 && tiled_smem_bytes(th, p->ny, p->nx) > budget) --th;
     if (th <= 4) return false;
     int core_h = th - 1;
     int tiles_y = (H + core_h - 1) / core_h;
@@ -68,7 +68,7 @@ static inline bool roi_align_tiled_plan(int N, int R, int H, int W, int C, int P
     p->core_w = kTX - 1; p->tiles_x = (W + p->core_w - 1) / p->core_w;
     if ((long long)N * tiles_y * p->tiles_x > (1 << 20)) return false;
     p->tiles_total = N * tiles_y * p->tiles_x;
-    p->smem_bytes = tiled_smem_bytes(p->tile_h);
+    p->smem_bytes = tiled_smem_bytes(p->tile_h, p->ny, p->nx);
     size_t off = 0;
     p->hdr_off = off;  off = align_up(off + (size_t)R * sizeof(RoiHeader), 256);
     p->ytab_off = off; off = align_up(off + (size_t)R * p->ny * sizeof(AxisEntry), 256);
