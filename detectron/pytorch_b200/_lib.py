@@ -19,6 +19,7 @@ _SIGNATURES = {
     "b200_roi_ops_abi_version": (ctypes.c_int, []),
     "b200_roi_ops_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "b200_roi_ops_launch_count": (ctypes.c_ulonglong, []),
+    "b200_roi_ops_debug_timing_buffer": (None, [ctypes.c_void_p]),
     # (bottom, scale, N, R, H, W, C, PH, PW, sr, rois, top, stream)
     "b200_roi_align_forward": (ctypes.c_int, [_c_float_p, ctypes.c_float] + [ctypes.c_int] * 8 + [_c_float_p, _c_float_p, _stream_t]),
     "b200_roi_align_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 7),

@@ -30,6 +30,10 @@
 
 namespace b200 {
 
+// Optional phase timing (tools/fwd_phase_probe.py): when a buffer is registered, lane 0 of every warp adds
+// its clock64 deltas per phase.  Null by default: one predictable branch per work item.
+__device__ unsigned long long* g_fwd_timing = nullptr;
+
 // ------------------------------------------------------------------------------------------------
 // prepass
 // ------------------------------------------------------------------------------------------------
@@ -123,6 +127,9 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
         // the NEXT item is claimed now, so the global atomic's latency hides behind this item
         int next_work = 0;
         if (tid == 0) { next_work = atomicAdd(work_counter, 1); misc[1] = 0; }
+        unsigned long long* const timing = g_fwd_timing;
+        long long t_start = 0, t_staged = 0, t_done = 0;
+        if (timing) t_start = clock64();
         const int tile_id = work / n_cgroups;             // consecutive items share a tile (same list, tables hit L2)
         const int c0 = (work - tile_id * n_cgroups) * kCG;
         const int n_list = tile_count[tile_id];
@@ -174,6 +181,8 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
             }
         }
         __syncthreads();
+        if (timing) t_staged = clock64();
+        int n_items = 0, n_kb = 0;
 
         // ---- warps pull RoIs of this tile; the axis tables of the NEXT RoI are fetched into registers
         //      while the current one is processed
@@ -226,8 +235,10 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
             const unsigned div_m = 65536u / (unsigned)npw + 1u;          // b / npw == (b * div_m) >> 16 for b < 1024
             float* out_r = out + (size_t)r_cur * C * bins + (size_t)c0 * bins;
             const float* tbase = tile + 4 * i;
+            ++n_items;
 
             for (int kb = 0; kb < nb; kb += kStageBins) {
+                ++n_kb;
 #pragma unroll
                 for (int jj = 0; jj < kStageBins / 4; ++jj) {
                     const int b = kb + jj * 4 + q;
@@ -288,9 +299,23 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
                 __syncwarp();
             }
         }
+        if (timing) t_done = clock64();
         __syncthreads();                                  // every warp has read misc[0] and is done with the tile
+        if (timing && lane == 0) {
+            atomicAdd(&timing[0], (unsigned long long)(t_staged - t_start));
+            atomicAdd(&timing[1], (unsigned long long)(t_done - t_staged));
+            atomicAdd(&timing[2], (unsigned long long)(clock64() - t_done));
+            atomicAdd(&timing[3], 1ull);
+            atomicAdd(&timing[4], (unsigned long long)n_items);
+            atomicAdd(&timing[5], (unsigned long long)n_kb);
+            atomicMax(&timing[6], (unsigned long long)(t_done - t_staged));
+        }
         if (tid == 0) misc[0] = next_work;
     }
+}
+
+void roi_align_tiled_set_timing_buffer(unsigned long long* buf) {
+    cudaMemcpyToSymbol(g_fwd_timing, &buf, sizeof(buf));
 }
 
 size_t roi_align_tiled_workspace_bytes(int N, int R, int H, int W, int PH, int PW, int sr) {

@@ -145,6 +145,9 @@ B200_API int b200_nms(const float* boxes_dev, int boxes_num, int boxes_dim, floa
 /* ---- introspection used by the benchmark / tests (no compute) ----------------------------------
  * Number of kernel launches the library has enqueued since load (all entry points). */
 B200_API unsigned long long b200_roi_ops_launch_count(void);
+/* Debug: register (or clear with NULL) a device buffer of 8 x uint64 into which the tiled RoIAlign forward
+ * adds per-warp clock64 deltas [staging, compute, end-of-item wait, warp-items, RoI items, 8-bin groups, max compute]. */
+B200_API void b200_roi_ops_debug_timing_buffer(void* device_u64x8);
 
 #ifdef __cplusplus
 }
