@@ -41,8 +41,9 @@ __global__ void __launch_bounds__(128)
 roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int R, int C, int H, int W, int PH, int PW, int sr,
                      int ny, int nx, int core_h, int core_w, int tiles_y, int tiles_x,
                      RoiHeader* __restrict__ hdr, AxisEntry* __restrict__ ytab, AxisEntry* __restrict__ xtab,
-                     int* __restrict__ tile_count, unsigned short* __restrict__ tile_list, float* __restrict__ out) {
+                     int* __restrict__ tile_count, unsigned* __restrict__ tile_list, int groups_max, float* __restrict__ out) {
     __shared__ int s_ty[kAxisMax], s_tx[kAxisMax];
+    __shared__ int s_nbin_y[kAxisMax], s_nbin_x[kAxisMax];     // bin rows / cols this RoI has in tile row ty0+k / col tx0+k
     __shared__ unsigned short s_split[kAxisMax * kAxisMax];
     __shared__ int s_nsplit;
     const int r = blockIdx.x;
@@ -67,12 +68,31 @@ roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int R, 
         h.pad0 = h.pad1 = h.pad2 = 0;
         hdr[r] = h;
     }
+    // Work entries: one per (tile, 8-bin group of this RoI in that tile), so that no warp of the main kernel is
+    // ever stuck with more than 8 bins while its CTA waits.  The bin rectangle of a tile is derived exactly as
+    // the main kernel derives it: [first sample in tile / sr, last sample in tile / sr] per axis.
+    const int nty = ty1 - ty0 + 1, ntx = tx1 - tx0 + 1;
+    if (t < nty + ntx) {
+        const bool isy = t < nty;
+        const int want = isy ? ty0 + t : tx0 + (t - nty);
+        const int* arr = isy ? s_ty : s_tx;
+        const int cnt = isy ? ny : nx;
+        int first = -1, last = -1;
+        for (int s = 0; s < cnt; ++s) if (arr[s] == want) { if (first < 0) first = s; last = s; }
+        const int nbin = first < 0 ? 0 : last / sr - first / sr + 1;
+        if (isy) s_nbin_y[t] = nbin; else s_nbin_x[t - nty] = nbin;
+    }
+    __syncthreads();
     if (batch_ok) {
-        const int nty = ty1 - ty0 + 1, ntx = tx1 - tx0 + 1;
         for (int k = t; k < nty * ntx; k += blockDim.x) {
-            const int tile = (g.batch * tiles_y + ty0 + k / ntx) * tiles_x + tx0 + k % ntx;
-            const int pos = atomicAdd(&tile_count[tile], 1);
-            tile_list[(size_t)tile * R + pos] = (unsigned short)r;
+            const int ky = k / ntx, kx = k - ky * ntx;
+            const int nb = s_nbin_y[ky] * s_nbin_x[kx];
+            if (nb == 0) continue;
+            const int ngroups = (nb + kStageBins - 1) / kStageBins;
+            const int tile = (g.batch * tiles_y + ty0 + ky) * tiles_x + tx0 + kx;
+            const int pos = atomicAdd(&tile_count[tile], ngroups);
+            unsigned* dst = tile_list + (size_t)tile * R * groups_max + pos;
+            for (int gI = 0; gI < ngroups; ++gI) dst[gI] = (unsigned)r | ((unsigned)gI << 16);
         }
     }
     // bins the main kernel accumulates into (their samples straddle tiles) or never visits (bad batch index)
@@ -99,7 +119,7 @@ template <int SR>
 __global__ void __launch_bounds__(kTiledThreads, 2)
 roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restrict__ g_ytab, const AxisEntry* __restrict__ g_xtab,
                     int* __restrict__ work_counter, const int* __restrict__ tile_count,
-                    const unsigned short* __restrict__ tile_list, float* __restrict__ out,
+                    const unsigned* __restrict__ tile_list, int list_stride, float* __restrict__ out,
                     int N, int R, int C, int H, int W, int PH, int PW, int ny, int nx,
                     int core_h, int core_w, int tile_h, int tiles_y, int tiles_x, int n_cgroups, int n_work) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -138,7 +158,7 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
             if (tid == 0) misc[0] = next_work;
             continue;
         }
-        const unsigned short* list = tile_list + (size_t)tile_id * R;
+        const unsigned* list = tile_list + (size_t)tile_id * list_stride;
         const int tx = tile_id % tiles_x, ty = (tile_id / tiles_x) % tiles_y, n = tile_id / (tiles_x * tiles_y);
         const int y0 = ty * core_h, x0 = tx * core_w;
         const int y_end = y0 + core_h, x_end = x0 + core_w;      // core = [y0, y_end) x [x0, x_end)
@@ -191,9 +211,10 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
         item = __shfl_sync(0xffffffffu, item, 0);
         AxisEntry pre_y, pre_x;
         pre_y.low = pre_x.low = 0; pre_y.valid = pre_x.valid = 0; pre_y.l = pre_y.h = pre_x.l = pre_x.h = 0.f;
-        int r = 0;
+        unsigned entry = 0;
         if (item < n_list) {
-            r = list[item];
+            entry = list[item];
+            const int r = entry & 0xffffu;
             if (lane < ny) pre_y = g_ytab[(size_t)r * ny + lane];
             if (lane < nx) pre_x = g_xtab[(size_t)r * nx + lane];
         }
@@ -218,11 +239,12 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
             if (lane < ny) wy[lane] = ty_e;
             if (lane < nx) wx[lane] = tx_e;
             __syncwarp();
-            const int r_cur = r;
+            const int r_cur = entry & 0xffffu, kb = (int)(entry >> 16) * kStageBins;
             if (lane == 0) item = atomicAdd(&misc[1], 1);
             item = __shfl_sync(0xffffffffu, item, 0);
             if (item < n_list) {
-                r = list[item];
+                entry = list[item];
+                const int r = entry & 0xffffu;
                 if (lane < ny) pre_y = g_ytab[(size_t)r * ny + lane];
                 if (lane < nx) pre_x = g_xtab[(size_t)r * nx + lane];
             }
@@ -236,8 +258,7 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
             float* out_r = out + (size_t)r_cur * C * bins + (size_t)c0 * bins;
             const float* tbase = tile + 4 * i;
             ++n_items;
-
-            for (int kb = 0; kb < nb; kb += kStageBins) {
+            if (kb < nb) {                                   // always true for entries the prepass wrote
                 ++n_kb;
 #pragma unroll
                 for (int jj = 0; jj < kStageBins / 4; ++jj) {
@@ -337,7 +358,7 @@ int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int 
     int* zero = (int*)(ws + p.zero_off);
     int* work_counter = zero;
     int* tile_count = zero + 4;
-    unsigned short* tile_list = (unsigned short*)(ws + p.tile_list_off);
+    unsigned* tile_list = (unsigned*)(ws + p.tile_list_off);
 
     static bool attr_set[64] = {false};     // per device: the attribute lives in the device's context
     static int sm_count[64] = {0};
@@ -355,13 +376,14 @@ int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int 
     cudaError_t err = cudaMemsetAsync(zero, 0, p.zero_bytes, stream);
     if (err != cudaSuccess) return (int)err;
     roi_align_tiled_prep<<<R, 128, 0, stream>>>(rois, scale, N, R, C, H, W, PH, PW, sr, p.ny, p.nx, p.core_h, p.core_w,
-                                               p.tiles_y, p.tiles_x, hdr, ytab, xtab, tile_count, tile_list, top);
+                                               p.tiles_y, p.tiles_x, hdr, ytab, xtab, tile_count, tile_list, p.groups_max, top);
     const int n_cgroups = (C + kCG - 1) / kCG;
     const int n_work = p.tiles_total * n_cgroups;
     const int grid = n_work < 2 * sm_count[dev] ? n_work : 2 * sm_count[dev];      // persistent: two CTAs per SM
 #define B200_LAUNCH_TILED(SRV)                                                                                              \
     roi_align_tiled_fwd<SRV><<<grid, kTiledThreads, p.smem_bytes, stream>>>(bottom, ytab, xtab, work_counter, tile_count,   \
-        tile_list, top, N, R, C, H, W, PH, PW, p.ny, p.nx, p.core_h, p.core_w, p.tile_h, p.tiles_y, p.tiles_x, n_cgroups, n_work)
+        tile_list, R * p.groups_max, top, N, R, C, H, W, PH, PW, p.ny, p.nx, p.core_h, p.core_w, p.tile_h, p.tiles_y, p.tiles_x, \
+        n_cgroups, n_work)
     switch (sr) {
         case 1: B200_LAUNCH_TILED(1); break;
         case 2: B200_LAUNCH_TILED(2); break;

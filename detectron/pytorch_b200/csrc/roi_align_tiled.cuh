@@ -37,7 +37,8 @@ struct TiledPlan {
     // workspace sections (byte offsets)
     size_t hdr_off, ytab_off, xtab_off;
     size_t zero_off, zero_bytes;        // block that must be zero at kernel start: [work counter][overflow count][tile counts][row counts]
-    size_t tile_list_off;               // ushort [tiles_total][R]
+    int groups_max;                     // 8-bin groups one RoI can contribute to one tile = ceil(PH*PW / 8)
+    size_t tile_list_off;               // uint32 [tiles_total][R * groups_max]: RoI index | (8-bin group << 16)
     size_t row_list_off;                // backward: uint32 [tiles_total * core_h][kRowCap]
     size_t overflow_off;                // backward: uint2  [R * ny * tiles_x]
     size_t ws_bytes;
@@ -76,7 +77,8 @@ static inline bool roi_align_tiled_plan(int N, int R, int H, int W, int C, int P
     p->zero_off = off;
     p->zero_bytes = align_up(sizeof(int) * (size_t)(4 + p->tiles_total + (backward ? p->tiles_total * core_h : 0)), 256);
     off += p->zero_bytes;
-    p->tile_list_off = off; off = align_up(off + (size_t)p->tiles_total * R * sizeof(unsigned short), 256);
+    p->groups_max = (PH * PW + kStageBins - 1) / kStageBins;
+    p->tile_list_off = off; off = align_up(off + (size_t)p->tiles_total * R * p->groups_max * sizeof(unsigned), 256);
     p->row_list_off = off;
     p->overflow_off = off;
     if (backward) {
