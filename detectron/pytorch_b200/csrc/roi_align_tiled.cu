@@ -30,9 +30,14 @@
 
 namespace b200 {
 
-// Optional phase timing (tools/fwd_phase_probe.py): when a buffer is registered, lane 0 of every warp adds
-// its clock64 deltas per phase.  Null by default: one predictable branch per work item.
+// Optional phase timing (tools/fwd_phase_probe.py; build with -DB200_FWD_TIMING): when a buffer is registered,
+// lane 0 of every warp adds its clock64 deltas per phase.  Compiled out by default (it costs registers).
 __device__ unsigned long long* g_fwd_timing = nullptr;
+#ifdef B200_FWD_TIMING
+#define B200_TIMING_PTR g_fwd_timing
+#else
+#define B200_TIMING_PTR ((unsigned long long*)nullptr)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // prepass
@@ -147,7 +152,7 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
         // the NEXT item is claimed now, so the global atomic's latency hides behind this item
         int next_work = 0;
         if (tid == 0) { next_work = atomicAdd(work_counter, 1); misc[1] = 0; }
-        unsigned long long* const timing = g_fwd_timing;
+        unsigned long long* const timing = B200_TIMING_PTR;
         long long t_start = 0, t_staged = 0, t_done = 0;
         if (timing) t_start = clock64();
         const int tile_id = work / n_cgroups;             // consecutive items share a tile (same list, tables hit L2)

@@ -21,7 +21,7 @@ if [ "$MODE" = "full" ]; then
   python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference.json" 2>> "$OUT/bench.err"; echo "bench-ref rc=$?" | tee -a "$OUT/status.txt"
   cat "$OUT/bench_reference.json"
 fi
-echo "== phase probe"; python tools/fwd_phase_probe.py > "$OUT/fwd_phase.txt" 2>&1; cat "$OUT/fwd_phase.txt"
+echo "== phase probe (needs B200_NVCC_EXTRA=-DB200_FWD_TIMING build)"
 echo "== ubench"; true
 echo "== ncu nms"; ncu --set full --clock-control none --import-source on -k regex:nms_scan -s 2 -c 1 -o "$OUT/prof_nms" -f python tools/nms_probe.py > "$OUT/ncu_nms.log" 2>&1; tail -2 "$OUT/ncu_nms.log"
 echo "== ncu launch list"
