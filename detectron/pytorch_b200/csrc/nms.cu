@@ -12,6 +12,7 @@
 // 1024 threads OR the kept rows into the running removal words) instead of a 4.5 MB blocking D2H
 // copy + single-threaded CPU loop + H2D; no cudaMalloc/cudaFree: scratch comes from the caller.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -216,6 +217,129 @@ nms_scan_pipelined_kernel(const u64* __restrict__ mask, int n, int col_blocks, i
     if (tid == 0) *num_out = s_count;
 }
 
+// Decoupled scan: the greedy chain is carried by ONE warp (the resolver); the other 31 warps (workers) prefetch
+// mask rows and fold the kept rows into the removal words in the background.  Per 64-box block the resolver
+// only (1) waits for the block's rows (prefetched two blocks ahead) and for the workers to have folded every
+// block <= b-2, (2) adds the contribution of block b-1 to column b itself (one masked OR-reduction over 64
+// words), (3) runs the 64-step branch-free resolve, (4) publishes the kept mask.  Nothing else sits on the
+// dependency chain.  Hand-offs use shared-memory progress counters (+ __threadfence_block) and a named
+// barrier among the workers only.
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kScanThreads - 32) : "memory"); }
+__device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+__global__ void __launch_bounds__(kScanThreads)
+nms_scan_decoupled_kernel(const u64* __restrict__ mask, int n, int col_blocks, int* __restrict__ keep_out, int* __restrict__ num_out) {
+    extern __shared__ u64 sm[];
+    u64* remv = sm;                                          // [col_blocks] contributions folded by the workers
+    u64* kept_hist = sm + ((col_blocks + 1) & ~1);           // [col_blocks] kept mask of every resolved block
+    u64* ring = kept_hist + ((col_blocks + 1) & ~1);         // [2][64][col_blocks]
+    __shared__ int s_ring_ready;                             // rows of blocks < s_ring_ready have landed
+    __shared__ int s_resolved;                               // blocks < s_resolved are resolved (kept_hist valid)
+    __shared__ int s_folded;                                 // blocks < s_folded are folded into remv[j], j >= block + 2
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t buf_words = (size_t)kNmsTile * col_blocks;
+    constexpr int kWorkerWarps = kScanThreads / 32 - 1;
+
+    for (int j = tid; j < col_blocks; j += kScanThreads) remv[j] = 0;
+    if (tid == 0) { s_ring_ready = 0; s_resolved = 0; s_folded = 0; }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ resolver
+        u64 carry = 0;                                       // contribution of block b-1 to column b
+        int count = 0;
+        for (int b = 0; b < col_blocks; ++b) {
+            while (ld_volatile_s32(&s_ring_ready) < b + 1) { }
+            while (ld_volatile_s32(&s_folded) < b - 1) { }
+            __threadfence_block();
+            const u64* rows = ring + (size_t)(b & 1) * buf_words;
+            const int lim = min(kNmsTile, n - b * kNmsTile);
+            u64 r = *reinterpret_cast<volatile u64*>(&remv[b]) | carry;
+            u64 kept = 0;
+            const u64* diag = rows + b;
+#pragma unroll
+            for (int k = 0; k < kNmsTile; ++k) {
+                const u64 dk = (k < lim) ? diag[(size_t)k * col_blocks] : 0ULL;
+                const bool alive = ((r >> k) & 1ULL) == 0ULL;
+                kept |= alive ? (1ULL << k) : 0ULL;
+                r |= alive ? dk : 0ULL;
+            }
+            if (lim < kNmsTile) kept &= (1ULL << lim) - 1ULL;
+            // contribution of this block to the NEXT column, needed by the very next resolve.  It reads this block's
+            // rows, so it comes BEFORE the publication that lets the workers recycle the ring buffer.
+            carry = 0;
+            if (b + 1 < col_blocks) {
+                u64 c = 0;
+                if ((kept >> lane) & 1ULL) c |= rows[(size_t)lane * col_blocks + b + 1];
+                if ((kept >> (lane + 32)) & 1ULL) c |= rows[(size_t)(lane + 32) * col_blocks + b + 1];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c |= __shfl_xor_sync(0xffffffffu, c, o);
+                carry = c;
+            }
+            if (lane == 0) { kept_hist[b] = kept; __threadfence_block(); *reinterpret_cast<volatile int*>(&s_resolved) = b + 1; }
+            // kept indices, ascending
+            const u64 lo_mask = (1ULL << lane) - 1ULL;
+            if ((kept >> lane) & 1ULL) keep_out[count + __popcll(kept & lo_mask)] = b * kNmsTile + lane;
+            if ((kept >> (lane + 32)) & 1ULL) keep_out[count + __popcll(kept & ((lo_mask << 32) | 0xffffffffULL))] = b * kNmsTile + lane + 32;
+            count += __popcll(kept);
+        }
+        if (lane == 0) *num_out = count;
+    } else {
+        // ------------------------------------------------------------------ workers
+        const int wt = tid - 32;                             // 0 .. 991
+        const int wwarp = warp - 1;
+        auto prefetch = [&](int b) {                         // rows of block b, columns [b, col_blocks)
+            if (b < col_blocks) {
+                u64* dst = ring + (size_t)(b & 1) * buf_words;
+                const int rows = min(kNmsTile, n - b * kNmsTile);
+                for (int k = wwarp; k < rows; k += kWorkerWarps) {
+                    const u64* src = mask + (size_t)(b * kNmsTile + k) * col_blocks;
+                    u64* d = dst + (size_t)k * col_blocks;
+                    for (int j = b + lane; j < col_blocks; j += 32) cp_async8(d + j, src + j);
+                }
+            }
+            cp_async_commit();
+        };
+        prefetch(0);
+        prefetch(1);
+        cp_async_wait<1>();
+        worker_barrier();
+        if (wt == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(&s_ring_ready) = 1; }
+        for (int b = 0; b < col_blocks; ++b) {
+            // rows of block b+1 (issued one iteration ago) must land before the resolver gets there
+            cp_async_wait<0>();
+            worker_barrier();
+            if (wt == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(&s_ring_ready) = min(b + 2, col_blocks); }
+            while (ld_volatile_s32(&s_resolved) < b + 1) { }
+            __threadfence_block();
+            const u64 kept = *reinterpret_cast<volatile u64*>(&kept_hist[b]);
+            const u64* rows = ring + (size_t)(b & 1) * buf_words;
+            // fold the kept rows of block b into remv[j], j >= b + 2 (column b + 1 is the resolver's carry):
+            // lane = (column of a group of 4, row residue of 8); shuffles combine the 8 partials; single writer per word
+            const int kg = lane & 7, jl = lane >> 3;
+            for (int j0 = b + 2 + wwarp * 4; j0 < col_blocks; j0 += kWorkerWarps * 4) {
+                const int j = j0 + jl;
+                u64 acc = 0;
+                if (j < col_blocks) {
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const int k = kg + 8 * kk;
+                        if ((kept >> k) & 1ULL) acc |= rows[(size_t)k * col_blocks + j];
+                    }
+                }
+                acc |= __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc |= __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc |= __shfl_xor_sync(0xffffffffu, acc, 4);
+                if (kg == 0 && j < col_blocks && acc) remv[j] |= acc;
+            }
+            worker_barrier();                                // every fold of block b is done; ring[b & 1] is free
+            if (wt == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(&s_folded) = b + 1; }
+            prefetch(b + 2);
+        }
+        cp_async_wait<0>();
+    }
+}
+
 __global__ void nms_empty_kernel(int* num_out) { *num_out = 0; }
 
 size_t nms_workspace_bytes(int n) {
@@ -236,11 +360,18 @@ int nms(const float* boxes, int n, int dim, float thresh, int* keep_out, int* nu
     u64* mask = (u64*)workspace;
     dim3 grid(cb, cb);
     nms_mask_kernel<<<grid, kNmsTile, 0, stream>>>(boxes, n, dim, thresh, mask);
-    const size_t smem_pipe = sizeof(u64) * (((size_t)cb + 1) / 2 * 2 + 2 * (size_t)kNmsTile * cb);
+    const size_t smem_pipe = sizeof(u64) * (2 * (((size_t)cb + 1) / 2 * 2) + 2 * (size_t)kNmsTile * cb);
     if (smem_pipe <= 220 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(nms_scan_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
+        const char* e_mode = getenv("B200_NMS_SCAN");         // "pipelined" selects the older barrier-per-block scan (A/B tests)
+        if (e_mode && e_mode[0] == 'p') {
+            cudaError_t e = cudaFuncSetAttribute(nms_scan_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
+            if (e != cudaSuccess) return (int)e;
+            nms_scan_pipelined_kernel<<<1, kScanThreads, smem_pipe, stream>>>(mask, n, cb, keep_out, num_out);
+            return finish_launch(2);
+        }
+        cudaError_t e = cudaFuncSetAttribute(nms_scan_decoupled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
         if (e != cudaSuccess) return (int)e;
-        nms_scan_pipelined_kernel<<<1, kScanThreads, smem_pipe, stream>>>(mask, n, cb, keep_out, num_out);
+        nms_scan_decoupled_kernel<<<1, kScanThreads, smem_pipe, stream>>>(mask, n, cb, keep_out, num_out);
         return finish_launch(2);
     }
     // very large inputs (> ~14k boxes): the ring does not fit; fall back to the unpipelined scan
