@@ -257,12 +257,27 @@ nms_scan_decoupled_kernel(const u64* __restrict__ mask, int n, int col_blocks, i
             u64 r = *reinterpret_cast<volatile u64*>(&remv[b]) | carry;
             u64 kept = 0;
             const u64* diag = rows + b;
+            // The 64 diagonal words do not depend on the running state: they are loaded 8 at a time, one batch
+            // AHEAD of the batch being resolved, so no shared-memory latency sits on the dependent chain
+            // (bit test -> predicated OR, ~2 ALU latencies per box).
+            u64 d[2][8];
 #pragma unroll
-            for (int k = 0; k < kNmsTile; ++k) {
-                const u64 dk = (k < lim) ? diag[(size_t)k * col_blocks] : 0ULL;
-                const bool alive = ((r >> k) & 1ULL) == 0ULL;
-                kept |= alive ? (1ULL << k) : 0ULL;
-                r |= alive ? dk : 0ULL;
+            for (int i8 = 0; i8 < 8; ++i8) d[0][i8] = (i8 < lim) ? diag[(size_t)i8 * col_blocks] : 0ULL;
+#pragma unroll
+            for (int k0 = 0; k0 < kNmsTile; k0 += 8) {
+                const int cur = (k0 >> 3) & 1;
+                if (k0 + 8 < kNmsTile) {
+#pragma unroll
+                    for (int i8 = 0; i8 < 8; ++i8)
+                        d[cur ^ 1][i8] = (k0 + 8 + i8 < lim) ? diag[(size_t)(k0 + 8 + i8) * col_blocks] : 0ULL;
+                }
+#pragma unroll
+                for (int i8 = 0; i8 < 8; ++i8) {
+                    const int k = k0 + i8;
+                    const bool alive = ((r >> k) & 1ULL) == 0ULL;
+                    kept |= alive ? (1ULL << k) : 0ULL;
+                    r |= alive ? d[cur][i8] : 0ULL;
+                }
             }
             if (lim < kNmsTile) kept &= (1ULL << lim) - 1ULL;
             // contribution of this block to the NEXT column, needed by the very next resolve.  It reads this block's
