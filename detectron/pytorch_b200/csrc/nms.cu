@@ -355,6 +355,108 @@ nms_scan_decoupled_kernel(const u64* __restrict__ mask, int n, int col_blocks, i
     }
 }
 
+// Resolver scan (default for n <= ~9000): everything the greedy chain itself touches -- the diagonal word of
+// every row and the two words right of it -- is copied to shared memory once (3 x n x 8 B), so the single
+// resolver warp never waits for global memory: per 64-box block it resolves (branch-free, diagonal words
+// prefetched a batch ahead) and derives from its own kept rows the contribution to the next TWO column
+// blocks.  The other 31 warps fold the kept rows into the remaining columns (j >= block + 3) straight
+// from global memory, one block per warp, 31 blocks in flight; the resolver only checks that the block
+// three steps back has been folded.
+__global__ void __launch_bounds__(kScanThreads)
+nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, int* __restrict__ keep_out, int* __restrict__ num_out) {
+    extern __shared__ u64 sm[];
+    const int n_pad = col_blocks * kNmsTile;
+    u64* D0 = sm;                       // mask[i][blk(i)]
+    u64* D1 = D0 + n_pad;               // mask[i][blk(i) + 1]
+    u64* D2 = D1 + n_pad;               // mask[i][blk(i) + 2]
+    u64* remv = D2 + n_pad;             // [col_blocks]  contributions of blocks <= j - 3 (workers, shared-memory atomics)
+    u64* kept_hist = remv + col_blocks; // [col_blocks]
+    volatile int* fold_done = reinterpret_cast<volatile int*>(kept_hist + col_blocks);   // [col_blocks]
+    __shared__ int s_resolved;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < n_pad; i += kScanThreads) {
+        u64 d0 = 0, d1 = 0, d2 = 0;
+        if (i < n) {
+            const int cbk = i >> 6;
+            const u64* row = mask + (size_t)i * col_blocks + cbk;
+            d0 = row[0];
+            if (cbk + 1 < col_blocks) d1 = row[1];
+            if (cbk + 2 < col_blocks) d2 = row[2];
+        }
+        D0[i] = d0; D1[i] = d1; D2[i] = d2;
+    }
+    for (int j = tid; j < col_blocks; j += kScanThreads) { remv[j] = 0; fold_done[j] = 0; }
+    if (tid == 0) s_resolved = 0;
+    __syncthreads();
+
+    if (warp == 0) {
+        u64 c1 = 0, c2 = 0;             // contributions of the last two blocks to the next two columns
+        int count = 0;
+        for (int b = 0; b < col_blocks; ++b) {
+            if (b >= 3) { while (fold_done[b - 3] == 0) { } }
+            __threadfence_block();
+            const int lim = min(kNmsTile, n - b * kNmsTile);
+            u64 r = *reinterpret_cast<volatile u64*>(&remv[b]) | c1;
+            u64 kept = 0;
+            const u64* diag = D0 + b * kNmsTile;
+            u64 d[2][8];
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) d[0][i8] = diag[i8];
+#pragma unroll
+            for (int k0 = 0; k0 < kNmsTile; k0 += 8) {
+                const int cur = (k0 >> 3) & 1;
+                if (k0 + 8 < kNmsTile) {
+#pragma unroll
+                    for (int i8 = 0; i8 < 8; ++i8) d[cur ^ 1][i8] = diag[k0 + 8 + i8];
+                }
+#pragma unroll
+                for (int i8 = 0; i8 < 8; ++i8) {
+                    const int k = k0 + i8;
+                    const bool alive = ((r >> k) & 1ULL) == 0ULL;
+                    kept |= alive ? (1ULL << k) : 0ULL;
+                    r |= alive ? d[cur][i8] : 0ULL;
+                }
+            }
+            if (lim < kNmsTile) kept &= (1ULL << lim) - 1ULL;      // padded rows have zero masks but must not be kept
+            // contributions of this block's kept rows to the next two columns
+            u64 k1 = 0, k2 = 0;
+            if ((kept >> lane) & 1ULL) { k1 = D1[b * kNmsTile + lane]; k2 = D2[b * kNmsTile + lane]; }
+            if ((kept >> (lane + 32)) & 1ULL) { k1 |= D1[b * kNmsTile + lane + 32]; k2 |= D2[b * kNmsTile + lane + 32]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { k1 |= __shfl_xor_sync(0xffffffffu, k1, o); k2 |= __shfl_xor_sync(0xffffffffu, k2, o); }
+            c1 = c2 | k1;
+            c2 = k2;
+            if (lane == 0) { kept_hist[b] = kept; __threadfence_block(); *reinterpret_cast<volatile int*>(&s_resolved) = b + 1; }
+            const u64 lo_mask = (1ULL << lane) - 1ULL;
+            if ((kept >> lane) & 1ULL) keep_out[count + __popcll(kept & lo_mask)] = b * kNmsTile + lane;
+            if ((kept >> (lane + 32)) & 1ULL) keep_out[count + __popcll(kept & ((lo_mask << 32) | 0xffffffffULL))] = b * kNmsTile + lane + 32;
+            count += __popcll(kept);
+        }
+        if (lane == 0) *num_out = count;
+    } else {
+        constexpr int kWorkerWarps = kScanThreads / 32 - 1;
+        for (int b = warp - 1; b < col_blocks; b += kWorkerWarps) {
+            while (ld_volatile_s32(&s_resolved) < b + 1) { }
+            __threadfence_block();
+            const u64 kept = *reinterpret_cast<volatile u64*>(&kept_hist[b]);
+            const u64* rows = mask + (size_t)b * kNmsTile * col_blocks;
+            for (int j = b + 3 + lane; j < col_blocks; j += 32) {
+                u64 acc = 0, kk = kept;
+                while (kk) {
+                    const int k = __ffsll((long long)kk) - 1;
+                    kk &= kk - 1;
+                    acc |= rows[(size_t)k * col_blocks + j];
+                }
+                if (acc) atomicOr(&remv[j], acc);
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) fold_done[b] = 1;
+        }
+    }
+}
+
 __global__ void nms_empty_kernel(int* num_out) { *num_out = 0; }
 
 size_t nms_workspace_bytes(int n) {
@@ -375,9 +477,16 @@ int nms(const float* boxes, int n, int dim, float thresh, int* keep_out, int* nu
     u64* mask = (u64*)workspace;
     dim3 grid(cb, cb);
     nms_mask_kernel<<<grid, kNmsTile, 0, stream>>>(boxes, n, dim, thresh, mask);
+    const char* e_mode = getenv("B200_NMS_SCAN");             // "pipelined" / "decoupled" select the older scans (A/B tests)
+    const size_t smem_res = sizeof(u64) * (3 * (size_t)cb * kNmsTile + 2 * (size_t)cb) + sizeof(int) * (size_t)cb + 16;
+    if (smem_res <= 220 * 1024 && !(e_mode && (e_mode[0] == 'p' || e_mode[0] == 'd'))) {
+        cudaError_t e = cudaFuncSetAttribute(nms_scan_resolver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res);
+        if (e != cudaSuccess) return (int)e;
+        nms_scan_resolver_kernel<<<1, kScanThreads, smem_res, stream>>>(mask, n, cb, keep_out, num_out);
+        return finish_launch(2);
+    }
     const size_t smem_pipe = sizeof(u64) * (2 * (((size_t)cb + 1) / 2 * 2) + 2 * (size_t)kNmsTile * cb);
     if (smem_pipe <= 220 * 1024) {
-        const char* e_mode = getenv("B200_NMS_SCAN");         // "pipelined" selects the older barrier-per-block scan (A/B tests)
         if (e_mode && e_mode[0] == 'p') {
             cudaError_t e = cudaFuncSetAttribute(nms_scan_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
             if (e != cudaSuccess) return (int)e;
