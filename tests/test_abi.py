@@ -53,6 +53,22 @@ def test_argument_validation_without_gpu():
     assert lib.b200_nms_workspace_bytes(64) == 64 * 8
 
 
+def test_workspace_sizing_is_host_arithmetic():
+    lib = _lib.load()
+    # forward fast path: per-RoI tables + per-tile work lists; 0 when the parameters are outside the fast path
+    w = lib.b200_roi_align_workspace_bytes(1, 512, 200, 272, 7, 7, 2)
+    assert w > 512 * (32 + 28 * 16) and w % 256 == 0
+    assert lib.b200_roi_align_workspace_bytes(1, 512, 200, 272, 7, 7, 0) == 0          # adaptive sampling -> generic kernel
+    assert lib.b200_roi_align_workspace_bytes(1, 512, 200, 272, 40, 40, 2) == 0        # P * sr > 32 per axis
+    assert lib.b200_roi_align_workspace_bytes(1, 0, 200, 272, 7, 7, 2) == 0
+    # backward vector-reduction path: one channel-innermost scratch image of dX
+    assert lib.b200_roi_align_backward_workspace_bytes(1, 256, 200, 272) == 256 * 200 * 272 * 4
+    assert lib.b200_roi_align_backward_workspace_bytes(0, 256, 200, 272) == 0
+    # NULL workspace is legal for the _ws entry points (generic kernels run); bad dims are still rejected first
+    assert lib.b200_roi_align_forward_ws(None, 0.25, 1, 4, 10, 10, 3, 0, 7, 2, None, None, None, 0, None) == -1
+    assert lib.b200_roi_align_backward_ws(None, 0.25, 1, 4, 10, -1, 3, 7, 7, 2, None, None, None, 0, None) == -1
+
+
 def test_product_package_never_imports_oracle():
     pkg = os.path.join(ROOT, "detectron")
     for dirpath, _, files in os.walk(pkg):
