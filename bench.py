@@ -311,9 +311,10 @@ def main():
     # ---- e2e: the reference-shaped plugin with HOST buffers; H2D of features/rois/dY and D2H of
     #      out/dX are inside the timed region, every step
     fn = RoIAlignFunction(P, P, scale, sr)
-    h_feat = torch.randn(shape).pin_memory(); h_rois = torch.from_numpy(rois_np[0]).pin_memory()
-    h_dy = torch.randn((R, C, P, P)).pin_memory()
-    h_out = torch.empty((R, C, P, P)).pin_memory(); h_dx = torch.empty(shape).pin_memory()
+    with benchutil.numa_local(local):                 # pinned buffers first-touched on the GPU's NUMA node
+        h_feat = torch.randn(shape).pin_memory(); h_rois = torch.from_numpy(rois_np[0]).pin_memory()
+        h_dy = torch.randn((R, C, P, P)).pin_memory()
+        h_out = torch.empty((R, C, P, P)).pin_memory(); h_dx = torch.empty(shape).pin_memory()
     h2d = h_feat.numel() * 4 + h_rois.numel() * 4 + h_dy.numel() * 4
     d2h = h_out.numel() * 4 + h_dx.numel() * 4
 

@@ -112,6 +112,57 @@ def shard_images(num_images, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+# NUMA placement of pinned host buffers
+# ------------------------------------------------------------------------------------------------
+def gpu_local_cpus(device_index=0):
+    """CPUs on the NUMA node the GPU's PCIe root hangs off (from sysfs), or None if unknown."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        return cpus or None
+    except Exception:  # noqa: BLE001
+        return None
+
+
+class numa_local(object):
+    """Context manager: run on the GPU-local CPUs (so that pinned allocations made inside are
+    first-touched on the GPU's NUMA node), then restore the previous affinity."""
+
+    def __init__(self, device_index=0):
+        self.cpus = gpu_local_cpus(device_index)
+        self.prev = None
+
+    def __enter__(self):
+        if self.cpus:
+            try:
+                self.prev = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.cpus)
+            except OSError:
+                self.prev = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            try:
+                os.sched_setaffinity(0, self.prev)
+            except OSError:
+                pass
+        return False
+
+
+# ------------------------------------------------------------------------------------------------
 # clocks / throttle reasons during the timed region
 # ------------------------------------------------------------------------------------------------
 _QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
