@@ -18,6 +18,7 @@ namespace b200 {
 
 constexpr int kNmsTile = 64;
 constexpr int kScanThreads = 1024;
+constexpr int kFoldGroups = 4, kFoldWarps = 7;      // resolver scan: 4 blocks folded concurrently by 7 warps each
 
 typedef unsigned long long u64;
 
@@ -394,7 +395,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
         u64 c1 = 0, c2 = 0;             // contributions of the last two blocks to the next two columns
         int count = 0;
         for (int b = 0; b < col_blocks; ++b) {
-            if (b >= 3) { while (fold_done[b - 3] == 0) { } }
+            if (b >= 3) { while (fold_done[b - 3] < kFoldWarps) { } }
             __threadfence_block();
             const int lim = min(kNmsTile, n - b * kNmsTile);
             u64 r = *reinterpret_cast<volatile u64*>(&remv[b]) | c1;
@@ -435,24 +436,33 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
         }
         if (lane == 0) *num_out = count;
     } else {
-        constexpr int kWorkerWarps = kScanThreads / 32 - 1;
-        for (int b = warp - 1; b < col_blocks; b += kWorkerWarps) {
-            while (ld_volatile_s32(&s_resolved) < b + 1) { }
-            __threadfence_block();
-            const u64 kept = *reinterpret_cast<volatile u64*>(&kept_hist[b]);
-            const u64* rows = mask + (size_t)b * kNmsTile * col_blocks;
-            for (int j = b + 3 + lane; j < col_blocks; j += 32) {
-                u64 acc = 0, kk = kept;
-                while (kk) {
-                    const int k = __ffsll((long long)kk) - 1;
-                    kk &= kk - 1;
-                    acc |= rows[(size_t)k * col_blocks + j];
+        // 28 worker warps = 4 groups x 7 warps.  Group g folds blocks b = g, g+4, ...; inside a group warp wi takes the
+        // columns j = b+3+wi, +7, ...  Lanes are ROWS (lane l: rows l and l+32 of the block), so every kept row's word
+        // of a column is fetched in one go, OR-reduced across the warp with REDUX, and merged by one shared-memory
+        // atomic.  All loads of a warp are independent: a block is folded in ~2 L2 latencies, 4 blocks in flight.
+        const int ww = warp - 1;
+        if (ww < kFoldGroups * kFoldWarps) {
+            const int g = ww / kFoldWarps, wi = ww - g * kFoldWarps;
+            for (int b = g; b < col_blocks; b += kFoldGroups) {
+                while (ld_volatile_s32(&s_resolved) < b + 1) { }
+                __threadfence_block();
+                const u64 kept = *reinterpret_cast<volatile u64*>(&kept_hist[b]);
+                const bool k0 = (kept >> lane) & 1ULL, k1 = (kept >> (lane + 32)) & 1ULL;
+                const u64* row0 = mask + (size_t)(b * kNmsTile + lane) * col_blocks;
+                const u64* row1 = row0 + (size_t)32 * col_blocks;
+#pragma unroll 4
+                for (int j = b + 3 + wi; j < col_blocks; j += kFoldWarps) {
+                    u64 v = 0;
+                    if (k0) v = row0[j];
+                    if (k1) v |= row1[j];
+                    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+                    const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+                    if (lane == 0 && (lo | hi)) atomicOr(&remv[j], ((u64)hi << 32) | lo);
                 }
-                if (acc) atomicOr(&remv[j], acc);
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) atomicAdd(const_cast<int*>(&fold_done[b]), 1);
             }
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) fold_done[b] = 1;
         }
     }
 }
