@@ -356,51 +356,47 @@ nms_scan_decoupled_kernel(const u64* __restrict__ mask, int n, int col_blocks, i
     }
 }
 
-// Resolver scan (default for n <= ~9000): everything the greedy chain itself touches -- the diagonal word of
-// every row and the two words right of it -- is copied to shared memory once (3 x n x 8 B), so the single
-// resolver warp never waits for global memory: per 64-box block it resolves (branch-free, diagonal words
-// prefetched a batch ahead) and derives from its own kept rows the contribution to the next TWO column
-// blocks.  The other 31 warps fold the kept rows into the remaining columns (j >= block + 3) straight
-// from global memory, one block per warp, 31 blocks in flight; the resolver only checks that the block
-// three steps back has been folded.
+// Resolver scan (default while REACH * n * 8 B fits shared memory): everything the greedy chain itself touches --
+// the diagonal word of every row and the REACH-1 words right of it -- is copied to shared memory once, so the
+// single resolver warp never waits for global memory: per 64-box block it resolves (branch-free, diagonal words
+// prefetched a batch ahead) and derives from its own kept rows the contribution to the next REACH-1 column
+// blocks.  28 worker warps (4 groups x 7) fold the kept rows into the remaining columns (j >= block + REACH)
+// straight from global memory with every load of a block in flight at once; the resolver only checks that the
+// block REACH steps back has been folded.
+template <int REACH>
 __global__ void __launch_bounds__(kScanThreads)
 nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, int* __restrict__ keep_out, int* __restrict__ num_out) {
     extern __shared__ u64 sm[];
     const int n_pad = col_blocks * kNmsTile;
-    u64* D0 = sm;                       // mask[i][blk(i)]
-    u64* D1 = D0 + n_pad;               // mask[i][blk(i) + 1]
-    u64* D2 = D1 + n_pad;               // mask[i][blk(i) + 2]
-    u64* remv = D2 + n_pad;             // [col_blocks]  contributions of blocks <= j - 3 (workers, shared-memory atomics)
-    u64* kept_hist = remv + col_blocks; // [col_blocks]
-    volatile int* fold_done = reinterpret_cast<volatile int*>(kept_hist + col_blocks);   // [col_blocks]
+    u64* D = sm;                                    // D[t][i] = mask[i][blk(i) + t], t < REACH
+    u64* remv = D + (size_t)REACH * n_pad;          // [col_blocks]  contributions of blocks <= j - REACH (workers, smem atomics)
+    u64* kept_hist = remv + col_blocks;             // [col_blocks]
+    volatile int* fold_done = reinterpret_cast<volatile int*>(kept_hist + col_blocks);   // [col_blocks] warps that finished folding
     __shared__ int s_resolved;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int i = tid; i < n_pad; i += kScanThreads) {
-        u64 d0 = 0, d1 = 0, d2 = 0;
-        if (i < n) {
-            const int cbk = i >> 6;
-            const u64* row = mask + (size_t)i * col_blocks + cbk;
-            d0 = row[0];
-            if (cbk + 1 < col_blocks) d1 = row[1];
-            if (cbk + 2 < col_blocks) d2 = row[2];
-        }
-        D0[i] = d0; D1[i] = d1; D2[i] = d2;
+        const int cbk = i >> 6;
+        const u64* row = mask + (size_t)i * col_blocks + cbk;
+#pragma unroll
+        for (int t = 0; t < REACH; ++t) D[(size_t)t * n_pad + i] = (i < n && cbk + t < col_blocks) ? row[t] : 0ULL;
     }
     for (int j = tid; j < col_blocks; j += kScanThreads) { remv[j] = 0; fold_done[j] = 0; }
     if (tid == 0) s_resolved = 0;
     __syncthreads();
 
     if (warp == 0) {
-        u64 c1 = 0, c2 = 0;             // contributions of the last two blocks to the next two columns
+        u64 c[REACH];                               // c[t]: contribution of already resolved blocks to column b + t (t >= 1)
+#pragma unroll
+        for (int t = 0; t < REACH; ++t) c[t] = 0;
         int count = 0;
         for (int b = 0; b < col_blocks; ++b) {
-            if (b >= 3) { while (fold_done[b - 3] < kFoldWarps) { } }
+            if (b >= REACH) { while (fold_done[b - REACH] < kFoldWarps) { } }
             __threadfence_block();
             const int lim = min(kNmsTile, n - b * kNmsTile);
-            u64 r = *reinterpret_cast<volatile u64*>(&remv[b]) | c1;
+            u64 r = *reinterpret_cast<volatile u64*>(&remv[b]) | c[1];
             u64 kept = 0;
-            const u64* diag = D0 + b * kNmsTile;
+            const u64* diag = D + b * kNmsTile;
             u64 d[2][8];
 #pragma unroll
             for (int i8 = 0; i8 < 8; ++i8) d[0][i8] = diag[i8];
@@ -420,26 +416,30 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
                 }
             }
             if (lim < kNmsTile) kept &= (1ULL << lim) - 1ULL;      // padded rows have zero masks but must not be kept
-            // contributions of this block's kept rows to the next two columns
-            u64 k1 = 0, k2 = 0;
-            if ((kept >> lane) & 1ULL) { k1 = D1[b * kNmsTile + lane]; k2 = D2[b * kNmsTile + lane]; }
-            if ((kept >> (lane + 32)) & 1ULL) { k1 |= D1[b * kNmsTile + lane + 32]; k2 |= D2[b * kNmsTile + lane + 32]; }
+            // contributions of this block's kept rows to the next REACH-1 columns; shift the carries by one column
+            const bool ka = (kept >> lane) & 1ULL, kb2 = (kept >> (lane + 32)) & 1ULL;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { k1 |= __shfl_xor_sync(0xffffffffu, k1, o); k2 |= __shfl_xor_sync(0xffffffffu, k2, o); }
-            c1 = c2 | k1;
-            c2 = k2;
+            for (int t = 1; t < REACH; ++t) {
+                u64 v = 0;
+                if (ka) v = D[(size_t)t * n_pad + b * kNmsTile + lane];
+                if (kb2) v |= D[(size_t)t * n_pad + b * kNmsTile + lane + 32];
+                const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+                const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+                const u64 kt = ((u64)hi << 32) | lo;
+                c[t] = ((t + 1 < REACH) ? c[t + 1] : 0ULL) | kt;
+            }
             if (lane == 0) { kept_hist[b] = kept; __threadfence_block(); *reinterpret_cast<volatile int*>(&s_resolved) = b + 1; }
             const u64 lo_mask = (1ULL << lane) - 1ULL;
-            if ((kept >> lane) & 1ULL) keep_out[count + __popcll(kept & lo_mask)] = b * kNmsTile + lane;
-            if ((kept >> (lane + 32)) & 1ULL) keep_out[count + __popcll(kept & ((lo_mask << 32) | 0xffffffffULL))] = b * kNmsTile + lane + 32;
+            if (ka) keep_out[count + __popcll(kept & lo_mask)] = b * kNmsTile + lane;
+            if (kb2) keep_out[count + __popcll(kept & ((lo_mask << 32) | 0xffffffffULL))] = b * kNmsTile + lane + 32;
             count += __popcll(kept);
         }
         if (lane == 0) *num_out = count;
     } else {
         // 28 worker warps = 4 groups x 7 warps.  Group g folds blocks b = g, g+4, ...; inside a group warp wi takes the
-        // columns j = b+3+wi, +7, ...  Lanes are ROWS (lane l: rows l and l+32 of the block), so every kept row's word
-        // of a column is fetched in one go, OR-reduced across the warp with REDUX, and merged by one shared-memory
-        // atomic.  All loads of a warp are independent: a block is folded in ~2 L2 latencies, 4 blocks in flight.
+        // columns j = b+REACH+wi, +7, ...  Lanes are ROWS (lane l: rows l and l+32 of the block): every kept row's word of
+        // a column is fetched in one go, OR-reduced across the warp with REDUX and merged by one shared-memory atomic.
+        // The loads of up to 14 columns are issued before the first reduction, so a block is folded in ~1 L2 latency.
         const int ww = warp - 1;
         if (ww < kFoldGroups * kFoldWarps) {
             const int g = ww / kFoldWarps, wi = ww - g * kFoldWarps;
@@ -450,14 +450,22 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
                 const bool k0 = (kept >> lane) & 1ULL, k1 = (kept >> (lane + 32)) & 1ULL;
                 const u64* row0 = mask + (size_t)(b * kNmsTile + lane) * col_blocks;
                 const u64* row1 = row0 + (size_t)32 * col_blocks;
-#pragma unroll 4
-                for (int j = b + 3 + wi; j < col_blocks; j += kFoldWarps) {
-                    u64 v = 0;
-                    if (k0) v = row0[j];
-                    if (k1) v |= row1[j];
-                    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
-                    const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
-                    if (lane == 0 && (lo | hi)) atomicOr(&remv[j], ((u64)hi << 32) | lo);
+                for (int j0 = b + REACH + wi; j0 < col_blocks; j0 += kFoldWarps * 14) {
+                    u64 v[14];
+#pragma unroll
+                    for (int t = 0; t < 14; ++t) {
+                        const int j = j0 + t * kFoldWarps;
+                        u64 x = 0;
+                        if (j < col_blocks) { if (k0) x = row0[j]; if (k1) x |= row1[j]; }
+                        v[t] = x;
+                    }
+#pragma unroll
+                    for (int t = 0; t < 14; ++t) {
+                        const int j = j0 + t * kFoldWarps;
+                        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v[t]);
+                        const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v[t] >> 32));
+                        if (lane == 0 && j < col_blocks && (lo | hi)) atomicOr(&remv[j], ((u64)hi << 32) | lo);
+                    }
                 }
                 __threadfence_block();
                 __syncwarp();
@@ -488,11 +496,16 @@ int nms(const float* boxes, int n, int dim, float thresh, int* keep_out, int* nu
     dim3 grid(cb, cb);
     nms_mask_kernel<<<grid, kNmsTile, 0, stream>>>(boxes, n, dim, thresh, mask);
     const char* e_mode = getenv("B200_NMS_SCAN");             // "pipelined" / "decoupled" select the older scans (A/B tests)
-    const size_t smem_res = sizeof(u64) * (3 * (size_t)cb * kNmsTile + 2 * (size_t)cb) + sizeof(int) * (size_t)cb + 16;
-    if (smem_res <= 220 * 1024 && !(e_mode && (e_mode[0] == 'p' || e_mode[0] == 'd'))) {
-        cudaError_t e = cudaFuncSetAttribute(nms_scan_resolver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res);
+    const bool old_scan = e_mode && (e_mode[0] == 'p' || e_mode[0] == 'd');
+    for (int reach = 4; reach >= 3 && !old_scan; --reach) {
+        const size_t smem_res = sizeof(u64) * ((size_t)reach * cb * kNmsTile + 2 * (size_t)cb) + sizeof(int) * (size_t)cb + 16;
+        if (smem_res > 220 * 1024) continue;
+        cudaError_t e = (reach == 4)
+            ? cudaFuncSetAttribute(nms_scan_resolver_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res)
+            : cudaFuncSetAttribute(nms_scan_resolver_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res);
         if (e != cudaSuccess) return (int)e;
-        nms_scan_resolver_kernel<<<1, kScanThreads, smem_res, stream>>>(mask, n, cb, keep_out, num_out);
+        if (reach == 4) nms_scan_resolver_kernel<4><<<1, kScanThreads, smem_res, stream>>>(mask, n, cb, keep_out, num_out);
+        else nms_scan_resolver_kernel<3><<<1, kScanThreads, smem_res, stream>>>(mask, n, cb, keep_out, num_out);
         return finish_launch(2);
     }
     const size_t smem_pipe = sizeof(u64) * (2 * (((size_t)cb + 1) / 2 * 2) + 2 * (size_t)kNmsTile * cb);
