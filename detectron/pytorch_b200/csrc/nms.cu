@@ -394,10 +394,12 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
             if (b >= REACH) { while (fold_done[b - REACH] < kFoldWarps) { } }
             __threadfence_block();
             const int lim = min(kNmsTile, n - b * kNmsTile);
-            u64 r = *reinterpret_cast<volatile u64*>(&remv[b]) | c[1];
-            u64 kept = 0;
-            const u64* diag = D + b * kNmsTile;
-            u64 d[2][8];
+            const u64 r0 = *reinterpret_cast<volatile u64*>(&remv[b]) | c[1];
+            // 64-step greedy resolve on 32-bit halves: per box one bit test that sets a predicate and predicated
+            // ORs -- two dependent ALU operations.  The diagonal words are fetched 8 boxes ahead (uint2 loads).
+            unsigned r_lo = (unsigned)r0, r_hi = (unsigned)(r0 >> 32), kept_lo = 0u, kept_hi = 0u;
+            const uint2* diag = reinterpret_cast<const uint2*>(D + b * kNmsTile);
+            uint2 d[2][8];
 #pragma unroll
             for (int i8 = 0; i8 < 8; ++i8) d[0][i8] = diag[i8];
 #pragma unroll
@@ -410,11 +412,14 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
 #pragma unroll
                 for (int i8 = 0; i8 < 8; ++i8) {
                     const int k = k0 + i8;
-                    const bool alive = ((r >> k) & 1ULL) == 0ULL;
-                    kept |= alive ? (1ULL << k) : 0ULL;
-                    r |= alive ? d[cur][i8] : 0ULL;
+                    if (k < 32) {
+                        if (!(r_lo & (1u << k))) { kept_lo |= 1u << k; r_lo |= d[cur][i8].x; r_hi |= d[cur][i8].y; }
+                    } else {                        // a diagonal word only has bits above its own row: the low half is dead
+                        if (!(r_hi & (1u << (k - 32)))) { kept_hi |= 1u << (k - 32); r_hi |= d[cur][i8].y; }
+                    }
                 }
             }
+            u64 kept = ((u64)kept_hi << 32) | kept_lo;
             if (lim < kNmsTile) kept &= (1ULL << lim) - 1ULL;      // padded rows have zero masks but must not be kept
             // contributions of this block's kept rows to the next REACH-1 columns; shift the carries by one column
             const bool ka = (kept >> lane) & 1ULL, kb2 = (kept >> (lane + 32)) & 1ULL;
