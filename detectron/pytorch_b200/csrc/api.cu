@@ -17,6 +17,7 @@ int roi_crop_backward(const float*, const float*, int, int, int, int, int, int, 
 size_t nms_workspace_bytes(int);
 size_t roi_align_tiled_workspace_bytes(int, int, int, int, int, int, int);
 void roi_align_tiled_set_timing_buffer(unsigned long long*);
+void nms_set_timing_buffer(unsigned long long*);
 int roi_align_forward_tiled(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, void*, size_t, cudaStream_t);
 
 // B200_ROI_ALIGN_PATH=generic|tiled|auto (default auto) -- test/benchmark override of the forward dispatch
@@ -72,7 +73,10 @@ const char* b200_roi_ops_strerror(int status) {
 
 unsigned long long b200_roi_ops_launch_count(void) { return g_launch_count; }
 
-void b200_roi_ops_debug_timing_buffer(void* device_u64x8) { roi_align_tiled_set_timing_buffer((unsigned long long*)device_u64x8); }
+void b200_roi_ops_debug_timing_buffer(void* device_u64x8) {
+    roi_align_tiled_set_timing_buffer((unsigned long long*)device_u64x8);
+    nms_set_timing_buffer((unsigned long long*)device_u64x8);
+}
 
 size_t b200_roi_align_workspace_bytes(int batch_size, int num_rois, int height, int width, int aligned_height,
                                       int aligned_width, int sampling_ratio) {

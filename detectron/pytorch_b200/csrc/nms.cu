@@ -22,6 +22,9 @@ constexpr int kFoldGroups = 4, kFoldWarps = 7;      // resolver scan: 4 blocks f
 
 typedef unsigned long long u64;
 
+// Debug: per-phase clock64 totals of the resolver warp (tools/nms_probe.py); null by default.
+__device__ unsigned long long* g_nms_timing = nullptr;
+
 struct __align__(16) ColBox {
     float x0, y0, x1, y1;
 };
@@ -390,9 +393,13 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
 #pragma unroll
         for (int t = 0; t < REACH; ++t) c[t] = 0;
         int count = 0;
+        unsigned long long* const timing = g_nms_timing;
+        long long t_wait = 0, t_res = 0, t_rest = 0;
         for (int b = 0; b < col_blocks; ++b) {
+            const long long t0 = timing ? clock64() : 0;
             if (b >= REACH) { while (fold_done[b - REACH] < kFoldWarps) { } }
             __threadfence_block();
+            const long long t1 = timing ? clock64() : 0;
             const int lim = min(kNmsTile, n - b * kNmsTile);
             const u64 r0 = *reinterpret_cast<volatile u64*>(&remv[b]) | c[1];
             // 64-step greedy resolve on 32-bit halves: per box one bit test that sets a predicate and predicated
@@ -420,6 +427,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
                 }
             }
             u64 kept = ((u64)kept_hi << 32) | kept_lo;
+            const long long t2 = timing ? clock64() : 0;
             if (lim < kNmsTile) kept &= (1ULL << lim) - 1ULL;      // padded rows have zero masks but must not be kept
             // contributions of this block's kept rows to the next REACH-1 columns; shift the carries by one column
             const bool ka = (kept >> lane) & 1ULL, kb2 = (kept >> (lane + 32)) & 1ULL;
@@ -438,8 +446,10 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
             if (ka) keep_out[count + __popcll(kept & lo_mask)] = b * kNmsTile + lane;
             if (kb2) keep_out[count + __popcll(kept & ((lo_mask << 32) | 0xffffffffULL))] = b * kNmsTile + lane + 32;
             count += __popcll(kept);
+            if (timing) { const long long t3 = clock64(); t_wait += t1 - t0; t_res += t2 - t1; t_rest += t3 - t2; }
         }
         if (lane == 0) *num_out = count;
+        if (timing && lane == 0) { timing[0] = t_wait; timing[1] = t_res; timing[2] = t_rest; timing[3] = col_blocks; }
     } else {
         // 28 worker warps = 4 groups x 7 warps.  Group g folds blocks b = g, g+4, ...; inside a group warp wi takes the
         // columns j = b+REACH+wi, +7, ...  Lanes are ROWS (lane l: rows l and l+32 of the block): every kept row's word of
@@ -481,6 +491,8 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
 }
 
 __global__ void nms_empty_kernel(int* num_out) { *num_out = 0; }
+
+void nms_set_timing_buffer(unsigned long long* buf) { cudaMemcpyToSymbol(g_nms_timing, &buf, sizeof(buf)); }
 
 size_t nms_workspace_bytes(int n) {
     if (n <= 0) return 256;

@@ -13,3 +13,11 @@ for _ in range(20):
     ops.nms_raw(b, 0.7)
 e1.record(); torch.cuda.synchronize()
 print("nms 6000: %.1f us/call, kept %d" % (e0.elapsed_time(e1) / 20 * 1e3, int(num.item())))
+
+from detectron.pytorch_b200 import _lib
+buf = torch.zeros(8, dtype=torch.int64, device="cuda")
+lib = _lib.load(); lib.b200_roi_ops_debug_timing_buffer(buf.data_ptr())
+ops.nms_raw(b, 0.7); torch.cuda.synchronize(); lib.b200_roi_ops_debug_timing_buffer(None)
+t = buf.tolist()
+if t[3]:
+    print("resolver cycles/block: wait-for-folds %.0f  resolve %.0f  carry+publish+keep %.0f  (blocks %d)" % (t[0] / t[3], t[1] / t[3], t[2] / t[3], t[3]))
