@@ -18,7 +18,7 @@ namespace b200 {
 
 constexpr int kNmsTile = 64;
 constexpr int kScanThreads = 1024;
-constexpr int kFoldGroups = 4, kFoldWarps = 7;      // resolver scan: 4 blocks folded concurrently by 7 warps each
+constexpr int kFoldGroups = 4, kFoldWarps = 6;      // resolver scan: 4 blocks folded concurrently by 6 warps each (24 worker warps)
 
 typedef unsigned long long u64;
 
@@ -451,13 +451,16 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
         if (lane == 0) *num_out = count;
         if (timing && lane == 0) { timing[0] = t_wait; timing[1] = t_res; timing[2] = t_rest; timing[3] = col_blocks; }
     } else {
-        // 28 worker warps = 4 groups x 7 warps.  Group g folds blocks b = g, g+4, ...; inside a group warp wi takes the
-        // columns j = b+REACH+wi, +7, ...  Lanes are ROWS (lane l: rows l and l+32 of the block): every kept row's word of
-        // a column is fetched in one go, OR-reduced across the warp with REDUX and merged by one shared-memory atomic.
-        // The loads of up to 14 columns are issued before the first reduction, so a block is folded in ~1 L2 latency.
-        const int ww = warp - 1;
-        if (ww < kFoldGroups * kFoldWarps) {
+        // 24 worker warps = 4 groups x 6 warps, all on warp slots with (warp & 3) != 0: warp w issues from scheduler
+        // w & 3, so the resolver warp (warp 0) has scheduler 0 to itself and its dependent chain is never delayed by
+        // the workers' polling loops.  Group g folds blocks b = g, g+4, ...; inside a group warp wi takes a CONTIGUOUS
+        // run of columns (a kept row's words then share 32-byte sectors).  Lanes are ROWS (lane l: rows l and l+32 of
+        // the block): every kept row's word of a column is fetched in one go, OR-reduced across the warp with REDUX and
+        // merged by 32-bit shared-memory atomics (64-bit shared atomicOr is a CAS loop).
+        if ((warp & 3) != 0) {
+            const int ww = (warp >> 2) * 3 + (warp & 3) - 1;
             const int g = ww / kFoldWarps, wi = ww - g * kFoldWarps;
+            unsigned* remv32 = reinterpret_cast<unsigned*>(remv);
             for (int b = g; b < col_blocks; b += kFoldGroups) {
                 while (ld_volatile_s32(&s_resolved) < b + 1) { }
                 __threadfence_block();
@@ -465,21 +468,27 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
                 const bool k0 = (kept >> lane) & 1ULL, k1 = (kept >> (lane + 32)) & 1ULL;
                 const u64* row0 = mask + (size_t)(b * kNmsTile + lane) * col_blocks;
                 const u64* row1 = row0 + (size_t)32 * col_blocks;
-                for (int j0 = b + REACH + wi; j0 < col_blocks; j0 += kFoldWarps * 14) {
-                    u64 v[14];
+                const int ncols = col_blocks - (b + REACH);
+                const int chunk = (ncols + kFoldWarps - 1) / kFoldWarps;
+                const int jb = b + REACH + wi * chunk, je = min(jb + chunk, col_blocks);
+                for (int j0 = jb; j0 < je; j0 += 10) {
+                    u64 v[10];
 #pragma unroll
-                    for (int t = 0; t < 14; ++t) {
-                        const int j = j0 + t * kFoldWarps;
+                    for (int t = 0; t < 10; ++t) {
+                        const int j = j0 + t;
                         u64 x = 0;
-                        if (j < col_blocks) { if (k0) x = row0[j]; if (k1) x |= row1[j]; }
+                        if (j < je) { if (k0) x = row0[j]; if (k1) x |= row1[j]; }
                         v[t] = x;
                     }
 #pragma unroll
-                    for (int t = 0; t < 14; ++t) {
-                        const int j = j0 + t * kFoldWarps;
+                    for (int t = 0; t < 10; ++t) {
+                        const int j = j0 + t;
                         const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v[t]);
                         const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v[t] >> 32));
-                        if (lane == 0 && j < col_blocks && (lo | hi)) atomicOr(&remv[j], ((u64)hi << 32) | lo);
+                        if (lane == 0 && j < je) {
+                            if (lo) atomicOr(&remv32[2 * j], lo);
+                            if (hi) atomicOr(&remv32[2 * j + 1], hi);
+                        }
                     }
                 }
                 __threadfence_block();
