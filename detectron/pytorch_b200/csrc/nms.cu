@@ -44,7 +44,7 @@ __device__ __forceinline__ bool nms_bit(float a0, float a1, float a2, float a3, 
 // grid = (col_blocks, row_blocks); tiles below the diagonal exit immediately (their mask words
 // are never read by the scan).
 __global__ void __launch_bounds__(kNmsTile)
-nms_mask_kernel(const float* __restrict__ boxes, int n, int dim, float thresh, u64* __restrict__ mask) {
+nms_mask_kernel(const float* __restrict__ boxes, int n, int dim, float thresh, u64* __restrict__ mask, u64* __restrict__ diag_t) {
     const int row_start = blockIdx.y, col_start = blockIdx.x;
     if (row_start > col_start) return;
     const int row_size = min(n - row_start * kNmsTile, kNmsTile);
@@ -69,6 +69,18 @@ nms_mask_kernel(const float* __restrict__ boxes, int n, int dim, float thresh, u
         }
         const int col_blocks = (n + kNmsTile - 1) / kNmsTile;
         mask[(size_t)cur * col_blocks + col_start] = t;
+        if (row_start == col_start) {
+            // Transposed diagonal word: bit j (< own index) <=> box j's mask word has this box's bit set.  Same function,
+            // same operand roles (box j is the "row" box with the rounded area) as the thread of row j evaluates above,
+            // so the two are the same bits by construction.  Used by the resolver scan's parallel block resolve.
+            u64 tt = 0;
+            for (int j = 0; j < (int)threadIdx.x; ++j) {
+                const ColBox r = cols[j];
+                const float Sr = __fmul_rn(__fadd_rn(__fsub_rn(r.x1, r.x0), 1.f), __fadd_rn(__fsub_rn(r.y1, r.y0), 1.f));
+                if (nms_bit(r.x0, r.y0, r.x1, r.y1, Sr, a0, a1, a2, a3, thresh)) tt |= 1ULL << j;
+            }
+            diag_t[cur] = tt;
+        }
     }
 }
 
@@ -359,19 +371,25 @@ nms_scan_decoupled_kernel(const u64* __restrict__ mask, int n, int col_blocks, i
     }
 }
 
-// Resolver scan (default while REACH * n * 8 B fits shared memory): everything the greedy chain itself touches --
-// the diagonal word of every row and the REACH-1 words right of it -- is copied to shared memory once, so the
-// single resolver warp never waits for global memory: per 64-box block it resolves (branch-free, diagonal words
-// prefetched a batch ahead) and derives from its own kept rows the contribution to the next REACH-1 column
-// blocks.  28 worker warps (4 groups x 7) fold the kept rows into the remaining columns (j >= block + REACH)
-// straight from global memory with every load of a block in flight at once; the resolver only checks that the
-// block REACH steps back has been folded.
+// Resolver scan (default while REACH * n * 8 B fits shared memory).  Everything the greedy chain itself touches is
+// copied to shared memory once, so the single resolver warp never waits for global memory:
+//   * T[i]   -- the TRANSPOSED diagonal word of box i (which earlier boxes of its own 64-block suppress it), and
+//   * D[t][i] -- the mask words t = 1 .. REACH-1 column blocks right of the diagonal.
+// A block is resolved in parallel, lanes = boxes (two per lane), by iterating to the fixed point of the greedy rule:
+// an undecided box whose in-block suppressors are all removed is kept; one with a kept suppressor is removed.  The
+// lowest undecided box is decided in every round, so this terminates with exactly the sequential result; the number
+// of rounds is the longest suppression chain inside the block (2-4 for proposal-like inputs, 64 at worst) instead of
+// 64 dependent steps.  The resolver then derives from its own kept rows the contribution to the next REACH-1 column
+// blocks.  24 worker warps (4 groups x 6) fold the kept rows into the remaining columns (j >= block + REACH) from
+// global memory, lanes = columns (coalesced 256-byte row segments, up to 16 rows in flight per warp); the resolver
+// only checks that the block REACH steps back has been folded.
 template <int REACH>
 __global__ void __launch_bounds__(kScanThreads)
-nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, int* __restrict__ keep_out, int* __restrict__ num_out) {
+nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ diag_t, int n, int col_blocks,
+                         int* __restrict__ keep_out, int* __restrict__ num_out) {
     extern __shared__ u64 sm[];
     const int n_pad = col_blocks * kNmsTile;
-    u64* D = sm;                                    // D[t][i] = mask[i][blk(i) + t], t < REACH
+    u64* D = sm;                                    // D[0][i] = T[i]; D[t][i] = mask[i][blk(i) + t], 1 <= t < REACH
     u64* remv = D + (size_t)REACH * n_pad;          // [col_blocks]  contributions of blocks <= j - REACH (workers, smem atomics)
     u64* kept_hist = remv + col_blocks;             // [col_blocks]
     volatile int* fold_done = reinterpret_cast<volatile int*>(kept_hist + col_blocks);   // [col_blocks] warps that finished folding
@@ -381,8 +399,9 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
     for (int i = tid; i < n_pad; i += kScanThreads) {
         const int cbk = i >> 6;
         const u64* row = mask + (size_t)i * col_blocks + cbk;
+        D[i] = (i < n) ? diag_t[i] : 0ULL;
 #pragma unroll
-        for (int t = 0; t < REACH; ++t) D[(size_t)t * n_pad + i] = (i < n && cbk + t < col_blocks) ? row[t] : 0ULL;
+        for (int t = 1; t < REACH; ++t) D[(size_t)t * n_pad + i] = (i < n && cbk + t < col_blocks) ? row[t] : 0ULL;
     }
     for (int j = tid; j < col_blocks; j += kScanThreads) { remv[j] = 0; fold_done[j] = 0; }
     if (tid == 0) s_resolved = 0;
@@ -394,41 +413,31 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
         for (int t = 0; t < REACH; ++t) c[t] = 0;
         int count = 0;
         unsigned long long* const timing = g_nms_timing;
-        long long t_wait = 0, t_res = 0, t_rest = 0;
+        long long t_wait = 0, t_res = 0, t_rest = 0, rounds = 0;
+        const u64 bit0 = 1ULL << lane, bit1 = 1ULL << (lane + 32);
         for (int b = 0; b < col_blocks; ++b) {
+            const u64 T0 = D[b * kNmsTile + lane], T1 = D[b * kNmsTile + lane + 32];
             const long long t0 = timing ? clock64() : 0;
             if (b >= REACH) { while (fold_done[b - REACH] < kFoldWarps) { } }
             __threadfence_block();
             const long long t1 = timing ? clock64() : 0;
             const int lim = min(kNmsTile, n - b * kNmsTile);
-            const u64 r0 = *reinterpret_cast<volatile u64*>(&remv[b]) | c[1];
-            // 64-step greedy resolve on 32-bit halves: per box one bit test that sets a predicate and predicated
-            // ORs -- two dependent ALU operations.  The diagonal words are fetched 8 boxes ahead (uint2 loads).
-            unsigned r_lo = (unsigned)r0, r_hi = (unsigned)(r0 >> 32), kept_lo = 0u, kept_hi = 0u;
-            const uint2* diag = reinterpret_cast<const uint2*>(D + b * kNmsTile);
-            uint2 d[2][8];
-#pragma unroll
-            for (int i8 = 0; i8 < 8; ++i8) d[0][i8] = diag[i8];
-#pragma unroll
-            for (int k0 = 0; k0 < kNmsTile; k0 += 8) {
-                const int cur = (k0 >> 3) & 1;
-                if (k0 + 8 < kNmsTile) {
-#pragma unroll
-                    for (int i8 = 0; i8 < 8; ++i8) d[cur ^ 1][i8] = diag[k0 + 8 + i8];
-                }
-#pragma unroll
-                for (int i8 = 0; i8 < 8; ++i8) {
-                    const int k = k0 + i8;
-                    if (k < 32) {
-                        if (!(r_lo & (1u << k))) { kept_lo |= 1u << k; r_lo |= d[cur][i8].x; r_hi |= d[cur][i8].y; }
-                    } else {                        // a diagonal word only has bits above its own row: the low half is dead
-                        if (!(r_hi & (1u << (k - 32)))) { kept_hi |= 1u << (k - 32); r_hi |= d[cur][i8].y; }
-                    }
-                }
+            u64 rem = *reinterpret_cast<volatile u64*>(&remv[b]) | c[1];
+            if (lim < kNmsTile) rem |= ~((1ULL << lim) - 1ULL);       // padded rows: decided, never kept
+            u64 kept = 0;
+            while ((kept | rem) != ~0ULL) {
+                const u64 dec = kept | rem;
+                const bool u0 = !(dec & bit0), u1 = !(dec & bit1);
+                const bool nk0 = u0 && !(T0 & ~rem), nk1 = u1 && !(T1 & ~rem);      // every suppressor already removed
+                const bool nr0 = u0 && (T0 & kept), nr1 = u1 && (T1 & kept);        // suppressed by a kept box
+                const unsigned k_lo = __ballot_sync(0xffffffffu, nk0), k_hi = __ballot_sync(0xffffffffu, nk1);
+                const unsigned r_lo = __ballot_sync(0xffffffffu, nr0), r_hi = __ballot_sync(0xffffffffu, nr1);
+                kept |= ((u64)k_hi << 32) | k_lo;
+                rem |= ((u64)r_hi << 32) | r_lo;
+                if (timing) ++rounds;
             }
-            u64 kept = ((u64)kept_hi << 32) | kept_lo;
+            if (lane == 0) { kept_hist[b] = kept; __threadfence_block(); *reinterpret_cast<volatile int*>(&s_resolved) = b + 1; }
             const long long t2 = timing ? clock64() : 0;
-            if (lim < kNmsTile) kept &= (1ULL << lim) - 1ULL;      // padded rows have zero masks but must not be kept
             // contributions of this block's kept rows to the next REACH-1 columns; shift the carries by one column
             const bool ka = (kept >> lane) & 1ULL, kb2 = (kept >> (lane + 32)) & 1ULL;
 #pragma unroll
@@ -441,7 +450,6 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
                 const u64 kt = ((u64)hi << 32) | lo;
                 c[t] = ((t + 1 < REACH) ? c[t + 1] : 0ULL) | kt;
             }
-            if (lane == 0) { kept_hist[b] = kept; __threadfence_block(); *reinterpret_cast<volatile int*>(&s_resolved) = b + 1; }
             const u64 lo_mask = (1ULL << lane) - 1ULL;
             if (ka) keep_out[count + __popcll(kept & lo_mask)] = b * kNmsTile + lane;
             if (kb2) keep_out[count + __popcll(kept & ((lo_mask << 32) | 0xffffffffULL))] = b * kNmsTile + lane + 32;
@@ -449,53 +457,62 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, int n, int col_blocks, in
             if (timing) { const long long t3 = clock64(); t_wait += t1 - t0; t_res += t2 - t1; t_rest += t3 - t2; }
         }
         if (lane == 0) *num_out = count;
-        if (timing && lane == 0) { timing[0] = t_wait; timing[1] = t_res; timing[2] = t_rest; timing[3] = col_blocks; }
-    } else {
-        // 24 worker warps = 4 groups x 6 warps, all on warp slots with (warp & 3) != 0: warp w issues from scheduler
-        // w & 3, so the resolver warp (warp 0) has scheduler 0 to itself and its dependent chain is never delayed by
-        // the workers' polling loops.  Group g folds blocks b = g, g+4, ...; inside a group warp wi takes a CONTIGUOUS
-        // run of columns (a kept row's words then share 32-byte sectors).  Lanes are ROWS (lane l: rows l and l+32 of
-        // the block): every kept row's word of a column is fetched in one go, OR-reduced across the warp with REDUX and
-        // merged by 32-bit shared-memory atomics (64-bit shared atomicOr is a CAS loop).
-        if ((warp & 3) != 0) {
-            const int ww = (warp >> 2) * 3 + (warp & 3) - 1;
-            const int g = ww / kFoldWarps, wi = ww - g * kFoldWarps;
-            unsigned* remv32 = reinterpret_cast<unsigned*>(remv);
-            for (int b = g; b < col_blocks; b += kFoldGroups) {
-                while (ld_volatile_s32(&s_resolved) < b + 1) { }
-                __threadfence_block();
-                const u64 kept = *reinterpret_cast<volatile u64*>(&kept_hist[b]);
-                const bool k0 = (kept >> lane) & 1ULL, k1 = (kept >> (lane + 32)) & 1ULL;
-                const u64* row0 = mask + (size_t)(b * kNmsTile + lane) * col_blocks;
-                const u64* row1 = row0 + (size_t)32 * col_blocks;
-                const int ncols = col_blocks - (b + REACH);
-                const int chunk = (ncols + kFoldWarps - 1) / kFoldWarps;
-                const int jb = b + REACH + wi * chunk, je = min(jb + chunk, col_blocks);
-                for (int j0 = jb; j0 < je; j0 += 10) {
-                    u64 v[10];
+        if (timing && lane == 0) { timing[0] = t_wait; timing[1] = t_res; timing[2] = t_rest; timing[3] = col_blocks; timing[4] = rounds; }
+    } else if ((warp & 3) != 0) {
+        // Workers sit on warp slots with (warp & 3) != 0: warp w issues from scheduler w & 3, so the resolver warp has
+        // scheduler 0 to itself and its dependent chain is never delayed by the workers' polling loops.  Group g folds
+        // blocks b = g, g+4, ...; the block's (32-column chunk, row part) units are dealt round-robin to its 6 warps.
+        // Shared-memory merges are 32-bit atomics (a 64-bit shared atomicOr is a CAS loop).
+        const int ww = (warp >> 2) * 3 + (warp & 3) - 1;
+        const int g = ww / kFoldWarps, wi = ww - g * kFoldWarps;
+        unsigned* remv32 = reinterpret_cast<unsigned*>(remv);
+        unsigned long long* const timing = (ww == 0) ? g_nms_timing : nullptr;
+        long long t_spin = 0, t_fold = 0, folds = 0;
+        for (int b = g; b < col_blocks; b += kFoldGroups) {
+            const long long t0 = timing ? clock64() : 0;
+            while (ld_volatile_s32(&s_resolved) < b + 1) { }
+            __threadfence_block();
+            const long long t1 = timing ? clock64() : 0;
+            const u64 kept = *reinterpret_cast<volatile u64*>(&kept_hist[b]);
+            const int ncols = col_blocks - (b + REACH);
+            if (ncols > 0) {
+                const int nchunks = (ncols + 31) >> 5;
+                const int part_shift = (nchunks == 1) ? 2 : 1;            // 4 row parts of 16 rows, else 2 of 32
+                const int rows_per = kNmsTile >> part_shift;
+                const int units = nchunks << part_shift;
+                for (int u = wi; u < units; u += kFoldWarps) {
+                    const int cch = u >> part_shift, part = u & ((1 << part_shift) - 1);
+                    unsigned kb = (unsigned)(kept >> (part * rows_per));
+                    if (rows_per < 32) kb &= (1u << rows_per) - 1u;
+                    const int j = b + REACH + cch * 32 + lane;
+                    const bool jok = j < col_blocks;
+                    const u64* base = mask + (size_t)(b * kNmsTile + part * rows_per) * col_blocks + (jok ? j : 0);
+                    u64 acc = 0;
+                    while (kb) {
+                        u64 v[16];
 #pragma unroll
-                    for (int t = 0; t < 10; ++t) {
-                        const int j = j0 + t;
-                        u64 x = 0;
-                        if (j < je) { if (k0) x = row0[j]; if (k1) x |= row1[j]; }
-                        v[t] = x;
-                    }
-#pragma unroll
-                    for (int t = 0; t < 10; ++t) {
-                        const int j = j0 + t;
-                        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v[t]);
-                        const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v[t] >> 32));
-                        if (lane == 0 && j < je) {
-                            if (lo) atomicOr(&remv32[2 * j], lo);
-                            if (hi) atomicOr(&remv32[2 * j + 1], hi);
+                        for (int t = 0; t < 16; ++t) {
+                            const bool has = kb != 0u;
+                            const int r = has ? (__ffs(kb) - 1) : 0;
+                            v[t] = (has && jok) ? base[(size_t)r * col_blocks] : 0ULL;
+                            kb &= kb - 1u;
                         }
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) acc |= v[t];
+                    }
+                    if (jok) {
+                        const unsigned lo = (unsigned)acc, hi = (unsigned)(acc >> 32);
+                        if (lo) atomicOr(&remv32[2 * j], lo);
+                        if (hi) atomicOr(&remv32[2 * j + 1], hi);
                     }
                 }
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) atomicAdd(const_cast<int*>(&fold_done[b]), 1);
             }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) atomicAdd(const_cast<int*>(&fold_done[b]), 1);
+            if (timing) { const long long t2 = clock64(); t_spin += t1 - t0; t_fold += t2 - t1; ++folds; }
         }
+        if (timing && lane == 0) { timing[5] = t_spin; timing[6] = t_fold; timing[7] = folds; }
     }
 }
 
@@ -506,7 +523,7 @@ void nms_set_timing_buffer(unsigned long long* buf) { cudaMemcpyToSymbol(g_nms_t
 size_t nms_workspace_bytes(int n) {
     if (n <= 0) return 256;
     const size_t cb = (size_t)(n + kNmsTile - 1) / kNmsTile;
-    return ((size_t)n * cb * sizeof(u64) + 255) / 256 * 256;
+    return (((size_t)n * cb + cb * kNmsTile) * sizeof(u64) + 255) / 256 * 256;     // mask words + transposed diagonal words
 }
 
 int nms(const float* boxes, int n, int dim, float thresh, int* keep_out, int* num_out, void* workspace,
@@ -519,8 +536,9 @@ int nms(const float* boxes, int n, int dim, float thresh, int* keep_out, int* nu
     if (workspace == nullptr || workspace_bytes < nms_workspace_bytes(n)) return B200_ROI_EWORKSPACE;
     const int cb = (n + kNmsTile - 1) / kNmsTile;
     u64* mask = (u64*)workspace;
+    u64* diag_t = mask + (size_t)n * cb;
     dim3 grid(cb, cb);
-    nms_mask_kernel<<<grid, kNmsTile, 0, stream>>>(boxes, n, dim, thresh, mask);
+    nms_mask_kernel<<<grid, kNmsTile, 0, stream>>>(boxes, n, dim, thresh, mask, diag_t);
     const char* e_mode = getenv("B200_NMS_SCAN");             // "pipelined" / "decoupled" select the older scans (A/B tests)
     const bool old_scan = e_mode && (e_mode[0] == 'p' || e_mode[0] == 'd');
     for (int reach = 4; reach >= 3 && !old_scan; --reach) {
@@ -530,8 +548,8 @@ int nms(const float* boxes, int n, int dim, float thresh, int* keep_out, int* nu
             ? cudaFuncSetAttribute(nms_scan_resolver_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res)
             : cudaFuncSetAttribute(nms_scan_resolver_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res);
         if (e != cudaSuccess) return (int)e;
-        if (reach == 4) nms_scan_resolver_kernel<4><<<1, kScanThreads, smem_res, stream>>>(mask, n, cb, keep_out, num_out);
-        else nms_scan_resolver_kernel<3><<<1, kScanThreads, smem_res, stream>>>(mask, n, cb, keep_out, num_out);
+        if (reach == 4) nms_scan_resolver_kernel<4><<<1, kScanThreads, smem_res, stream>>>(mask, diag_t, n, cb, keep_out, num_out);
+        else nms_scan_resolver_kernel<3><<<1, kScanThreads, smem_res, stream>>>(mask, diag_t, n, cb, keep_out, num_out);
         return finish_launch(2);
     }
     const size_t smem_pipe = sizeof(u64) * (2 * (((size_t)cb + 1) / 2 * 2) + 2 * (size_t)kNmsTile * cb);

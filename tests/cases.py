@@ -39,3 +39,24 @@ def crop_case(seed=0):
 
 def nms_case(n, seed=0):
     return S.make_nms_boxes(n, seed=seed)
+
+
+def nms_chain_case(n, shift=10.0, width=100.0):
+    """Worst case of the block-parallel resolve: box i overlaps box i+1 above 0.7 but not box i+2, so the greedy
+    result alternates keep / drop and every decision depends on the previous one (suppression chain of length n)."""
+    import numpy as np
+    x1 = np.arange(n, dtype=np.float32) * np.float32(shift)
+    b = np.stack([x1, np.zeros(n, np.float32), x1 + np.float32(width), np.full(n, 50, np.float32),
+                  np.linspace(1.0, 0.1, n).astype(np.float32)], axis=1)
+    return b.astype(np.float32)
+
+
+def nms_clustered_case(n, seed=0, copies=10):
+    """Score-sorted proposals where near-duplicates are ADJACENT in the order (dense diagonal blocks)."""
+    import numpy as np
+    b = S.make_nms_boxes(n, seed=seed, copies=copies)
+    rng = np.random.RandomState(seed + 1)
+    seeds = b[rng.permutation(n)[: max(1, n // copies)], :4]
+    rep = np.repeat(seeds, copies, axis=0)[:n] + rng.normal(0, 2.0, (n, 4)).astype(np.float32)
+    rep[:, 2:] = np.maximum(rep[:, 2:], rep[:, :2] + 1)
+    return np.concatenate([rep, b[:, 4:5]], axis=1).astype(np.float32)

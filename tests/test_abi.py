@@ -48,9 +48,9 @@ def test_argument_validation_without_gpu():
     assert b"invalid argument" in lib.b200_roi_ops_strerror(EINVAL)
     assert lib.b200_roi_ops_strerror(0) == b"success"
     # workspace sizing is pure host arithmetic: n rows x ceil(n/64) 64-bit words
-    assert lib.b200_nms_workspace_bytes(6000) == 6000 * 94 * 8
+    assert lib.b200_nms_workspace_bytes(6000) == (6000 * 94 + 94 * 64) * 8      # mask words + transposed diagonal words
     assert lib.b200_nms_workspace_bytes(0) > 0
-    assert lib.b200_nms_workspace_bytes(64) == 64 * 8
+    assert lib.b200_nms_workspace_bytes(64) == (64 + 64) * 8
 
 
 def test_workspace_sizing_is_host_arithmetic():

@@ -274,6 +274,21 @@ def test_nms_large_input_uses_fallback_scan():
     assert np.array_equal(k, O.nms_cuda(b, 0.7))
 
 
+@pytest.mark.parametrize("n", [63, 64, 65, 1000, 4097])
+def test_nms_suppression_chain(n):
+    b = cases.nms_chain_case(n)             # every decision depends on the previous one: 64 resolve rounds per block
+    k = nms_gpu(dev(b), 0.7).cpu().numpy().reshape(-1)
+    assert np.array_equal(k, O.nms_cuda(b, 0.7))
+    assert np.array_equal(k, np.arange(0, n, 2))
+
+
+@pytest.mark.parametrize("n,thresh", [(3000, 0.7), (6000, 0.5), (777, 0.3)])
+def test_nms_clustered_order(n, thresh):
+    b = cases.nms_clustered_case(n, seed=n)
+    k = nms_gpu(dev(b), thresh).cpu().numpy().reshape(-1)
+    assert np.array_equal(k, O.nms_cuda(b, thresh))
+
+
 def test_nms_edge_cases():
     assert nms_wrapper(torch.zeros((0, 5), device="cuda"), 0.7) == []
     one = dev(np.array([[0, 0, 10, 10, 0.5]], np.float32))
