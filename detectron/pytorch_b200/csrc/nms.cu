@@ -18,9 +18,13 @@ namespace b200 {
 
 constexpr int kNmsTile = 64;
 constexpr int kScanThreads = 1024;
-constexpr int kFoldGroups = 4, kFoldWarps = 6;      // resolver scan: 4 blocks folded concurrently by 6 warps each (24 worker warps)
+constexpr int kFoldGroups = 2, kFoldWarps = 12;     // resolver scan: 2 blocks folded concurrently by 12 warps each (24 worker warps)
 
 typedef unsigned long long u64;
+
+// acq_rel fence at CTA scope (MEMBAR.ALL.CTA).  __threadfence_block() is membar.cta = fence.sc.cta, the much slower
+// sequentially-consistent flavour, which the flag handshakes below do not need.
+__device__ __forceinline__ void cta_fence() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
 // Debug: per-phase clock64 totals of the resolver warp (tools/nms_probe.py); null by default.
 __device__ unsigned long long* g_nms_timing = nullptr;
@@ -380,8 +384,8 @@ nms_scan_decoupled_kernel(const u64* __restrict__ mask, int n, int col_blocks, i
 // lowest undecided box is decided in every round, so this terminates with exactly the sequential result; the number
 // of rounds is the longest suppression chain inside the block (2-4 for proposal-like inputs, 64 at worst) instead of
 // 64 dependent steps.  The resolver then derives from its own kept rows the contribution to the next REACH-1 column
-// blocks.  24 worker warps (4 groups x 6) fold the kept rows into the remaining columns (j >= block + REACH) from
-// global memory, lanes = columns (coalesced 256-byte row segments, up to 16 rows in flight per warp); the resolver
+// blocks.  24 worker warps (2 groups x 12) fold the kept rows into the remaining columns (j >= block + REACH) from
+// global memory, lanes = columns (coalesced 256-byte row segments, 8 rows in flight per warp); the resolver
 // only checks that the block REACH steps back has been folded.
 template <int REACH>
 __global__ void __launch_bounds__(kScanThreads)
@@ -419,7 +423,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
             const u64 T0 = D[b * kNmsTile + lane], T1 = D[b * kNmsTile + lane + 32];
             const long long t0 = timing ? clock64() : 0;
             if (b >= REACH) { while (fold_done[b - REACH] < kFoldWarps) { } }
-            __threadfence_block();
+            cta_fence();
             const long long t1 = timing ? clock64() : 0;
             const int lim = min(kNmsTile, n - b * kNmsTile);
             u64 rem = *reinterpret_cast<volatile u64*>(&remv[b]) | c[1];
@@ -436,7 +440,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
                 rem |= ((u64)r_hi << 32) | r_lo;
                 if (timing) ++rounds;
             }
-            if (lane == 0) { kept_hist[b] = kept; __threadfence_block(); *reinterpret_cast<volatile int*>(&s_resolved) = b + 1; }
+            if (lane == 0) { kept_hist[b] = kept; cta_fence(); *reinterpret_cast<volatile int*>(&s_resolved) = b + 1; }
             const long long t2 = timing ? clock64() : 0;
             // contributions of this block's kept rows to the next REACH-1 columns; shift the carries by one column
             const bool ka = (kept >> lane) & 1ULL, kb2 = (kept >> (lane + 32)) & 1ULL;
@@ -461,7 +465,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
     } else if ((warp & 3) != 0) {
         // Workers sit on warp slots with (warp & 3) != 0: warp w issues from scheduler w & 3, so the resolver warp has
         // scheduler 0 to itself and its dependent chain is never delayed by the workers' polling loops.  Group g folds
-        // blocks b = g, g+4, ...; the block's (32-column chunk, row part) units are dealt round-robin to its 6 warps.
+        // blocks b = g, g+2, ...; the block's (32-column chunk, 16-row part) units are dealt round-robin to its 12 warps.
         // Shared-memory merges are 32-bit atomics (a 64-bit shared atomicOr is a CAS loop).
         const int ww = (warp >> 2) * 3 + (warp & 3) - 1;
         const int g = ww / kFoldWarps, wi = ww - g * kFoldWarps;
@@ -471,13 +475,13 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
         for (int b = g; b < col_blocks; b += kFoldGroups) {
             const long long t0 = timing ? clock64() : 0;
             while (ld_volatile_s32(&s_resolved) < b + 1) { }
-            __threadfence_block();
+            cta_fence();
             const long long t1 = timing ? clock64() : 0;
             const u64 kept = *reinterpret_cast<volatile u64*>(&kept_hist[b]);
             const int ncols = col_blocks - (b + REACH);
             if (ncols > 0) {
                 const int nchunks = (ncols + 31) >> 5;
-                const int part_shift = (nchunks == 1) ? 2 : 1;            // 4 row parts of 16 rows, else 2 of 32
+                constexpr int part_shift = 2;                             // 4 row parts of 16 rows: <= 12 units for <= 96 columns
                 const int rows_per = kNmsTile >> part_shift;
                 const int units = nchunks << part_shift;
                 for (int u = wi; u < units; u += kFoldWarps) {
@@ -488,17 +492,15 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
                     const bool jok = j < col_blocks;
                     const u64* base = mask + (size_t)(b * kNmsTile + part * rows_per) * col_blocks + (jok ? j : 0);
                     u64 acc = 0;
-                    while (kb) {
-                        u64 v[16];
+                    if (jok) {
+#pragma unroll 1
+                        for (int r0 = 0; r0 < rows_per; r0 += 8) {      // 8 predicated (warp-uniform) loads in flight
+                            u64 v[8];
 #pragma unroll
-                        for (int t = 0; t < 16; ++t) {
-                            const bool has = kb != 0u;
-                            const int r = has ? (__ffs(kb) - 1) : 0;
-                            v[t] = (has && jok) ? base[(size_t)r * col_blocks] : 0ULL;
-                            kb &= kb - 1u;
+                            for (int t = 0; t < 8; ++t) v[t] = ((kb >> (r0 + t)) & 1u) ? base[(size_t)(r0 + t) * col_blocks] : 0ULL;
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) acc |= v[t];
                         }
-#pragma unroll
-                        for (int t = 0; t < 16; ++t) acc |= v[t];
                     }
                     if (jok) {
                         const unsigned lo = (unsigned)acc, hi = (unsigned)(acc >> 32);
@@ -507,7 +509,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
                     }
                 }
             }
-            __threadfence_block();
+            cta_fence();
             __syncwarp();
             if (lane == 0) atomicAdd(const_cast<int*>(&fold_done[b]), 1);
             if (timing) { const long long t2 = clock64(); t_spin += t1 - t0; t_fold += t2 - t1; ++folds; }

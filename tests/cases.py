@@ -56,7 +56,7 @@ def nms_clustered_case(n, seed=0, copies=10):
     import numpy as np
     b = S.make_nms_boxes(n, seed=seed, copies=copies)
     rng = np.random.RandomState(seed + 1)
-    seeds = b[rng.permutation(n)[: max(1, n // copies)], :4]
+    seeds = b[rng.permutation(n)[: (n + copies - 1) // copies], :4]
     rep = np.repeat(seeds, copies, axis=0)[:n] + rng.normal(0, 2.0, (n, 4)).astype(np.float32)
     rep[:, 2:] = np.maximum(rep[:, 2:], rep[:, :2] + 1)
     return np.concatenate([rep, b[:, 4:5]], axis=1).astype(np.float32)

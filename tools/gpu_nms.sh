@@ -6,3 +6,5 @@ timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovi
 timeout 120 python tools/nms_probe.py | tee "$OUT/nms_probe.txt"
 B200_NMS_SCAN=decoupled timeout 120 python tools/nms_probe.py | tee -a "$OUT/nms_probe.txt"
 B200_NMS_SCAN=pipelined timeout 120 python tools/nms_probe.py | tee -a "$OUT/nms_probe.txt"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 24 --csv --log-file "$OUT/nms_launches.csv" python tools/nms_probe.py > /dev/null 2>&1
+grep -o 'b200::nms[a-z_]*\|"[0-9]*"$' "$OUT/nms_launches.csv" | paste - - | sort | uniq -c | sort -rn | head -8
