@@ -12,6 +12,7 @@
 // 1024 threads OR the kept rows into the running removal words) instead of a 4.5 MB blocking D2H
 // copy + single-threaded CPU loop + H2D; no cudaMalloc/cudaFree: scratch comes from the caller.
 #include "common.cuh"
+#include <math.h>
 #include <stdlib.h>
 
 namespace b200 {
@@ -25,6 +26,28 @@ typedef unsigned long long u64;
 // acq_rel fence at CTA scope (MEMBAR.ALL.CTA).  __threadfence_block() is membar.cta = fence.sc.cta, the much slower
 // sequentially-consistent flavour, which the flag handshakes below do not need.
 __device__ __forceinline__ void cta_fence() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
+// mbarrier handshakes (shared::cta): waiting warps are suspended by the hardware instead of polling shared memory
+// (24 polling warps saturate the LSU queue the resolver's own shared loads go through).  arrive = release,
+// try_wait = acquire at CTA scope, so no separate fences are needed around the flag.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 // Debug: per-phase clock64 totals of the resolver warp (tools/nms_probe.py); null by default.
 __device__ unsigned long long* g_nms_timing = nullptr;
@@ -45,46 +68,97 @@ __device__ __forceinline__ bool nms_bit(float a0, float a1, float a2, float a3, 
     return __fdiv_rn(inter, den) > thresh;
 }
 
-// grid = (col_blocks, row_blocks); tiles below the diagonal exit immediately (their mask words
-// are never read by the scan).
+struct __align__(16) ColBoxEx {
+    float x0, y0, x1, y1;
+    float bw, bh, pad0, pad1;           // (x1 - x0) + 1, (y1 - y0) + 1: the operands of the fused column-box area
+};
+
+// One CTA per 64x64 tile of the upper triangle (linear tile index: the diagonal tiles, which also produce the
+// transposed words, come first).  The IoU test is decided without the IEEE division whenever that is safe:
+// q' = inter * rcp.approx(den) is within 2^-21 (relative) of the correctly rounded quotient once den is a positive
+// normal number well inside the exponent range, so q' > thresh (1 + 2^-18) or q' < thresh (1 - 2^-18) settles the
+// comparison; everything else (the band around the threshold, den <= 0 / tiny / huge / NaN, thresholds outside
+// [2^-20, 2^20]: lo = -inf, hi = +inf) is marked undecided and re-evaluated with the exact recipe (nms_bit) after
+// the main loop.  Results are therefore bit-identical to the all-division version; the main loop is branch-free,
+// fully unrolled (bit positions are immediates) and ~26 instructions per pair instead of ~42.
 __global__ void __launch_bounds__(kNmsTile)
-nms_mask_kernel(const float* __restrict__ boxes, int n, int dim, float thresh, u64* __restrict__ mask, u64* __restrict__ diag_t) {
-    const int row_start = blockIdx.y, col_start = blockIdx.x;
-    if (row_start > col_start) return;
+nms_mask_kernel(const float* __restrict__ boxes, int n, int dim, float thresh, float lo, float hi,
+                u64* __restrict__ mask, u64* __restrict__ diag_t) {
+    const int col_blocks = (n + kNmsTile - 1) / kNmsTile;
+    int row_start, col_start;
+    {
+        const int idx = blockIdx.x;
+        if (idx < col_blocks) {
+            row_start = col_start = idx;
+        } else {                                    // k enumerates the pairs row < col: k = col (col - 1) / 2 + row
+            const int k = idx - col_blocks;
+            int c = (int)((1.f + sqrtf(1.f + 8.f * (float)k)) * 0.5f);
+            while ((long long)c * (c - 1) / 2 > k) --c;
+            while ((long long)(c + 1) * c / 2 <= k) ++c;
+            col_start = c;
+            row_start = k - (int)((long long)c * (c - 1) / 2);
+        }
+    }
     const int row_size = min(n - row_start * kNmsTile, kNmsTile);
     const int col_size = min(n - col_start * kNmsTile, kNmsTile);
-    __shared__ ColBox cols[kNmsTile];
-    if ((int)threadIdx.x < col_size) {
-        const float* p = boxes + (size_t)(col_start * kNmsTile + threadIdx.x) * dim;
-        ColBox b; b.x0 = p[0]; b.y0 = p[1]; b.x1 = p[2]; b.y1 = p[3];
+    __shared__ ColBoxEx cols[kNmsTile];
+    {
+        ColBoxEx b; b.x0 = b.y0 = b.x1 = b.y1 = 0.f; b.pad0 = b.pad1 = 0.f;
+        if ((int)threadIdx.x < col_size) {
+            const float* p = boxes + (size_t)(col_start * kNmsTile + threadIdx.x) * dim;
+            b.x0 = p[0]; b.y0 = p[1]; b.x1 = p[2]; b.y1 = p[3];
+        }
+        b.bw = __fadd_rn(__fsub_rn(b.x1, b.x0), 1.f);
+        b.bh = __fadd_rn(__fsub_rn(b.y1, b.y0), 1.f);
         cols[threadIdx.x] = b;
     }
     __syncthreads();
-    if ((int)threadIdx.x < row_size) {
-        const int cur = row_start * kNmsTile + threadIdx.x;
-        const float* a = boxes + (size_t)cur * dim;
-        const float a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
-        const float Sa = __fmul_rn(__fadd_rn(__fsub_rn(a2, a0), 1.f), __fadd_rn(__fsub_rn(a3, a1), 1.f));
-        u64 t = 0;
-        const int start = (row_start == col_start) ? threadIdx.x + 1 : 0;
-        for (int i = start; i < col_size; ++i) {
-            const ColBox b = cols[i];
-            if (nms_bit(a0, a1, a2, a3, Sa, b.x0, b.y0, b.x1, b.y1, thresh)) t |= 1ULL << i;
+    if ((int)threadIdx.x >= row_size) return;
+    const int cur = row_start * kNmsTile + threadIdx.x;
+    const float* a = boxes + (size_t)cur * dim;
+    const float a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
+    const float Sa = __fmul_rn(__fadd_rn(__fsub_rn(a2, a0), 1.f), __fadd_rn(__fsub_rn(a3, a1), 1.f));
+    unsigned t_lo = 0u, t_hi = 0u, u_lo = 0u, u_hi = 0u;        // decided-true bits / undecided bits
+    const float qnan = __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int i = 0; i < kNmsTile; ++i) {
+        const float4 bx = *reinterpret_cast<const float4*>(&cols[i].x0);
+        const float2 bs = *reinterpret_cast<const float2*>(&cols[i].bw);
+        const float left = fmaxf(a0, bx.x), right = fminf(a2, bx.z);
+        const float top = fmaxf(a1, bx.y), bottom = fminf(a3, bx.w);
+        const float w = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+        const float h = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+        const float inter = __fmul_rn(w, h);
+        const float den = __fsub_rn(__fmaf_rn(bs.x, bs.y, Sa), inter);
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+        const bool in_range = (__float_as_uint(den) - 0x20800000u) < (0x5E800000u - 0x20800000u);     // 2^-62 <= den < 2^62
+        const float q = in_range ? __fmul_rn(inter, r) : qnan;
+        const bool yes = q > hi, decided = yes || (q < lo);
+        if (i < 32) { if (yes) t_lo |= 1u << i; if (!decided) u_lo |= 1u << i; }
+        else        { if (yes) t_hi |= 1u << (i - 32); if (!decided) u_hi |= 1u << (i - 32); }
+    }
+    u64 t = ((u64)t_hi << 32) | t_lo, und = ((u64)u_hi << 32) | u_lo;
+    u64 live = (col_size == kNmsTile) ? ~0ULL : ((1ULL << col_size) - 1ULL);
+    if (row_start == col_start) live &= ~((2ULL << threadIdx.x) - 1ULL);       // only columns above the own index
+    t &= live; und &= live;
+    while (und) {                                   // rare: exact evaluation of the pairs the fast test could not settle
+        const int i = __ffsll((long long)und) - 1;
+        und &= und - 1ULL;
+        const ColBoxEx b = cols[i];
+        if (nms_bit(a0, a1, a2, a3, Sa, b.x0, b.y0, b.x1, b.y1, thresh)) t |= 1ULL << i;
+    }
+    mask[(size_t)cur * col_blocks + col_start] = t;
+    if (row_start == col_start) {
+        // Transposed diagonal word: bit j (< own index) <=> box j's mask word has this box's bit set.  Same function,
+        // same operand roles (box j is the "row" box with the rounded area) as the thread of row j evaluates, so the
+        // two are the same bits by construction.  Used by the resolver scan's parallel block resolve.
+        u64 tt = 0;
+        for (int j = 0; j < (int)threadIdx.x; ++j) {
+            const ColBoxEx r = cols[j];
+            if (nms_bit(r.x0, r.y0, r.x1, r.y1, __fmul_rn(r.bw, r.bh), a0, a1, a2, a3, thresh)) tt |= 1ULL << j;
         }
-        const int col_blocks = (n + kNmsTile - 1) / kNmsTile;
-        mask[(size_t)cur * col_blocks + col_start] = t;
-        if (row_start == col_start) {
-            // Transposed diagonal word: bit j (< own index) <=> box j's mask word has this box's bit set.  Same function,
-            // same operand roles (box j is the "row" box with the rounded area) as the thread of row j evaluates above,
-            // so the two are the same bits by construction.  Used by the resolver scan's parallel block resolve.
-            u64 tt = 0;
-            for (int j = 0; j < (int)threadIdx.x; ++j) {
-                const ColBox r = cols[j];
-                const float Sr = __fmul_rn(__fadd_rn(__fsub_rn(r.x1, r.x0), 1.f), __fadd_rn(__fsub_rn(r.y1, r.y0), 1.f));
-                if (nms_bit(r.x0, r.y0, r.x1, r.y1, Sr, a0, a1, a2, a3, thresh)) tt |= 1ULL << j;
-            }
-            diag_t[cur] = tt;
-        }
+        diag_t[cur] = tt;
     }
 }
 
@@ -396,8 +470,8 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
     u64* D = sm;                                    // D[0][i] = T[i]; D[t][i] = mask[i][blk(i) + t], 1 <= t < REACH
     u64* remv = D + (size_t)REACH * n_pad;          // [col_blocks]  contributions of blocks <= j - REACH (workers, smem atomics)
     u64* kept_hist = remv + col_blocks;             // [col_blocks]
-    volatile int* fold_done = reinterpret_cast<volatile int*>(kept_hist + col_blocks);   // [col_blocks] warps that finished folding
-    __shared__ int s_resolved;
+    u64* res_bar = kept_hist + col_blocks;          // [col_blocks] mbarrier: block resolved (1 arrival, resolver lane 0)
+    u64* fold_bar = res_bar + col_blocks;           // [col_blocks] mbarrier: block folded (kFoldWarps arrivals)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int i = tid; i < n_pad; i += kScanThreads) {
@@ -407,8 +481,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
 #pragma unroll
         for (int t = 1; t < REACH; ++t) D[(size_t)t * n_pad + i] = (i < n && cbk + t < col_blocks) ? row[t] : 0ULL;
     }
-    for (int j = tid; j < col_blocks; j += kScanThreads) { remv[j] = 0; fold_done[j] = 0; }
-    if (tid == 0) s_resolved = 0;
+    for (int j = tid; j < col_blocks; j += kScanThreads) { remv[j] = 0; mbar_init(&res_bar[j], 1); mbar_init(&fold_bar[j], kFoldWarps); }
     __syncthreads();
 
     if (warp == 0) {
@@ -422,8 +495,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
         for (int b = 0; b < col_blocks; ++b) {
             const u64 T0 = D[b * kNmsTile + lane], T1 = D[b * kNmsTile + lane + 32];
             const long long t0 = timing ? clock64() : 0;
-            if (b >= REACH) { while (fold_done[b - REACH] < kFoldWarps) { } }
-            cta_fence();
+            if (b >= REACH) mbar_wait(&fold_bar[b - REACH], 0);
             const long long t1 = timing ? clock64() : 0;
             const int lim = min(kNmsTile, n - b * kNmsTile);
             u64 rem = *reinterpret_cast<volatile u64*>(&remv[b]) | c[1];
@@ -440,7 +512,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
                 rem |= ((u64)r_hi << 32) | r_lo;
                 if (timing) ++rounds;
             }
-            if (lane == 0) { kept_hist[b] = kept; cta_fence(); *reinterpret_cast<volatile int*>(&s_resolved) = b + 1; }
+            if (lane == 0) { kept_hist[b] = kept; mbar_arrive(&res_bar[b]); }
             const long long t2 = timing ? clock64() : 0;
             // contributions of this block's kept rows to the next REACH-1 columns; shift the carries by one column
             const bool ka = (kept >> lane) & 1ULL, kb2 = (kept >> (lane + 32)) & 1ULL;
@@ -474,8 +546,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
         long long t_spin = 0, t_fold = 0, folds = 0;
         for (int b = g; b < col_blocks; b += kFoldGroups) {
             const long long t0 = timing ? clock64() : 0;
-            while (ld_volatile_s32(&s_resolved) < b + 1) { }
-            cta_fence();
+            mbar_wait(&res_bar[b], 0);
             const long long t1 = timing ? clock64() : 0;
             const u64 kept = *reinterpret_cast<volatile u64*>(&kept_hist[b]);
             const int ncols = col_blocks - (b + REACH);
@@ -509,9 +580,8 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
                     }
                 }
             }
-            cta_fence();
             __syncwarp();
-            if (lane == 0) atomicAdd(const_cast<int*>(&fold_done[b]), 1);
+            if (lane == 0) mbar_arrive(&fold_bar[b]);
             if (timing) { const long long t2 = clock64(); t_spin += t1 - t0; t_fold += t2 - t1; ++folds; }
         }
         if (timing && lane == 0) { timing[5] = t_spin; timing[6] = t_fold; timing[7] = folds; }
@@ -539,12 +609,18 @@ int nms(const float* boxes, int n, int dim, float thresh, int* keep_out, int* nu
     const int cb = (n + kNmsTile - 1) / kNmsTile;
     u64* mask = (u64*)workspace;
     u64* diag_t = mask + (size_t)n * cb;
-    dim3 grid(cb, cb);
-    nms_mask_kernel<<<grid, kNmsTile, 0, stream>>>(boxes, n, dim, thresh, mask, diag_t);
+    float lo = -INFINITY, hi = INFINITY;            // decision band of the division-free IoU test (see nms_mask_kernel)
+    if (thresh >= 9.5367431640625e-07f && thresh <= 1048576.f) {
+        lo = (float)((double)thresh * (1.0 - 3.814697265625e-06));
+        hi = (float)((double)thresh * (1.0 + 3.814697265625e-06));
+    }
+    const long long tiles = (long long)cb * (cb + 1) / 2;
+    if (tiles > 0x7fffffffLL) return B200_ROI_EINVAL;
+    nms_mask_kernel<<<(unsigned)tiles, kNmsTile, 0, stream>>>(boxes, n, dim, thresh, lo, hi, mask, diag_t);
     const char* e_mode = getenv("B200_NMS_SCAN");             // "pipelined" / "decoupled" select the older scans (A/B tests)
     const bool old_scan = e_mode && (e_mode[0] == 'p' || e_mode[0] == 'd');
     for (int reach = 4; reach >= 3 && !old_scan; --reach) {
-        const size_t smem_res = sizeof(u64) * ((size_t)reach * cb * kNmsTile + 2 * (size_t)cb) + sizeof(int) * (size_t)cb + 16;
+        const size_t smem_res = sizeof(u64) * ((size_t)reach * cb * kNmsTile + 4 * (size_t)cb) + 16;
         if (smem_res > 220 * 1024) continue;
         cudaError_t e = (reach == 4)
             ? cudaFuncSetAttribute(nms_scan_resolver_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res)
