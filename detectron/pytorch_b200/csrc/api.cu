@@ -73,9 +73,9 @@ const char* b200_roi_ops_strerror(int status) {
 
 unsigned long long b200_roi_ops_launch_count(void) { return g_launch_count; }
 
-void b200_roi_ops_debug_timing_buffer(void* device_u64x8) {
-    roi_align_tiled_set_timing_buffer((unsigned long long*)device_u64x8);
-    nms_set_timing_buffer((unsigned long long*)device_u64x8);
+void b200_roi_ops_debug_timing_buffer(void* device_u64x16) {
+    roi_align_tiled_set_timing_buffer((unsigned long long*)device_u64x16);
+    nms_set_timing_buffer((unsigned long long*)device_u64x16);
 }
 
 size_t b200_roi_align_workspace_bytes(int batch_size, int num_rois, int height, int width, int aligned_height,

@@ -27,6 +27,12 @@ typedef unsigned long long u64;
 // sequentially-consistent flavour, which the flag handshakes below do not need.
 __device__ __forceinline__ void cta_fence() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
+#ifdef B200_NMS_FOLD_CG
+#define B200_FOLD_LD(p) __ldcg(p)
+#else
+#define B200_FOLD_LD(p) (*(p))
+#endif
+
 // mbarrier handshakes (shared::cta): waiting warps are suspended by the hardware instead of polling shared memory
 // (24 polling warps saturate the LSU queue the resolver's own shared loads go through).  arrive = release,
 // try_wait = acquire at CTA scope, so no separate fences are needed around the flag.
@@ -490,7 +496,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
         for (int t = 0; t < REACH; ++t) c[t] = 0;
         int count = 0;
         unsigned long long* const timing = g_nms_timing;
-        long long t_wait = 0, t_res = 0, t_rest = 0, rounds = 0;
+        long long t_wait = 0, t_res = 0, t_rest = 0, t_keep = 0, rounds = 0;
         const u64 bit0 = 1ULL << lane, bit1 = 1ULL << (lane + 32);
         for (int b = 0; b < col_blocks; ++b) {
             const u64 T0 = D[b * kNmsTile + lane], T1 = D[b * kNmsTile + lane + 32];
@@ -526,14 +532,15 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
                 const u64 kt = ((u64)hi << 32) | lo;
                 c[t] = ((t + 1 < REACH) ? c[t + 1] : 0ULL) | kt;
             }
+            const long long t2b = timing ? clock64() : 0;
             const u64 lo_mask = (1ULL << lane) - 1ULL;
             if (ka) keep_out[count + __popcll(kept & lo_mask)] = b * kNmsTile + lane;
             if (kb2) keep_out[count + __popcll(kept & ((lo_mask << 32) | 0xffffffffULL))] = b * kNmsTile + lane + 32;
             count += __popcll(kept);
-            if (timing) { const long long t3 = clock64(); t_wait += t1 - t0; t_res += t2 - t1; t_rest += t3 - t2; }
+            if (timing) { const long long t3 = clock64(); t_wait += t1 - t0; t_res += t2 - t1; t_rest += t3 - t2; t_keep += t3 - t2b; }
         }
         if (lane == 0) *num_out = count;
-        if (timing && lane == 0) { timing[0] = t_wait; timing[1] = t_res; timing[2] = t_rest; timing[3] = col_blocks; timing[4] = rounds; }
+        if (timing && lane == 0) { timing[0] = t_wait; timing[1] = t_res; timing[2] = t_rest; timing[3] = col_blocks; timing[4] = rounds; timing[8] = t_keep; }
     } else if ((warp & 3) != 0) {
         // Workers sit on warp slots with (warp & 3) != 0: warp w issues from scheduler w & 3, so the resolver warp has
         // scheduler 0 to itself and its dependent chain is never delayed by the workers' polling loops.  Group g folds
@@ -543,7 +550,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
         const int g = ww / kFoldWarps, wi = ww - g * kFoldWarps;
         unsigned* remv32 = reinterpret_cast<unsigned*>(remv);
         unsigned long long* const timing = (ww == 0) ? g_nms_timing : nullptr;
-        long long t_spin = 0, t_fold = 0, folds = 0;
+        long long t_spin = 0, t_fold = 0, t_load = 0, folds = 0;
         for (int b = g; b < col_blocks; b += kFoldGroups) {
             const long long t0 = timing ? clock64() : 0;
             mbar_wait(&res_bar[b], 0);
@@ -568,11 +575,12 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
                         for (int r0 = 0; r0 < rows_per; r0 += 8) {      // 8 predicated (warp-uniform) loads in flight
                             u64 v[8];
 #pragma unroll
-                            for (int t = 0; t < 8; ++t) v[t] = ((kb >> (r0 + t)) & 1u) ? base[(size_t)(r0 + t) * col_blocks] : 0ULL;
+                            for (int t = 0; t < 8; ++t) v[t] = ((kb >> (r0 + t)) & 1u) ? B200_FOLD_LD(&base[(size_t)(r0 + t) * col_blocks]) : 0ULL;
 #pragma unroll
                             for (int t = 0; t < 8; ++t) acc |= v[t];
                         }
                     }
+                    if (timing) { t_load += clock64() - t1 + (long long)(acc == 0x123456789ULL); }
                     if (jok) {
                         const unsigned lo = (unsigned)acc, hi = (unsigned)(acc >> 32);
                         if (lo) atomicOr(&remv32[2 * j], lo);
@@ -584,7 +592,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
             if (lane == 0) mbar_arrive(&fold_bar[b]);
             if (timing) { const long long t2 = clock64(); t_spin += t1 - t0; t_fold += t2 - t1; ++folds; }
         }
-        if (timing && lane == 0) { timing[5] = t_spin; timing[6] = t_fold; timing[7] = folds; }
+        if (timing && lane == 0) { timing[5] = t_spin; timing[6] = t_fold; timing[7] = folds; timing[9] = t_load; }
     }
 }
 

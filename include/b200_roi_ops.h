@@ -147,7 +147,7 @@ B200_API int b200_nms(const float* boxes_dev, int boxes_num, int boxes_dim, floa
 B200_API unsigned long long b200_roi_ops_launch_count(void);
 /* Debug: register (or clear with NULL) a device buffer of 8 x uint64 into which the tiled RoIAlign forward
  * adds per-warp clock64 deltas [staging, compute, end-of-item wait, warp-items, RoI items, 8-bin groups, max compute]. */
-B200_API void b200_roi_ops_debug_timing_buffer(void* device_u64x8);
+B200_API void b200_roi_ops_debug_timing_buffer(void* device_u64x16);
 
 #ifdef __cplusplus
 }

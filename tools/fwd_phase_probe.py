@@ -7,7 +7,7 @@ cfg = S.CFG2
 f = torch.randn(cfg["shape"], device="cuda"); r = torch.from_numpy(S.make_rois(cfg["rois"], cfg["shape"], cfg["scale"])).cuda()
 for _ in range(3):
     ops.roi_align_forward(f, r, 7, 7, cfg["scale"], 2)
-buf = torch.zeros(8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(16, dtype=torch.int64, device="cuda")
 lib = _lib.load(); lib.b200_roi_ops_debug_timing_buffer(buf.data_ptr())
 n = 10
 for _ in range(n):
