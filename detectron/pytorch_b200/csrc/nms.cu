@@ -550,7 +550,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
         const int g = ww / kFoldWarps, wi = ww - g * kFoldWarps;
         unsigned* remv32 = reinterpret_cast<unsigned*>(remv);
         unsigned long long* const timing = (ww == 0) ? g_nms_timing : nullptr;
-        long long t_spin = 0, t_fold = 0, t_load = 0, folds = 0;
+        long long t_spin = 0, t_fold = 0, folds = 0;
         for (int b = g; b < col_blocks; b += kFoldGroups) {
             const long long t0 = timing ? clock64() : 0;
             mbar_wait(&res_bar[b], 0);
@@ -571,16 +571,18 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
                     const u64* base = mask + (size_t)(b * kNmsTile + part * rows_per) * col_blocks + (jok ? j : 0);
                     u64 acc = 0;
                     if (jok) {
-#pragma unroll 1
-                        for (int r0 = 0; r0 < rows_per; r0 += 8) {      // 8 predicated (warp-uniform) loads in flight
-                            u64 v[8];
+                        // all 16 rows of the part in flight at once; the address walks down the rows so that it
+                        // lives in one register pair instead of sixteen
+                        u64 v[16];
+                        const u64* p = base;
 #pragma unroll
-                            for (int t = 0; t < 8; ++t) v[t] = ((kb >> (r0 + t)) & 1u) ? B200_FOLD_LD(&base[(size_t)(r0 + t) * col_blocks]) : 0ULL;
-#pragma unroll
-                            for (int t = 0; t < 8; ++t) acc |= v[t];
+                        for (int t = 0; t < 16; ++t) {
+                            v[t] = ((kb >> t) & 1u) ? B200_FOLD_LD(p) : 0ULL;
+                            p += col_blocks;
                         }
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) acc |= v[t];
                     }
-                    if (timing) { t_load += clock64() - t1 + (long long)(acc == 0x123456789ULL); }
                     if (jok) {
                         const unsigned lo = (unsigned)acc, hi = (unsigned)(acc >> 32);
                         if (lo) atomicOr(&remv32[2 * j], lo);
@@ -592,7 +594,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
             if (lane == 0) mbar_arrive(&fold_bar[b]);
             if (timing) { const long long t2 = clock64(); t_spin += t1 - t0; t_fold += t2 - t1; ++folds; }
         }
-        if (timing && lane == 0) { timing[5] = t_spin; timing[6] = t_fold; timing[7] = folds; timing[9] = t_load; }
+        if (timing && lane == 0) { timing[5] = t_spin; timing[6] = t_fold; timing[7] = folds; }
     }
 }
 

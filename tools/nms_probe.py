@@ -22,4 +22,4 @@ t = buf.tolist()
 if t[3]:
     print("resolver cycles/block: wait-for-folds %.0f  resolve %.0f  carry+keep %.0f  (blocks %d, resolve rounds/block %.1f)" % (t[0] / t[3], t[1] / t[3], t[2] / t[3], t[3], t[4] / t[3]))
     if t[7]:
-        print("worker 0 cycles/fold: wait-for-resolver %.0f  fold %.0f  of which until loads consumed %.0f  (folds %d); resolver keep-stores %.0f/block" % (t[5] / t[7], t[6] / t[7], t[9] / t[7], t[7], t[8] / t[3]))
+        print("worker 0 cycles/fold: wait-for-resolver %.0f  fold %.0f  (folds %d); resolver keep-stores %.0f/block" % (t[5] / t[7], t[6] / t[7], t[7], t[8] / t[3]))
