@@ -7,9 +7,10 @@
 // the same integer logic -- box j is dropped iff a kept box i < j has bit (i, j) set.
 //
 // Differences in mechanism (not in results): only the upper triangle of 64x64 tiles is computed
-// (the reference commented its triangular skip out, :46, and did 2x the work); the suppression
-// scan runs on the GPU (one CTA; a warp resolves each 64-box diagonal block with shuffles, then
-// 1024 threads OR the kept rows into the running removal words) instead of a 4.5 MB blocking D2H
+// (the reference commented its triangular skip out, :46, and did 2x the work), with a division-free
+// fast path for the IoU test and the exact recipe for the pairs it cannot settle; the suppression
+// scan runs on the GPU (one CTA: a resolver warp walks the 64-box diagonal blocks, 24 worker warps
+// fold the kept rows into the running removal words behind it) instead of a 4.5 MB blocking D2H
 // copy + single-threaded CPU loop + H2D; no cudaMalloc/cudaFree: scratch comes from the caller.
 #include "common.cuh"
 #include <math.h>
@@ -26,6 +27,7 @@ typedef unsigned long long u64;
 // acq_rel fence at CTA scope (MEMBAR.ALL.CTA).  __threadfence_block() is membar.cta = fence.sc.cta, the much slower
 // sequentially-consistent flavour, which the flag handshakes below do not need.
 __device__ __forceinline__ void cta_fence() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+__device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 #ifdef B200_NMS_FOLD_CG
 #define B200_FOLD_LD(p) __ldcg(p)
@@ -221,240 +223,6 @@ nms_scan_kernel(const u64* __restrict__ mask, int n, int col_blocks, int* __rest
     if (tid == 0) *num_out = s_count;
 }
 
-// Pipelined scan (default): the greedy chain only ever needs, for block b, the 64 mask rows of block b.
-// Those do not depend on the scan state, so they are prefetched -- all 64 rows, kept or not -- two blocks
-// ahead with cp.async into a shared-memory ring; the critical path per block is then: wait, 64-step
-// shuffle resolve of the diagonal word, OR of the kept rows out of shared memory.  The mask is read
-// exactly once (upper triangle), and no global-memory latency sits on the dependency chain.
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__global__ void __launch_bounds__(kScanThreads)
-nms_scan_pipelined_kernel(const u64* __restrict__ mask, int n, int col_blocks, int* __restrict__ keep_out, int* __restrict__ num_out) {
-    extern __shared__ u64 sm[];
-    u64* remv = sm;                                   // [col_blocks]
-    u64* ring = sm + ((col_blocks + 1) & ~1);         // [2][64][col_blocks]
-    __shared__ u64 s_kept;
-    __shared__ int s_count;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t buf_words = (size_t)kNmsTile * col_blocks;
-
-    auto prefetch = [&](int b) {                      // rows of block b, columns [b, col_blocks): warp -> rows, lanes -> columns
-        if (b < col_blocks) {
-            u64* dst = ring + (size_t)(b & 1) * buf_words;
-            const int rows = min(kNmsTile, n - b * kNmsTile);
-            for (int k = warp; k < rows; k += kScanThreads / 32) {
-                const u64* src = mask + (size_t)(b * kNmsTile + k) * col_blocks;
-                u64* d = dst + (size_t)k * col_blocks;
-                for (int j = b + lane; j < col_blocks; j += 32) cp_async8(d + j, src + j);
-            }
-        }
-        cp_async_commit();
-    };
-
-    for (int j = tid; j < col_blocks; j += kScanThreads) remv[j] = 0;
-    if (tid == 0) s_count = 0;
-    prefetch(0);
-    prefetch(1);
-    for (int b = 0; b < col_blocks; ++b) {
-        cp_async_wait<1>();                           // block b's rows have landed (block b+1 may be in flight)
-        __syncthreads();
-        const u64* rows = ring + (size_t)(b & 1) * buf_words;
-        const int lim = min(kNmsTile, n - b * kNmsTile);
-        if (warp == 0) {
-            // Serial greedy resolve of the 64 boxes of block b.  Branch-free and fully unrolled: the diagonal
-            // words come from shared memory (broadcast loads that do not depend on the running state, so they
-            // are issued ahead), and the dependent chain per box is one bit test + one predicated OR.
-            u64 r = remv[b];
-            u64 kept = 0;
-            const u64* diag = rows + b;
-#pragma unroll
-            for (int k = 0; k < kNmsTile; ++k) {
-                const u64 dk = (k < lim) ? diag[(size_t)k * col_blocks] : 0ULL;
-                const bool alive = ((r >> k) & 1ULL) == 0ULL;
-                kept |= alive ? (1ULL << k) : 0ULL;
-                r |= alive ? dk : 0ULL;
-            }
-            if (lim < kNmsTile) kept &= (1ULL << lim) - 1ULL;
-            if (lane == 0) s_kept = kept;
-        }
-        __syncthreads();
-        const u64 kept = s_kept;
-        const int base = s_count;
-        if (tid < kNmsTile && ((kept >> tid) & 1ULL))
-            keep_out[base + __popcll(kept & ((1ULL << tid) - 1ULL))] = b * kNmsTile + tid;
-        // OR the rows of the kept boxes into the later column words.  lane = (column of a group of 4, row group of 8):
-        // every lane ORs <= 8 rows of its residue class, the 8 partials of a column are combined with shuffles,
-        // and one lane updates remv[j] (single writer per word, no atomics).  32 warps cover 128 columns per pass.
-        {
-            const int kg = lane & 7, jl = lane >> 3;
-            for (int j0 = b + 1 + warp * 4; j0 < col_blocks; j0 += (kScanThreads / 32) * 4) {
-                const int j = j0 + jl;
-                u64 acc = 0;
-                if (j < col_blocks) {
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const int k = kg + 8 * kk;
-                        if ((kept >> k) & 1ULL) acc |= rows[(size_t)k * col_blocks + j];
-                    }
-                }
-                acc |= __shfl_xor_sync(0xffffffffu, acc, 1);
-                acc |= __shfl_xor_sync(0xffffffffu, acc, 2);
-                acc |= __shfl_xor_sync(0xffffffffu, acc, 4);
-                if (kg == 0 && j < col_blocks && acc) remv[j] |= acc;
-            }
-        }
-        __syncthreads();                              // ring[b & 1] is free again; remv is complete for block b+1
-        if (tid == 0) s_count = base + __popcll(kept);
-        prefetch(b + 2);
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-    if (tid == 0) *num_out = s_count;
-}
-
-// Decoupled scan: the greedy chain is carried by ONE warp (the resolver); the other 31 warps (workers) prefetch
-// mask rows and fold the kept rows into the removal words in the background.  Per 64-box block the resolver
-// only (1) waits for the block's rows (prefetched two blocks ahead) and for the workers to have folded every
-// block <= b-2, (2) adds the contribution of block b-1 to column b itself (one masked OR-reduction over 64
-// words), (3) runs the 64-step branch-free resolve, (4) publishes the kept mask.  Nothing else sits on the
-// dependency chain.  Hand-offs use shared-memory progress counters (+ __threadfence_block) and a named
-// barrier among the workers only.
-__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kScanThreads - 32) : "memory"); }
-__device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
-
-__global__ void __launch_bounds__(kScanThreads)
-nms_scan_decoupled_kernel(const u64* __restrict__ mask, int n, int col_blocks, int* __restrict__ keep_out, int* __restrict__ num_out) {
-    extern __shared__ u64 sm[];
-    u64* remv = sm;                                          // [col_blocks] contributions folded by the workers
-    u64* kept_hist = sm + ((col_blocks + 1) & ~1);           // [col_blocks] kept mask of every resolved block
-    u64* ring = kept_hist + ((col_blocks + 1) & ~1);         // [2][64][col_blocks]
-    __shared__ int s_ring_ready;                             // rows of blocks < s_ring_ready have landed
-    __shared__ int s_resolved;                               // blocks < s_resolved are resolved (kept_hist valid)
-    __shared__ int s_folded;                                 // blocks < s_folded are folded into remv[j], j >= block + 2
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t buf_words = (size_t)kNmsTile * col_blocks;
-    constexpr int kWorkerWarps = kScanThreads / 32 - 1;
-
-    for (int j = tid; j < col_blocks; j += kScanThreads) remv[j] = 0;
-    if (tid == 0) { s_ring_ready = 0; s_resolved = 0; s_folded = 0; }
-    __syncthreads();
-
-    if (warp == 0) {
-        // ------------------------------------------------------------------ resolver
-        u64 carry = 0;                                       // contribution of block b-1 to column b
-        int count = 0;
-        for (int b = 0; b < col_blocks; ++b) {
-            while (ld_volatile_s32(&s_ring_ready) < b + 1) { }
-            while (ld_volatile_s32(&s_folded) < b - 1) { }
-            __threadfence_block();
-            const u64* rows = ring + (size_t)(b & 1) * buf_words;
-            const int lim = min(kNmsTile, n - b * kNmsTile);
-            u64 r = *reinterpret_cast<volatile u64*>(&remv[b]) | carry;
-            u64 kept = 0;
-            const u64* diag = rows + b;
-            // The 64 diagonal words do not depend on the running state: they are loaded 8 at a time, one batch
-            // AHEAD of the batch being resolved, so no shared-memory latency sits on the dependent chain
-            // (bit test -> predicated OR, ~2 ALU latencies per box).
-            u64 d[2][8];
-#pragma unroll
-            for (int i8 = 0; i8 < 8; ++i8) d[0][i8] = (i8 < lim) ? diag[(size_t)i8 * col_blocks] : 0ULL;
-#pragma unroll
-            for (int k0 = 0; k0 < kNmsTile; k0 += 8) {
-                const int cur = (k0 >> 3) & 1;
-                if (k0 + 8 < kNmsTile) {
-#pragma unroll
-                    for (int i8 = 0; i8 < 8; ++i8)
-                        d[cur ^ 1][i8] = (k0 + 8 + i8 < lim) ? diag[(size_t)(k0 + 8 + i8) * col_blocks] : 0ULL;
-                }
-#pragma unroll
-                for (int i8 = 0; i8 < 8; ++i8) {
-                    const int k = k0 + i8;
-                    const bool alive = ((r >> k) & 1ULL) == 0ULL;
-                    kept |= alive ? (1ULL << k) : 0ULL;
-                    r |= alive ? d[cur][i8] : 0ULL;
-                }
-            }
-            if (lim < kNmsTile) kept &= (1ULL << lim) - 1ULL;
-            // contribution of this block to the NEXT column, needed by the very next resolve.  It reads this block's
-            // rows, so it comes BEFORE the publication that lets the workers recycle the ring buffer.
-            carry = 0;
-            if (b + 1 < col_blocks) {
-                u64 c = 0;
-                if ((kept >> lane) & 1ULL) c |= rows[(size_t)lane * col_blocks + b + 1];
-                if ((kept >> (lane + 32)) & 1ULL) c |= rows[(size_t)(lane + 32) * col_blocks + b + 1];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) c |= __shfl_xor_sync(0xffffffffu, c, o);
-                carry = c;
-            }
-            if (lane == 0) { kept_hist[b] = kept; __threadfence_block(); *reinterpret_cast<volatile int*>(&s_resolved) = b + 1; }
-            // kept indices, ascending
-            const u64 lo_mask = (1ULL << lane) - 1ULL;
-            if ((kept >> lane) & 1ULL) keep_out[count + __popcll(kept & lo_mask)] = b * kNmsTile + lane;
-            if ((kept >> (lane + 32)) & 1ULL) keep_out[count + __popcll(kept & ((lo_mask << 32) | 0xffffffffULL))] = b * kNmsTile + lane + 32;
-            count += __popcll(kept);
-        }
-        if (lane == 0) *num_out = count;
-    } else {
-        // ------------------------------------------------------------------ workers
-        const int wt = tid - 32;                             // 0 .. 991
-        const int wwarp = warp - 1;
-        auto prefetch = [&](int b) {                         // rows of block b, columns [b, col_blocks)
-            if (b < col_blocks) {
-                u64* dst = ring + (size_t)(b & 1) * buf_words;
-                const int rows = min(kNmsTile, n - b * kNmsTile);
-                for (int k = wwarp; k < rows; k += kWorkerWarps) {
-                    const u64* src = mask + (size_t)(b * kNmsTile + k) * col_blocks;
-                    u64* d = dst + (size_t)k * col_blocks;
-                    for (int j = b + lane; j < col_blocks; j += 32) cp_async8(d + j, src + j);
-                }
-            }
-            cp_async_commit();
-        };
-        prefetch(0);
-        prefetch(1);
-        cp_async_wait<1>();
-        worker_barrier();
-        if (wt == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(&s_ring_ready) = 1; }
-        for (int b = 0; b < col_blocks; ++b) {
-            // rows of block b+1 (issued one iteration ago) must land before the resolver gets there
-            cp_async_wait<0>();
-            worker_barrier();
-            if (wt == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(&s_ring_ready) = min(b + 2, col_blocks); }
-            while (ld_volatile_s32(&s_resolved) < b + 1) { }
-            __threadfence_block();
-            const u64 kept = *reinterpret_cast<volatile u64*>(&kept_hist[b]);
-            const u64* rows = ring + (size_t)(b & 1) * buf_words;
-            // fold the kept rows of block b into remv[j], j >= b + 2 (column b + 1 is the resolver's carry):
-            // lane = (column of a group of 4, row residue of 8); shuffles combine the 8 partials; single writer per word
-            const int kg = lane & 7, jl = lane >> 3;
-            for (int j0 = b + 2 + wwarp * 4; j0 < col_blocks; j0 += kWorkerWarps * 4) {
-                const int j = j0 + jl;
-                u64 acc = 0;
-                if (j < col_blocks) {
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const int k = kg + 8 * kk;
-                        if ((kept >> k) & 1ULL) acc |= rows[(size_t)k * col_blocks + j];
-                    }
-                }
-                acc |= __shfl_xor_sync(0xffffffffu, acc, 1);
-                acc |= __shfl_xor_sync(0xffffffffu, acc, 2);
-                acc |= __shfl_xor_sync(0xffffffffu, acc, 4);
-                if (kg == 0 && j < col_blocks && acc) remv[j] |= acc;
-            }
-            worker_barrier();                                // every fold of block b is done; ring[b & 1] is free
-            if (wt == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(&s_folded) = b + 1; }
-            prefetch(b + 2);
-        }
-        cp_async_wait<0>();
-    }
-}
-
 // Resolver scan (default while REACH * n * 8 B fits shared memory).  Everything the greedy chain itself touches is
 // copied to shared memory once, so the single resolver warp never waits for global memory:
 //   * T[i]   -- the TRANSPOSED diagonal word of box i (which earlier boxes of its own 64-block suppress it), and
@@ -627,33 +395,19 @@ int nms(const float* boxes, int n, int dim, float thresh, int* keep_out, int* nu
     const long long tiles = (long long)cb * (cb + 1) / 2;
     if (tiles > 0x7fffffffLL) return B200_ROI_EINVAL;
     nms_mask_kernel<<<(unsigned)tiles, kNmsTile, 0, stream>>>(boxes, n, dim, thresh, lo, hi, mask, diag_t);
-    const char* e_mode = getenv("B200_NMS_SCAN");             // "pipelined" / "decoupled" select the older scans (A/B tests)
-    const bool old_scan = e_mode && (e_mode[0] == 'p' || e_mode[0] == 'd');
-    for (int reach = 4; reach >= 3 && !old_scan; --reach) {
+    const char* e_mode = getenv("B200_NMS_SCAN");             // "simple" selects the unpipelined scan (A/B tests)
+    const bool simple = e_mode && e_mode[0] == 's';
+    for (int reach = 4; reach >= 2 && !simple; --reach) {
         const size_t smem_res = sizeof(u64) * ((size_t)reach * cb * kNmsTile + 4 * (size_t)cb) + 16;
-        if (smem_res > 220 * 1024) continue;
-        cudaError_t e = (reach == 4)
-            ? cudaFuncSetAttribute(nms_scan_resolver_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res)
-            : cudaFuncSetAttribute(nms_scan_resolver_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res);
+        if (smem_res > 224 * 1024) continue;
+        void (*kern)(const u64*, const u64*, int, int, int*, int*) =
+            (reach == 4) ? nms_scan_resolver_kernel<4> : (reach == 3) ? nms_scan_resolver_kernel<3> : nms_scan_resolver_kernel<2>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res);
         if (e != cudaSuccess) return (int)e;
-        if (reach == 4) nms_scan_resolver_kernel<4><<<1, kScanThreads, smem_res, stream>>>(mask, diag_t, n, cb, keep_out, num_out);
-        else nms_scan_resolver_kernel<3><<<1, kScanThreads, smem_res, stream>>>(mask, diag_t, n, cb, keep_out, num_out);
+        kern<<<1, kScanThreads, smem_res, stream>>>(mask, diag_t, n, cb, keep_out, num_out);
         return finish_launch(2);
     }
-    const size_t smem_pipe = sizeof(u64) * (2 * (((size_t)cb + 1) / 2 * 2) + 2 * (size_t)kNmsTile * cb);
-    if (smem_pipe <= 220 * 1024) {
-        if (e_mode && e_mode[0] == 'p') {
-            cudaError_t e = cudaFuncSetAttribute(nms_scan_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
-            if (e != cudaSuccess) return (int)e;
-            nms_scan_pipelined_kernel<<<1, kScanThreads, smem_pipe, stream>>>(mask, n, cb, keep_out, num_out);
-            return finish_launch(2);
-        }
-        cudaError_t e = cudaFuncSetAttribute(nms_scan_decoupled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
-        if (e != cudaSuccess) return (int)e;
-        nms_scan_decoupled_kernel<<<1, kScanThreads, smem_pipe, stream>>>(mask, n, cb, keep_out, num_out);
-        return finish_launch(2);
-    }
-    // very large inputs (> ~14k boxes): the ring does not fit; fall back to the unpipelined scan
+    // very large inputs (> ~13.8k boxes): the near-diagonal words do not fit shared memory; unpipelined scan
     const size_t smem = sizeof(u64) * (size_t)cb;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

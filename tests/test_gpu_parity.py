@@ -268,8 +268,17 @@ def test_nms_thresholds_and_properties(thresh):
     assert np.array_equal(k2, np.arange(len(k)))            # idempotent
 
 
-def test_nms_large_input_uses_fallback_scan():
-    b = cases.nms_case(15000, seed=3)       # > 14k boxes: the shared-memory ring does not fit
+@pytest.mark.parametrize("n", [8000, 12000, 15000])
+def test_nms_large_inputs(n):
+    # 8000: near-diagonal reach 3; 12000: reach 2; 15000: words do not fit shared memory -> unpipelined scan
+    b = cases.nms_case(n, seed=3)
+    k = nms_gpu(dev(b), 0.7).cpu().numpy().reshape(-1)
+    assert np.array_equal(k, O.nms_cuda(b, 0.7))
+
+
+def test_nms_simple_scan_matches(monkeypatch):
+    monkeypatch.setenv("B200_NMS_SCAN", "simple")
+    b = cases.nms_case(3000, seed=11)
     k = nms_gpu(dev(b), 0.7).cpu().numpy().reshape(-1)
     assert np.array_equal(k, O.nms_cuda(b, 0.7))
 
