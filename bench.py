@@ -318,46 +318,8 @@ def main():
     h2d = h_feat.numel() * 4 + h_rois.numel() * 4 + h_dy.numel() * 4
     d2h = h_out.numel() * 4 + h_dx.numel() * 4
 
-    # Three streams, double-buffered device tensors: the H2D copy of step i+1, the kernels of step i and the
-    # D2H copy of step i-1 overlap (PCIe is full duplex); every step still moves all its inputs and results.
-    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-    d_feat = [torch.empty(shape, device=device) for _ in range(2)]
-    d_rois = [torch.empty((R, 5), device=device) for _ in range(2)]
-    d_dy = [torch.empty((R, C, P, P), device=device) for _ in range(2)]
-    ev_in = [torch.cuda.Event() for _ in range(2)]        # inputs of slot s have landed
-    ev_free = [torch.cuda.Event() for _ in range(2)]      # kernels that read slot s are done
-    ev_out = [torch.cuda.Event() for _ in range(2)]       # results of slot s are on the host side of the copy
-
-    def e2e_step(i):
-        s = i % 2
-        cur = torch.cuda.current_stream()
-        with torch.cuda.stream(s_in):
-            if i >= 2:
-                s_in.wait_event(ev_free[s])
-            d_feat[s].copy_(h_feat, non_blocking=True)
-            d_rois[s].copy_(h_rois, non_blocking=True)
-            d_dy[s].copy_(h_dy, non_blocking=True)
-            ev_in[s].record(s_in)
-        cur.wait_event(ev_in[s])
-        F = d_feat[s].detach().requires_grad_(True)
-        out = fn(F, d_rois[s])
-        out.backward(d_dy[s])
-        grad = F.grad
-        ev_free[s].record(cur)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_free[s])
-            if i >= 1:
-                s_out.wait_event(ev_out[(i - 1) % 2])      # host result buffers are reused every step
-            h_out.copy_(out.detach(), non_blocking=True)
-            h_dx.copy_(grad, non_blocking=True)
-            out.record_stream(s_out); grad.record_stream(s_out)
-            ev_out[s].record(s_out)
-
-    def e2e_run(n):
-        for i in range(n):
-            e2e_step(i)
-        torch.cuda.current_stream().wait_stream(s_out)     # the timed region ends when the last result is on the host
-        torch.cuda.current_stream().wait_stream(s_in)
+    pipe = benchutil.E2EPipeline(fn, shape, R, C, P, device, h_feat, h_rois, h_dy, h_out, h_dx)
+    e2e_run = pipe.run
 
     e2e_run(3)
     torch.cuda.synchronize()
@@ -371,7 +333,12 @@ def main():
     ms_e2e = e0.elapsed_time(e1)
     barrier()
     ms_e2e_max, units_e2e = benchutil.aggregate(ms_e2e, R * K_e2e, device=device)
-    e2e = {"value": units_e2e / (ms_e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+    try:
+        pcie = benchutil.pcie_bandwidth(device, h_feat, h_dx)
+        pcie["floor_ms_per_step"] = (h2d + d2h) / (pcie["duplex_gbs"] * 1e9) * 1e3
+    except Exception as exc:  # noqa: BLE001
+        pcie = {"error": str(exc)}
+    e2e = {"value": units_e2e / (ms_e2e_max * 1e-3), "unit": UNIT, "host_link": pcie, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "steps": K_e2e, "ms_per_step": ms_e2e_max / K_e2e,
            "path": "RoIAlignFunction(7,7,1/4,2)(features, rois) + .backward(dY); per step: H2D of features+rois+dY from pinned "
                    "host memory, D2H of out+dX; copies of neighbouring steps overlap the kernels (3 streams, 2 slots)"}

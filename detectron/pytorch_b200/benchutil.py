@@ -163,6 +163,105 @@ class numa_local(object):
 
 
 # ------------------------------------------------------------------------------------------------
+# end-to-end pipeline (host buffers in, host buffers out) used by bench.py's `e2e` leg
+# ------------------------------------------------------------------------------------------------
+class E2EPipeline(object):
+    """fn(features, rois) + backward(dY) through the reference-shaped autograd function with HOST buffers.
+
+    Three streams, double-buffered device tensors: the H2D copy of step i+1, the kernels of step i and the D2H copy
+    of step i-1 overlap (PCIe is full duplex); every step still moves all its inputs and all its results.
+    `h2d` / `compute` / `d2h` switch the legs off for tools/e2e_probe.py (what bounds the step?)."""
+
+    def __init__(self, fn, shape, R, C, P, device, h_feat, h_rois, h_dy, h_out, h_dx, h2d=True, compute=True, d2h=True):
+        import torch
+        self.torch = torch
+        self.fn = fn
+        self.h = (h_feat, h_rois, h_dy, h_out, h_dx)
+        self.legs = (h2d, compute, d2h)
+        self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        self.d_feat = [torch.zeros(shape, device=device) for _ in range(2)]
+        self.d_rois = [h_rois.to(device) for _ in range(2)]
+        self.d_dy = [torch.zeros((R, C, P, P), device=device) for _ in range(2)]
+        self.d_out = torch.zeros((R, C, P, P), device=device)       # stand-ins when the compute leg is off
+        self.d_dx = torch.zeros(shape, device=device)
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]          # inputs of slot s have landed
+        self.ev_free = [torch.cuda.Event() for _ in range(2)]        # kernels that read slot s are done
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]         # results of slot s are on the host side of the copy
+
+    def step(self, i):
+        torch = self.torch
+        h_feat, h_rois, h_dy, h_out, h_dx = self.h
+        h2d, compute, d2h = self.legs
+        s = i % 2
+        cur = torch.cuda.current_stream()
+        if h2d:
+            with torch.cuda.stream(self.s_in):
+                if i >= 2:
+                    self.s_in.wait_event(self.ev_free[s])
+                self.d_feat[s].copy_(h_feat, non_blocking=True)
+                self.d_rois[s].copy_(h_rois, non_blocking=True)
+                self.d_dy[s].copy_(h_dy, non_blocking=True)
+                self.ev_in[s].record(self.s_in)
+            cur.wait_event(self.ev_in[s])
+        if compute:
+            F = self.d_feat[s].detach().requires_grad_(True)
+            out = self.fn(F, self.d_rois[s])
+            out.backward(self.d_dy[s])
+            grad = F.grad
+            out = out.detach()
+        else:
+            out, grad = self.d_out, self.d_dx
+        self.ev_free[s].record(cur)
+        if d2h:
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_free[s])
+                if i >= 1:
+                    self.s_out.wait_event(self.ev_out[(i - 1) % 2])      # host result buffers are reused every step
+                h_out.copy_(out, non_blocking=True)
+                h_dx.copy_(grad, non_blocking=True)
+                out.record_stream(self.s_out); grad.record_stream(self.s_out)
+                self.ev_out[s].record(self.s_out)
+
+    def run(self, n):
+        for i in range(n):
+            self.step(i)
+        cur = self.torch.cuda.current_stream()
+        cur.wait_stream(self.s_out)            # the timed region ends when the last result is on the host
+        cur.wait_stream(self.s_in)
+
+
+def pcie_bandwidth(device, h_src, h_dst, reps=5):
+    """Copy bandwidth of this box's host link with the e2e leg's own pinned buffers: H2D alone, D2H alone and both
+    directions at once (GB/s, aggregate for `duplex`).  Context for the e2e number, which is bound by these."""
+    import torch
+    d_a = torch.empty_like(h_src, device=device)
+    d_b = torch.zeros_like(h_dst, device=device)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    out = {}
+    for mode in ("h2d", "d2h", "duplex"):
+        nbytes = 0
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream()
+        e0.record()
+        s1.wait_stream(cur); s2.wait_stream(cur)
+        for _ in range(reps):
+            if mode != "d2h":
+                with torch.cuda.stream(s1):
+                    d_a.copy_(h_src, non_blocking=True)
+                nbytes += h_src.numel() * h_src.element_size()
+            if mode != "h2d":
+                with torch.cuda.stream(s2):
+                    h_dst.copy_(d_b, non_blocking=True)
+                nbytes += h_dst.numel() * h_dst.element_size()
+        cur.wait_stream(s1); cur.wait_stream(s2)
+        e1.record()
+        torch.cuda.synchronize()
+        out[mode + "_gbs"] = nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # clocks / throttle reasons during the timed region
 # ------------------------------------------------------------------------------------------------
 _QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
