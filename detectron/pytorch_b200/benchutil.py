@@ -187,6 +187,7 @@ class E2EPipeline(object):
         self.ev_in = [torch.cuda.Event() for _ in range(2)]          # inputs of slot s have landed
         self.ev_free = [torch.cuda.Event() for _ in range(2)]        # kernels that read slot s are done
         self.ev_out = [torch.cuda.Event() for _ in range(2)]         # results of slot s are on the host side of the copy
+        self.keep = [None, None]                                     # results of slot s, alive until their D2H copy is done
 
     def step(self, i):
         torch = self.torch
@@ -203,6 +204,12 @@ class E2EPipeline(object):
                 self.d_dy[s].copy_(h_dy, non_blocking=True)
                 self.ev_in[s].record(self.s_in)
             cur.wait_event(self.ev_in[s])
+        if i >= 2 and d2h:
+            # The results of step i-2 are released here, after the compute stream has been ordered behind their D2H
+            # copy: the caching allocator then hands the same blocks out again every step (no record_stream, whose
+            # deferred frees make the allocator grow / cudaFree under this access pattern).
+            cur.wait_event(self.ev_out[s])
+        self.keep[s] = None
         if compute:
             F = self.d_feat[s].detach().requires_grad_(True)
             out = self.fn(F, self.d_rois[s])
@@ -219,8 +226,8 @@ class E2EPipeline(object):
                     self.s_out.wait_event(self.ev_out[(i - 1) % 2])      # host result buffers are reused every step
                 h_out.copy_(out, non_blocking=True)
                 h_dx.copy_(grad, non_blocking=True)
-                out.record_stream(self.s_out); grad.record_stream(self.s_out)
                 self.ev_out[s].record(self.s_out)
+            self.keep[s] = (out, grad)
 
     def run(self, n):
         for i in range(n):
@@ -228,6 +235,7 @@ class E2EPipeline(object):
         cur = self.torch.cuda.current_stream()
         cur.wait_stream(self.s_out)            # the timed region ends when the last result is on the host
         cur.wait_stream(self.s_in)
+        self.keep = [None, None]
 
 
 def pcie_bandwidth(device, h_src, h_dst, reps=5):

@@ -12,7 +12,7 @@ device = torch.device("cuda:0")
 shape = cfg["shape"]; R, C, P = cfg["rois"], cfg["shape"][1], cfg["pooled"]
 rois = S.make_rois(R, shape, cfg["scale"], seed=1)
 fn = RoIAlignFunction(P, P, cfg["scale"], cfg["sampling_ratio"])
-for placement in ("default", "numa_local"):
+for placement in ("default", "numa_local", "default", "numa_local"):
     ctx = benchutil.numa_local(0) if placement == "numa_local" else benchutil.numa_local.__new__(benchutil.numa_local)
     if placement == "default":
         ctx.cpus = None; ctx.prev = None
@@ -27,4 +27,4 @@ for placement in ("default", "numa_local"):
         pipe.run(3); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); pipe.run(20); e1.record(); torch.cuda.synchronize()
-        print("  legs h2d=%d compute=%d d2h=%d: %.3f ms/step" % (legs + (e0.elapsed_time(e1) / 20,)))
+        print("  legs h2d=%d compute=%d d2h=%d: %.3f ms/step  (allocator reserved %.0f MB)" % (legs + (e0.elapsed_time(e1) / 20, torch.cuda.memory_reserved() / 1e6)))
