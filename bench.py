@@ -175,7 +175,7 @@ def main():
                                                  outs[i].data_ptr(), wss[i].data_ptr() if ws_bytes else None, ws_bytes,
                                                  torch.cuda.current_stream().cuda_stream), "fwd")
 
-    bws_bytes = int(lib.b200_roi_align_backward_workspace_bytes(N, C, H, W))
+    bws_bytes = int(lib.b200_roi_align_backward_workspace_bytes(N, R, C, H, W, P, P, sr))
     bws = torch.empty((max(bws_bytes, 1),), dtype=torch.uint8, device=device)     # one scratch image, reused every step
 
     def bwd(i):

@@ -26,7 +26,7 @@ _SIGNATURES = {
     # (bottom, scale, N, R, H, W, C, PH, PW, sr, rois, top, workspace, workspace_bytes, stream)
     "b200_roi_align_forward_ws": (ctypes.c_int, [_c_float_p, ctypes.c_float] + [ctypes.c_int] * 8 +
                                   [_c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t, _stream_t]),
-    "b200_roi_align_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 4),
+    "b200_roi_align_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 8),
     "b200_roi_align_backward_ws": (ctypes.c_int, [_c_float_p, ctypes.c_float] + [ctypes.c_int] * 8 +
                                    [_c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t, _stream_t]),
     "b200_roi_align_backward": (ctypes.c_int, [_c_float_p, ctypes.c_float] + [ctypes.c_int] * 8 + [_c_float_p, _c_float_p, _stream_t]),
@@ -73,7 +73,7 @@ def load():
             fn = getattr(lib, name)          # AttributeError here == header/library mismatch: fail loudly
             fn.restype = restype
             fn.argtypes = argtypes
-        if lib.b200_roi_ops_abi_version() != 1:
+        if lib.b200_roi_ops_abi_version() != 2:
             raise ImportError("libb200_roi_ops.so ABI version mismatch")
         _lib = lib
     return _lib

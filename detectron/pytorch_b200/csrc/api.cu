@@ -37,11 +37,15 @@ int nms(const float*, int, int, float, int*, int*, void*, size_t, cudaStream_t);
 size_t roi_align_bwd_nhwc_workspace_bytes(int, int, int, int);
 int roi_align_backward_nhwc(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, void*, size_t, cudaStream_t);
 
-// B200_ROI_ALIGN_BWD_PATH=generic|nhwc|auto
+size_t roi_align_bwd_rows_workspace_bytes(int, int, int, int, int, int, int, int);
+int roi_align_backward_rows(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, void*, size_t, cudaStream_t);
+
+// B200_ROI_ALIGN_BWD_PATH=generic|nhwc|rows|auto
 static int backward_path_mode() {
     const char* e = getenv("B200_ROI_ALIGN_BWD_PATH");
     if (e && e[0] == 'g') return 1;
     if (e && e[0] == 'n') return 2;
+    if (e && e[0] == 'r') return 3;
     return 0;
 }
 
@@ -50,6 +54,18 @@ static bool nhwc_pays_off(int N, int R, int C, int H, int W, int PH, int PW, int
     if (sr < 1 || (C & 3)) return false;
     const long long taps = (long long)R * C * PH * PW * sr * sr * 4;
     return taps >= 2LL * N * C * H * W;
+}
+
+// 0: generic (scalar atomics), 2: NHWC vector reductions, 3: row-stationary gather
+static int backward_path_choice(int N, int R, int C, int H, int W, int PH, int PW, int sr) {
+    const int mode = backward_path_mode();
+    if (mode == 1 || R <= 0) return 0;
+    const bool pays = nhwc_pays_off(N, R, C, H, W, PH, PW, sr);
+    const bool rows_ok = roi_align_bwd_rows_workspace_bytes(N, R, C, H, W, PH, PW, sr) > 0;
+    if (mode == 3) return rows_ok ? 3 : 0;
+    if (mode == 2) return 2;
+    if (rows_ok && pays) return 3;
+    return pays ? 2 : 0;
 }
 
 static inline bool bad_dims(int N, int R, int H, int W, int C, int PH, int PW) {
@@ -61,7 +77,7 @@ using namespace b200;
 
 extern "C" {
 
-int b200_roi_ops_abi_version(void) { return 1; }
+int b200_roi_ops_abi_version(void) { return 2; }
 
 const char* b200_roi_ops_strerror(int status) {
     if (status == B200_ROI_OK) return "success";
@@ -127,9 +143,13 @@ int b200_roi_align_forward(const float* bottom_data, float spatial_scale, int ba
                                      (cudaStream_t)stream);
 }
 
-size_t b200_roi_align_backward_workspace_bytes(int batch_size, int channels, int height, int width) {
-    if (backward_path_mode() == 1 || batch_size <= 0 || channels <= 0 || height <= 0 || width <= 0) return 0;
-    return roi_align_bwd_nhwc_workspace_bytes(batch_size, channels, height, width);
+size_t b200_roi_align_backward_workspace_bytes(int batch_size, int num_rois, int channels, int height, int width,
+                                               int aligned_height, int aligned_width, int sampling_ratio) {
+    if (batch_size <= 0 || num_rois <= 0 || channels <= 0 || height <= 0 || width <= 0 || aligned_height <= 0 || aligned_width <= 0) return 0;
+    const int path = backward_path_choice(batch_size, num_rois, channels, height, width, aligned_height, aligned_width, sampling_ratio);
+    if (path == 3) return roi_align_bwd_rows_workspace_bytes(batch_size, num_rois, channels, height, width, aligned_height, aligned_width, sampling_ratio);
+    if (path == 2) return roi_align_bwd_nhwc_workspace_bytes(batch_size, channels, height, width);
+    return 0;
 }
 
 int b200_roi_align_backward_ws(const float* top_diff, float spatial_scale, int batch_size, int num_rois, int height,
@@ -139,9 +159,15 @@ int b200_roi_align_backward_ws(const float* top_diff, float spatial_scale, int b
     if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
     if ((size_t)batch_size * channels == 0) return B200_ROI_OK;
     if (!bottom_diff || (num_rois > 0 && (!top_diff || !bottom_rois))) return B200_ROI_EINVAL;
-    const int mode = backward_path_mode();
-    if (mode != 1 && workspace != nullptr && num_rois > 0 &&
-        (mode == 2 || nhwc_pays_off(batch_size, num_rois, channels, height, width, aligned_height, aligned_width, sampling_ratio))) {
+    int path = (workspace != nullptr) ? backward_path_choice(batch_size, num_rois, channels, height, width, aligned_height, aligned_width, sampling_ratio) : 0;
+    if (path == 3) {
+        const int rc = roi_align_backward_rows(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
+                                               aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff,
+                                               workspace, workspace_bytes, (cudaStream_t)stream);
+        if (rc != 1000) return rc;
+        path = 2;                                   // workspace too small for the gather path: try the NHWC one
+    }
+    if (path == 2) {
         const int rc = roi_align_backward_nhwc(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
                                                aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff,
                                                workspace, workspace_bytes, (cudaStream_t)stream);
@@ -158,10 +184,9 @@ int b200_roi_align_backward(const float* top_diff, float spatial_scale, int batc
     if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
     if ((size_t)batch_size * channels == 0) return B200_ROI_OK;
     if (!bottom_diff || (num_rois > 0 && (!top_diff || !bottom_rois))) return B200_ROI_EINVAL;
-    const int mode = backward_path_mode();
-    if (mode != 1 && num_rois > 0 &&
-        (mode == 2 || nhwc_pays_off(batch_size, num_rois, channels, height, width, aligned_height, aligned_width, sampling_ratio))) {
-        const size_t wsb = roi_align_bwd_nhwc_workspace_bytes(batch_size, channels, height, width);
+    const size_t wsb = b200_roi_align_backward_workspace_bytes(batch_size, num_rois, channels, height, width, aligned_height,
+                                                               aligned_width, sampling_ratio);
+    if (wsb > 0) {
         void* ws = nullptr;
         if (cudaMallocAsync(&ws, wsb, (cudaStream_t)stream) == cudaSuccess) {
             const int rc = b200_roi_align_backward_ws(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,

@@ -56,7 +56,8 @@ def roi_align_backward(grad_output, rois, feature_size, aligned_height, aligned_
     N, C, H, W = feature_size
     grad_input = torch.empty((N, C, H, W), dtype=torch.float32, device=grad_output.device)
     lib = _lib.load()
-    ws_bytes = int(lib.b200_roi_align_backward_workspace_bytes(N, C, H, W)) if rois.size(0) > 0 else 0
+    ws_bytes = int(lib.b200_roi_align_backward_workspace_bytes(N, rois.size(0), C, H, W, aligned_height, aligned_width,
+                                                              sampling_ratio)) if rois.size(0) > 0 else 0
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=grad_output.device) if ws_bytes else None
     with torch.cuda.device(grad_output.device):
         _lib.check(lib.b200_roi_align_backward_ws(grad_output.data_ptr(), spatial_scale, N, rois.size(0), H, W, C,

@@ -79,12 +79,15 @@ B200_API int b200_roi_align_forward_ws(const float* bottom_data, float spatial_s
                               int sampling_ratio, const float* bottom_rois, float* top_data,
                               void* workspace, size_t workspace_bytes, b200_stream_t stream);
 
-/* Workspace variant of the backward: the vector-reduction path accumulates into a channel-innermost
- * scratch image of dX and transposes it back; it needs
- * b200_roi_align_backward_workspace_bytes(batch_size, channels, height, width) bytes (= sizeof dX).
- * NULL / too small -> the scalar-atomic kernel runs.  The plain b200_roi_align_backward obtains the
- * scratch with cudaMallocAsync/cudaFreeAsync on `stream`. */
-B200_API size_t b200_roi_align_backward_workspace_bytes(int batch_size, int channels, int height, int width);
+/* Workspace variant of the backward.  The fast paths need device scratch:
+ *   - row-stationary gather path (no atomics): per-RoI tables, row-bucketed unit lists and a channel-innermost
+ *     copy of dY (~ sizeof dY);
+ *   - vector-reduction path: a channel-innermost scratch image of dX (= sizeof dX).
+ * b200_roi_align_backward_workspace_bytes(...) returns what the path chosen for these parameters needs (0: the
+ * scalar-atomic kernel runs and needs none).  NULL / too small -> the scalar-atomic kernel runs.  The plain
+ * b200_roi_align_backward obtains the scratch with cudaMallocAsync/cudaFreeAsync on `stream`. */
+B200_API size_t b200_roi_align_backward_workspace_bytes(int batch_size, int num_rois, int channels, int height, int width,
+                                                        int aligned_height, int aligned_width, int sampling_ratio);
 B200_API int b200_roi_align_backward_ws(const float* top_diff, float spatial_scale, int batch_size, int num_rois,
                                int height, int width, int channels, int aligned_height, int aligned_width,
                                int sampling_ratio, const float* bottom_rois, float* bottom_diff,

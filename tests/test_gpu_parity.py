@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 import torch
 
-from detectron.pytorch_b200 import synthetic as S
+from detectron.pytorch_b200 import _lib, synthetic as S
 from detectron.pytorch_b200.model.nms.nms_gpu import nms_gpu
 from detectron.pytorch_b200.model.nms.nms_wrapper import nms as nms_wrapper
 from detectron.pytorch_b200.model.roi_align.functions.roi_align import RoIAlignFunction as LegacyRoIAlignFunction
@@ -37,13 +37,14 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-@pytest.fixture(params=["generic", "tiled"])
+@pytest.fixture(params=["generic", "tiled", "tiled-rows"])
 def fwd_path(request, monkeypatch):
     """Force the RoIAlign forward AND backward dispatch (the env vars are read per call by the library):
     generic = RoI-centric kernels (scalar atomics in the backward), tiled = feature-map-stationary
-    forward + vector-reduction (NHWC scratch) backward."""
-    monkeypatch.setenv("B200_ROI_ALIGN_PATH", request.param)
-    monkeypatch.setenv("B200_ROI_ALIGN_BWD_PATH", "generic" if request.param == "generic" else "nhwc")
+    forward + vector-reduction (NHWC scratch) backward, tiled-rows = same forward + row-stationary gather
+    backward (falls back to the scalar-atomic kernel for shapes it does not cover)."""
+    monkeypatch.setenv("B200_ROI_ALIGN_PATH", "generic" if request.param == "generic" else "tiled")
+    monkeypatch.setenv("B200_ROI_ALIGN_BWD_PATH", {"generic": "generic", "tiled": "nhwc", "tiled-rows": "rows"}[request.param])
     return request.param
 
 
@@ -58,7 +59,7 @@ def run_fwd_bwd(fn, f, r, dy):
 def assert_fwd_matches(out, ref, path):
     """generic path: bit-exact.  tiled path: bit-exact except bins whose samples straddle two tiles,
     which add <= 4 partial means in a different association (~1 ulp): |a-b| <= 1e-6 + 1e-6*|b|."""
-    if path == "tiled":
+    if path.startswith("tiled"):
         np.testing.assert_allclose(out, ref, rtol=1e-6, atol=1e-6)
         assert np.mean(out == ref) > 0.5
     else:
@@ -118,6 +119,38 @@ def test_roi_align_baseline_cfg1_and_cfg2_full_size(fwd_path):
                                                                                             cfg["shape"][3], P, P, s, sr)
         if G.available():
             assert_fwd_matches(out, G.roi_align_forward(dev(f), dev(r), P, P, s, sr).cpu().numpy(), fwd_path)
+
+
+ROWS_CASES = {
+    # name: (shape, scale, P, sr, n_rois)  -- shapes the row-stationary backward covers (C % 64 == 0, P in {7, 14}, sr in {1, 2})
+    "c64_odd_w": ((2, 64, 25, 45), 1.0 / 16, 7, 2, 40),
+    "c128_sr1": ((1, 128, 30, 33), 1.0 / 8, 7, 1, 24),
+    "c128_cpl4": ((3, 128, 20, 70), 1.0 / 16, 7, 2, 48),
+    "p14_sr2": ((1, 64, 28, 40), 1.0 / 8, 14, 2, 16),
+    "p14_sr1": ((2, 64, 16, 31), 1.0 / 16, 14, 1, 16),
+    "w_lt_32": ((1, 64, 12, 9), 1.0 / 32, 7, 2, 12),
+}
+
+
+@pytest.mark.parametrize("name", sorted(ROWS_CASES))
+@pytest.mark.parametrize("cpl", ["2", "4"])
+def test_roi_align_backward_rows_path(name, cpl, monkeypatch):
+    """Row-stationary gather backward vs the oracle (fp64 accumulation): edge RoIs (outside the map, degenerate,
+    bad batch index), partial x-tiles, several images, both channel-per-lane variants."""
+    monkeypatch.setenv("B200_ROI_ALIGN_BWD_PATH", "rows")
+    monkeypatch.setenv("B200_ROI_ALIGN_BWD_CPL", cpl)
+    shape, s, P, sr, n = ROWS_CASES[name]
+    assert _lib.load().b200_roi_align_backward_workspace_bytes(shape[0], n, shape[1], shape[2], shape[3], P, P, sr) > 0
+    r = np.concatenate([S.make_rois(n, shape, s, seed=2), S.make_edge_rois(shape, s)]).astype(np.float32)
+    dy = np.random.RandomState(3).standard_normal((r.shape[0], shape[1], P, P)).astype(np.float32)
+    f = S.make_features(shape, seed=1)
+    out, dx = run_fwd_bwd(RoIAlignFunction(P, P, s, sr), f, r, dy)
+    ref_dx = O.roi_align_backward(dy, r, shape, P, P, s, sr, acc64=True)
+    np.testing.assert_allclose(dx, ref_dx, **GRAD_TOL)
+    assert np.array_equal(dx == 0, ref_dx == 0) or np.count_nonzero((dx == 0) != (ref_dx == 0)) < dx.size * 1e-4
+    # run-to-run: no atomics in this path, but the unit order inside a row comes from a counting sort with atomics
+    _, dx2 = run_fwd_bwd(RoIAlignFunction(P, P, s, sr), f, r, dy)
+    np.testing.assert_allclose(dx2, dx, rtol=1e-6, atol=1e-6)
 
 
 def test_roi_align_forward_linearity_and_determinism(fwd_path):
