@@ -150,7 +150,7 @@ def test_roi_align_backward_rows_path(name, cpl, monkeypatch):
     assert np.array_equal(dx == 0, ref_dx == 0) or np.count_nonzero((dx == 0) != (ref_dx == 0)) < dx.size * 1e-4
     # run-to-run: no atomics in this path, but the unit order inside a row comes from a counting sort with atomics
     _, dx2 = run_fwd_bwd(RoIAlignFunction(P, P, s, sr), f, r, dy)
-    np.testing.assert_allclose(dx2, dx, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(dx2, dx, **GRAD_TOL)
 
 
 def test_roi_align_forward_linearity_and_determinism(fwd_path):
