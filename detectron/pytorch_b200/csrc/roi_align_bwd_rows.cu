@@ -214,9 +214,10 @@ template <> struct Acc<4> {
 
 template <int CPL> __host__ __device__ constexpr int rows_acc_stride() { return 33 * CPL; }          // words per cell (odd multiple of CPL)
 template <int NX> __host__ __device__ constexpr int rows_stage_bytes() { return ((NX * 16 + 127) / 128) * 128; }
-template <int CPL, int NX> __host__ __device__ constexpr int rows_warp_smem() {                       // 32 cells + 1 scratch cell, two record buffers
-    return (kRowCells + 1) * rows_acc_stride<CPL>() * 4 + 2 * rows_stage_bytes<NX>();
+template <int CPL> __host__ __device__ constexpr int rows_acc_bytes() {                              // 32 cells + 1 scratch cell, 16-byte multiple
+    return (((kRowCells + 1) * rows_acc_stride<CPL>() * 4 + 15) / 16) * 16;
 }
+template <int CPL, int NX> __host__ __device__ constexpr int rows_warp_smem() { return rows_acc_bytes<CPL>() + 2 * rows_stage_bytes<NX>(); }
 
 template <int PW, int SR, int CPL, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -233,7 +234,7 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned acc_s = smem_u32addr(smem_raw) + (unsigned)warp * rows_warp_smem<CPL, NX>();
-    const unsigned stage_s = acc_s + (kRowCells + 1) * kCellBytes;
+    const unsigned stage_s = acc_s + rows_acc_bytes<CPL>();
     const unsigned lane_acc = acc_s + lane * (CPL * 4);
     const int cblocks = C / CHB;
     const int items_per_row = tiles_x * cblocks;
