@@ -6,22 +6,21 @@
 // WARP owns the item's accumulator ([cell][channel] in shared memory, lane = 2 / 4 adjacent channels), visits every
 // bilinear tap that lands in it and read-modify-writes the accumulator with plain 64/128-bit shared accesses.  Each
 // dX element is produced by exactly one warp and written exactly once with coalesced 128-byte stores, so there is
-// no memset, no atomic and no scratch image; accumulation order inside an item is sequential.
+// no memset, no atomic and no scratch image; accumulation order inside an item is sequential and fixed.
 //
 //   tables (1 launch, parallel)  per-RoI axis sample tables (all IEEE divisions) and, in the same launch,
 //                                dY (R, C, PH, PW) -> dYt (R, PH, PW, C) / count: channel-innermost, so that a
 //                                warp reads the gradient of a bin for its channels with one coalesced access.
-//   bucket (1 launch, one CTA)   every valid y-sample of every RoI contributes two "units" (row of its low cell
-//                                with weight hy, row of its high cell with weight ly), bucketed by image row with
-//                                a shared-memory counting sort (CSR row_off + units); rows ranked by unit count
-//                                so that heavy items are handed out first.  Integer work only.
-//   main   (persistent warps)    item <- atomic counter; zero accumulator; for each unit of the row whose RoI
-//                                overlaps the x-tile: lanes j < PW*sr build the tap records of x-sample j (cell
-//                                offset, wy * wx), staged in shared memory; the gradients of the needed bins are
-//                                loaded to registers (software pipelined one unit ahead); taps are applied with
-//                                LDS / FFMA2 / STS (taps outside the tile land in a scratch cell instead of
-//                                being branched around).  Finally the row segment is transposed to NCHW on the
-//                                way out.
+//   main   (persistent warps)    item <- atomic counter; zero accumulator; scan the RoI headers (lanes = RoIs) for
+//                                those that overlap the row and the x-tile; for each, lanes = y-samples find the
+//                                samples whose low / high cell is this row: every hit is a "unit" (RoI, y-sample,
+//                                weight hy or ly), collected in a small per-warp list.  Per unit: lanes j < PW*sr
+//                                build the tap records of x-sample j (cell offset, wy * wx), staged in shared
+//                                memory; the gradients of the needed bins are loaded to registers (software
+//                                pipelined one unit ahead); taps are applied with LDS / FFMA2 / STS (taps outside
+//                                the tile land in a scratch cell instead of being branched around).  Finally the
+//                                row segment is transposed to NCHW on the way out.  Units are visited in RoI
+//                                order, so the result is deterministic (bitwise reproducible run to run).
 //
 // Numerics: per tap the term is (dY / count) * (wy * wx) with count = sr^2 in {1, 4}: the division is an exact
 // scaling, so the term equals the reference's FMUL(dY, w) / count bit for bit (barring underflow); only the order
@@ -35,14 +34,14 @@ namespace b200 {
 
 constexpr int kRowCells = 32;             // cells per x-tile = lanes of the write-out
 constexpr int kTableThreads = 256;
-constexpr int kBucketThreads = 1024;
 constexpr int kTransposeChannels = 64;    // channels per transpose CTA
-constexpr int kMaxRows = 8192;            // N * H supported by the shared-memory counting sort
+constexpr int kListCap = 128;             // units a warp collects before it processes them
 
 struct __align__(16) BwdRoi {
     int batch;                            // -1: batch index out of range (contributes nothing)
     int x_lo, x_hi;                       // range of cells any x-sample of the RoI can touch
-    int pad;
+    int y_lo, y_hi;                       // same for rows
+    int pad0, pad1, pad2;
 };
 
 __device__ __forceinline__ unsigned smem_u32addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -50,22 +49,19 @@ __device__ __forceinline__ AxisEntry make_axis_zero() { AxisEntry e; e.low = 0; 
 
 struct RowsPlan {
     int ny, nx, tiles_x, rows;
-    size_t roi_off, xtab_off, ytab_off, row_off_off, row_rank_off, units_off, counter_off, dyt_off, ws_bytes;
+    size_t roi_off, xtab_off, ytab_off, counter_off, dyt_off, ws_bytes;
 };
 
 static bool rows_plan(int N, int R, int C, int H, int W, int PH, int PW, int sr, RowsPlan* p) {
     if (sr < 1 || sr > 2 || (PW != 7 && PW != 14) || PH * sr > kAxisMax || PW * sr > kAxisMax) return false;
     if (R <= 0 || R > 65535 || N <= 0 || C <= 0 || (C % 64) != 0 || H <= 0 || W <= 0) return false;
-    if ((long long)N * H > kMaxRows) return false;
+    if (H > 65535) return false;
     if ((long long)R * C * PH * PW >= (1LL << 31) || (long long)N * C * H * W >= (1LL << 31)) return false;
     p->ny = PH * sr; p->nx = PW * sr; p->tiles_x = (W + kRowCells - 1) / kRowCells; p->rows = N * H;
     size_t off = 0;
     p->roi_off = off;      off = align_up(off + (size_t)R * sizeof(BwdRoi), 256);
     p->xtab_off = off;     off = align_up(off + (size_t)R * p->nx * sizeof(AxisEntry), 256);
     p->ytab_off = off;     off = align_up(off + (size_t)R * p->ny * sizeof(AxisEntry), 256);
-    p->row_off_off = off;  off = align_up(off + ((size_t)p->rows + 1) * sizeof(int), 256);
-    p->row_rank_off = off; off = align_up(off + (size_t)p->rows * sizeof(int), 256);
-    p->units_off = off;    off = align_up(off + (size_t)R * p->ny * 2 * sizeof(uint2), 256);
     p->counter_off = off;  off = align_up(off + 64, 256);
     p->dyt_off = off;      off = align_up(off + (size_t)R * PH * PW * C * sizeof(float), 256);
     p->ws_bytes = off;
@@ -90,13 +86,14 @@ roi_align_bwd_rows_tables(const float* __restrict__ rois, const float* __restric
         const XfromRoi g = xfrom_roi(rois + 5 * (size_t)r, scale, PH, PW, sr);
         const bool isy = s < ny;
         const AxisEntry e = tiled_axis_entry(g, isy, isy ? s : s - ny, sr, H, W);
-        if (isy) {
+        if (isy) {                                                              // lows are monotone along an axis
             ytab[(size_t)r * ny + s] = e;
-            if (s == 0) roi_out[r].batch = (g.batch >= 0 && g.batch < N) ? g.batch : -1;
+            if (s == 0) { roi_out[r].batch = (g.batch >= 0 && g.batch < N) ? g.batch : -1; roi_out[r].y_lo = e.low; }
+            if (s == ny - 1) roi_out[r].y_hi = min(e.low + 1, H - 1);
         } else {
             xtab[(size_t)r * nx + (s - ny)] = e;
-            if (s == ny) roi_out[r].x_lo = e.low;                               // lows are monotone along the axis
-            if (s == per - 1) { roi_out[r].x_hi = min(e.low + 1, W - 1); roi_out[r].pad = 0; }
+            if (s == ny) roi_out[r].x_lo = e.low;
+            if (s == per - 1) roi_out[r].x_hi = min(e.low + 1, W - 1);
         }
         return;
     }
@@ -110,87 +107,17 @@ roi_align_bwd_rows_tables(const float* __restrict__ rois, const float* __restric
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kTableThreads / 32;
     const float* src = dy + ((size_t)r * C + c0) * bins;
-    const float cnt = (float)(sr * sr);
-    for (int c = warp; c < cc; c += kWarps)
-        for (int b = lane; b < bins; b += 32) s_tr[c * stride + b] = __fdiv_rn(src[c * bins + b], cnt);
+    const float inv = 1.f / (float)(sr * sr);               // count in {1, 4}: multiplying by the reciprocal is the exact division
+    if (stride == bins) {                                   // odd bin count: the block is copied linearly
+        for (int k = tid; k < cc * bins; k += kTableThreads) s_tr[k] = __fmul_rn(src[k], inv);
+    } else {
+        for (int c = warp; c < cc; c += kWarps)
+            for (int b = lane; b < bins; b += 32) s_tr[c * stride + b] = __fmul_rn(src[c * bins + b], inv);
+    }
     __syncthreads();
     float* dst = dyt + (size_t)r * bins * C + c0;
     for (int b = warp; b < bins; b += kWarps)
         for (int c = lane; c < cc; c += 32) dst[(size_t)b * C + c] = s_tr[c * stride + b];
-}
-
-// ------------------------------------------------------------------------------------------------
-// bucket: counting sort of the units by image row (one CTA, shared-memory atomics)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBucketThreads)
-roi_align_bwd_rows_bucket(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restrict__ ytab, int N, int R, int H, int ny,
-                          int* __restrict__ row_off, int* __restrict__ row_rank, uint2* __restrict__ units,
-                          int* __restrict__ counter) {
-    extern __shared__ __align__(16) int s_int[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rows = N * H;
-    int* cnt = s_int;                                       // [rows]  units per row, then the write cursor
-    int* offs = cnt + rows;                                 // [rows]  exclusive prefix
-    __shared__ int s_warp_sum[32];
-    for (int k = tid; k < rows; k += kBucketThreads) cnt[k] = 0;
-    if (tid == 0) *counter = 0;
-    __syncthreads();
-    const int total = R * ny;
-    for (int k = tid; k < total; k += kBucketThreads) {
-        const int batch = roi_in[k / ny].batch;
-        const AxisEntry e = ytab[k];
-        if (batch < 0 || !e.valid) continue;
-        atomicAdd(&cnt[batch * H + e.low], 1);
-        atomicAdd(&cnt[batch * H + min(e.low + 1, H - 1)], 1);
-    }
-    __syncthreads();
-    {   // exclusive scan of cnt[0 .. rows)
-        const int chunk = (rows + kBucketThreads - 1) / kBucketThreads;
-        const int b0 = tid * chunk;
-        int local = 0;
-        for (int k = 0; k < chunk; ++k) if (b0 + k < rows) local += cnt[b0 + k];
-        int incl = local;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-        if (lane == 31) s_warp_sum[warp] = incl;
-        __syncthreads();
-        if (tid < 32) {
-            int w = s_warp_sum[tid];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, d); if (tid >= d) w += v; }
-            s_warp_sum[tid] = w;                            // inclusive over warps
-        }
-        __syncthreads();
-        int run = incl - local + (warp > 0 ? s_warp_sum[warp - 1] : 0);
-        for (int k = 0; k < chunk; ++k) if (b0 + k < rows) { offs[b0 + k] = run; run += cnt[b0 + k]; }
-        __syncthreads();
-        for (int k = tid; k < rows; k += kBucketThreads) row_off[k] = offs[k];
-        if (tid == 0) row_off[rows] = s_warp_sum[31];
-    }
-    // rank of every row by unit count (heaviest first; ties by index): the main kernel hands items out in this order.
-    // One warp per row, lanes compare 32 other rows at a time.
-    for (int k = warp; k < rows; k += kBucketThreads / 32) {
-        const int mine = cnt[k];
-        int rank = 0;
-        for (int q = lane; q < rows; q += 32) { const int o = cnt[q]; rank += (o > mine) || (o == mine && q < k); }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, d);
-        if (lane == 0) row_rank[rank] = k;
-    }
-    __syncthreads();
-    for (int k = tid; k < rows; k += kBucketThreads) cnt[k] = offs[k];           // cursors
-    __syncthreads();
-    for (int k = tid; k < total; k += kBucketThreads) {
-        const int r = k / ny, i = k - r * ny;
-        const int batch = roi_in[r].batch;
-        const AxisEntry e = ytab[k];
-        if (batch < 0 || !e.valid) continue;
-        const unsigned key = (unsigned)r | ((unsigned)i << 16);
-        const int p0 = atomicAdd(&cnt[batch * H + e.low], 1);
-        units[p0] = make_uint2(key, __float_as_uint(e.h));                      // row of the low cell: weight hy
-        const int p1 = atomicAdd(&cnt[batch * H + min(e.low + 1, H - 1)], 1);
-        units[p1] = make_uint2(key | 0x80000000u, __float_as_uint(e.l));        // row of the high cell: weight ly
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -217,13 +144,15 @@ template <int NX> __host__ __device__ constexpr int rows_stage_bytes() { return 
 template <int CPL> __host__ __device__ constexpr int rows_acc_bytes() {                              // 32 cells + 1 scratch cell, 16-byte multiple
     return (((kRowCells + 1) * rows_acc_stride<CPL>() * 4 + 15) / 16) * 16;
 }
-template <int CPL, int NX> __host__ __device__ constexpr int rows_warp_smem() { return rows_acc_bytes<CPL>() + 2 * rows_stage_bytes<NX>(); }
+template <int CPL, int NX> __host__ __device__ constexpr int rows_warp_smem() {
+    return rows_acc_bytes<CPL>() + 2 * rows_stage_bytes<NX>() + kListCap * 8;
+}
 
 template <int PW, int SR, int CPL, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restrict__ xtab, const int* __restrict__ row_off,
-                   const int* __restrict__ row_rank, const uint2* __restrict__ units, int* __restrict__ counter,
-                   const float* __restrict__ dyt, float* __restrict__ dx, int N, int C, int H, int W, int PH, int tiles_x) {
+roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restrict__ xtab, const AxisEntry* __restrict__ ytab,
+                   int* __restrict__ counter, const float* __restrict__ dyt, float* __restrict__ dx, int N, int R, int C,
+                   int H, int W, int PH, int tiles_x) {
     constexpr int NX = PW * SR;
     constexpr int S = rows_acc_stride<CPL>();
     constexpr int CHB = 32 * CPL;                       // channels per item
@@ -235,6 +164,8 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned acc_s = smem_u32addr(smem_raw) + (unsigned)warp * rows_warp_smem<CPL, NX>();
     const unsigned stage_s = acc_s + rows_acc_bytes<CPL>();
+    const unsigned list_s = stage_s + 2 * SB;
+    const int ny = PH * SR;
     const unsigned lane_acc = acc_s + lane * (CPL * 4);
     const int cblocks = C / CHB;
     const int items_per_row = tiles_x * cblocks;
@@ -245,9 +176,8 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
         if (lane == 0) item = atomicAdd(counter, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= total) break;
-        const int rank = item / items_per_row;
-        const int row = row_rank[rank];                              // heaviest rows first
-        const int rem = item - rank * items_per_row;
+        const int row = item / items_per_row;
+        const int rem = item - row * items_per_row;
         const int cb = rem / tiles_x, tx = rem - cb * tiles_x;
         const int n = row / H, y = row - n * H;
         const int x0 = tx * kRowCells;
@@ -293,68 +223,118 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
                 int off_lo, off_hi, wl, wh;
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(off_lo), "=r"(off_hi), "=r"(wl), "=r"(wh)
                              : "r"(stage_s + slot * SB + j * 16));
-                u64x v[HV];
-                {
-                    const unsigned a = lane_acc + off_lo;
-                    const u64x ww = pack2(__int_as_float(wl), __int_as_float(wl));
-                    Acc<CPL>::ld(a, v);
+                const unsigned a_lo = lane_acc + off_lo, a_hi = lane_acc + off_hi;
+                const u64x w_lo = pack2(__int_as_float(wl), __int_as_float(wl)), w_hi = pack2(__int_as_float(wh), __int_as_float(wh));
+                u64x v[HV], t[HV];
+                if (off_lo != off_hi) {                 // two distinct cells: both read-modify-writes in flight together
+                    Acc<CPL>::ld(a_lo, v);
+                    Acc<CPL>::ld(a_hi, t);
 #pragma unroll
-                    for (int q = 0; q < HV; ++q) v[q] = fma2(G[j / SR][q], ww, v[q]);
-                    Acc<CPL>::st(a, v);
-                }
-                {
-                    const unsigned a = lane_acc + off_hi;
-                    const u64x ww = pack2(__int_as_float(wh), __int_as_float(wh));
-                    Acc<CPL>::ld(a, v);
+                    for (int q = 0; q < HV; ++q) { v[q] = fma2(G[j / SR][q], w_lo, v[q]); t[q] = fma2(G[j / SR][q], w_hi, t[q]); }
+                    Acc<CPL>::st(a_lo, v);
+                    Acc<CPL>::st(a_hi, t);
+                } else {                                // clamped at the last column: same cell twice, in order
+                    Acc<CPL>::ld(a_lo, v);
 #pragma unroll
-                    for (int q = 0; q < HV; ++q) v[q] = fma2(G[j / SR][q], ww, v[q]);
-                    Acc<CPL>::st(a, v);
+                    for (int q = 0; q < HV; ++q) v[q] = fma2(G[j / SR][q], w_lo, v[q]);
+#pragma unroll
+                    for (int q = 0; q < HV; ++q) v[q] = fma2(G[j / SR][q], w_hi, v[q]);
+                    Acc<CPL>::st(a_lo, v);
                 }
             }
         };
 
-        const int u_begin = row_off[row], u_end = row_off[row + 1];
-        for (int base = u_begin; base < u_end; base += 32) {
-            uint2 u = make_uint2(0u, 0u);
-            bool ov = false;
-            if (base + lane < u_end) {
-                u = units[base + lane];
-                const BwdRoi h = roi_in[u.x & 0xffffu];
-                ov = h.x_lo <= x0 + kRowCells - 1 && h.x_hi >= x0;
-            }
-            unsigned m = __ballot_sync(0xffffffffu, ov);
-            if (m == 0u) continue;
-            // Software pipeline over the overlapping units of this batch, two register sets for the gradients:
-            //   x-table entry of unit k+1 in flight | A(k): records + gradient loads | B(k-1): taps
-            u64x Ga[PW][HV], Gb[PW][HV];
-            unsigned bma = 0u, bmb = 0u;
-            unsigned key_n = 0u; float wy_n = 0.f; AxisEntry e_n = make_axis_zero();
-            auto fetch_next = [&]() -> bool {
-                if (m == 0u) return false;
-                const int l = __ffs(m) - 1; m &= m - 1u;
-                key_n = __shfl_sync(0xffffffffu, u.x, l);
-                wy_n = __uint_as_float(__shfl_sync(0xffffffffu, u.y, l));
-                if (lane < NX) e_n = xtab[(size_t)(key_n & 0xffffu) * NX + lane];
-                return true;
-            };
-            fetch_next();
-            unsigned key = key_n; float wy = wy_n; AxisEntry e = e_n;
-            bool more = fetch_next();
-            bma = stage_a(key, wy, e, 0, Ga);
+        // Process the first `count` units of the per-warp list.  Software pipeline, two register sets for the gradients:
+        //   x-table entry of unit k+1 in flight | A(k): records + gradient loads | B(k-1): taps
+        auto process_list = [&](int count) {
             __syncwarp();
-            for (;;) {
-                if (!more) { stage_b(0, Ga, bma); break; }
-                key = key_n; wy = wy_n; e = e_n; more = fetch_next();
-                bmb = stage_a(key, wy, e, 1, Gb);
-                stage_b(0, Ga, bma);
-                __syncwarp();
-                if (!more) { stage_b(1, Gb, bmb); break; }
-                key = key_n; wy = wy_n; e = e_n; more = fetch_next();
+            for (int base = 0; base < count; base += 32) {
+                unsigned ux = 0u, uy = 0u;
+                if (base + lane < count) asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(list_s + (base + lane) * 8));
+                unsigned m = (count - base >= 32) ? 0xffffffffu : ((1u << (count - base)) - 1u);
+                u64x Ga[PW][HV], Gb[PW][HV];
+                unsigned bma = 0u, bmb = 0u;
+                unsigned key_n = 0u; float wy_n = 0.f; AxisEntry e_n = make_axis_zero();
+                auto fetch_next = [&]() -> bool {
+                    if (m == 0u) return false;
+                    const int l = __ffs(m) - 1; m &= m - 1u;
+                    key_n = __shfl_sync(0xffffffffu, ux, l);
+                    wy_n = __uint_as_float(__shfl_sync(0xffffffffu, uy, l));
+                    if (lane < NX) e_n = xtab[(size_t)(key_n & 0xffffu) * NX + lane];
+                    return true;
+                };
+                fetch_next();
+                unsigned key = key_n; float wy = wy_n; AxisEntry e = e_n;
+                bool more = fetch_next();
                 bma = stage_a(key, wy, e, 0, Ga);
-                stage_b(1, Gb, bmb);
+                __syncwarp();
+                for (;;) {
+                    if (!more) { stage_b(0, Ga, bma); break; }
+                    key = key_n; wy = wy_n; e = e_n; more = fetch_next();
+                    bmb = stage_a(key, wy, e, 1, Gb);
+                    stage_b(0, Ga, bma);
+                    __syncwarp();
+                    if (!more) { stage_b(1, Gb, bmb); break; }
+                    key = key_n; wy = wy_n; e = e_n; more = fetch_next();
+                    bma = stage_a(key, wy, e, 0, Ga);
+                    stage_b(1, Gb, bmb);
+                    __syncwarp();
+                }
                 __syncwarp();
             }
-            __syncwarp();
+        };
+
+        // Collect the units of this item: RoIs overlapping the row and the x-tile (lanes = RoIs), then the y-samples of
+        // each such RoI whose low / high cell is row y (lanes = samples; the next RoI's table entry is already in flight).
+        const unsigned lt_mask = (1u << lane) - 1u;
+        int scan_base = 0, batch_base = 0;              // next header batch / batch the mask `m` refers to
+        unsigned m = 0u;
+        int rr_n = -1;                                  // next RoI (its y-table entry is in flight), -1: none left
+        AxisEntry ey_n = make_axis_zero();
+        auto advance_next = [&]() {
+            for (;;) {
+                if (m) {
+                    rr_n = batch_base + __ffs(m) - 1; m &= m - 1u;
+                    if (lane < ny) ey_n = ytab[(size_t)rr_n * ny + lane];
+                    return;
+                }
+                if (scan_base >= R) { rr_n = -1; return; }
+                bool ov = false;
+                if (scan_base + lane < R) {
+                    const int4 h = *reinterpret_cast<const int4*>(&roi_in[scan_base + lane]);     // batch, x_lo, x_hi, y_lo
+                    const int y_hi = roi_in[scan_base + lane].y_hi;
+                    ov = h.x == n && h.y <= x0 + kRowCells - 1 && h.z >= x0 && h.w <= y && y_hi >= y;
+                }
+                m = __ballot_sync(0xffffffffu, ov);
+                batch_base = scan_base; scan_base += 32;
+            }
+        };
+        advance_next();
+        int rr_c = -1;
+        AxisEntry ey_c = make_axis_zero();
+        bool pending = false;                           // rr_c did not fit into the list: first unit(s) of the next round
+        for (;;) {
+            int cnt = 0;
+            for (;;) {
+                if (!pending) {
+                    rr_c = rr_n; ey_c = ey_n;
+                    if (rr_c < 0) break;
+                    advance_next();
+                }
+                pending = false;
+                const bool hit_lo = lane < ny && ey_c.valid && ey_c.low == y;
+                const bool hit_hi = lane < ny && ey_c.valid && min(ey_c.low + 1, H - 1) == y;
+                const unsigned ml = __ballot_sync(0xffffffffu, hit_lo), mh = __ballot_sync(0xffffffffu, hit_hi);
+                if ((ml | mh) == 0u) continue;
+                const int nl = __popc(ml), nh = __popc(mh);
+                if (cnt + nl + nh > kListCap) { pending = true; break; }
+                const unsigned key = (unsigned)rr_c | ((unsigned)lane << 16);
+                if (hit_lo) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(list_s + (cnt + __popc(ml & lt_mask)) * 8), "r"(key), "r"(__float_as_int(ey_c.h)) : "memory");
+                if (hit_hi) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(list_s + (cnt + nl + __popc(mh & lt_mask)) * 8), "r"(key | 0x80000000u), "r"(__float_as_int(ey_c.l)) : "memory");
+                cnt += nl + nh;
+            }
+            process_list(cnt);
+            if (!pending) break;
         }
 
         {   // write-out: lane = cell; CPL channels per shared load, one coalesced 128-byte row segment per channel
@@ -385,7 +365,7 @@ size_t roi_align_bwd_rows_workspace_bytes(int N, int R, int C, int H, int W, int
 }
 
 template <int PW, int SR, int CPL, int WARPS>
-static int launch_rows(const RowsPlan& p, unsigned char* ws, float* dx, int N, int C, int H, int W, int PH, cudaStream_t stream) {
+static int launch_rows(const RowsPlan& p, unsigned char* ws, float* dx, int N, int R, int C, int H, int W, int PH, cudaStream_t stream) {
     constexpr int NX = PW * SR;
     const size_t smem = (size_t)WARPS * rows_warp_smem<CPL, NX>();
     auto kern = roi_align_bwd_rows<PW, SR, CPL, WARPS>;
@@ -401,9 +381,8 @@ static int launch_rows(const RowsPlan& p, unsigned char* ws, float* dx, int N, i
     if (grid * WARPS > warps_needed) grid = (warps_needed + WARPS - 1) / WARPS;
     kern<<<grid, WARPS * 32, smem, stream>>>(
         reinterpret_cast<const BwdRoi*>(ws + p.roi_off), reinterpret_cast<const AxisEntry*>(ws + p.xtab_off),
-        reinterpret_cast<const int*>(ws + p.row_off_off), reinterpret_cast<const int*>(ws + p.row_rank_off),
-        reinterpret_cast<const uint2*>(ws + p.units_off), reinterpret_cast<int*>(ws + p.counter_off),
-        reinterpret_cast<const float*>(ws + p.dyt_off), dx, N, C, H, W, PH, p.tiles_x);
+        reinterpret_cast<const AxisEntry*>(ws + p.ytab_off), reinterpret_cast<int*>(ws + p.counter_off),
+        reinterpret_cast<const float*>(ws + p.dyt_off), dx, N, R, C, H, W, PH, p.tiles_x);
     return B200_ROI_OK;
 }
 
@@ -415,13 +394,12 @@ int roi_align_backward_rows(const float* top_diff, float scale, int N, int R, in
     if (workspace == nullptr || workspace_bytes < p.ws_bytes) return 1000;
     unsigned char* ws = (unsigned char*)workspace;
     const int bins = PH * PW;
-    const size_t smem_bucket = (size_t)2 * p.rows * sizeof(int);
     const size_t smem_tr = (size_t)kTransposeChannels * (bins | 1) * sizeof(float);
-    if (smem_bucket > 200 * 1024 || smem_tr > 200 * 1024) return 1000;
+    if (smem_tr > 200 * 1024) return 1000;
     cudaError_t err = cudaSuccess;
     if (smem_tr > 48 * 1024) err = cudaFuncSetAttribute(roi_align_bwd_rows_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tr);
     if (err != cudaSuccess) return (int)err;
-    if (smem_bucket > 48 * 1024) err = cudaFuncSetAttribute(roi_align_bwd_rows_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bucket);
+    err = cudaMemsetAsync(ws + p.counter_off, 0, 64, stream);           // the main kernel's item counter
     if (err != cudaSuccess) return (int)err;
     const int cblocks = (C + kTransposeChannels - 1) / kTransposeChannels;
     const int table_ctas = (R * (p.ny + p.nx) + kTableThreads - 1) / kTableThreads;
@@ -429,24 +407,20 @@ int roi_align_backward_rows(const float* top_diff, float scale, int N, int R, in
         rois, top_diff, scale, N, R, C, H, W, PH, PW, sr, table_ctas, reinterpret_cast<BwdRoi*>(ws + p.roi_off),
         reinterpret_cast<AxisEntry*>(ws + p.xtab_off), reinterpret_cast<AxisEntry*>(ws + p.ytab_off),
         reinterpret_cast<float*>(ws + p.dyt_off));
-    roi_align_bwd_rows_bucket<<<1, kBucketThreads, smem_bucket, stream>>>(
-        reinterpret_cast<const BwdRoi*>(ws + p.roi_off), reinterpret_cast<const AxisEntry*>(ws + p.ytab_off), N, R, H, p.ny,
-        reinterpret_cast<int*>(ws + p.row_off_off), reinterpret_cast<int*>(ws + p.row_rank_off),
-        reinterpret_cast<uint2*>(ws + p.units_off), reinterpret_cast<int*>(ws + p.counter_off));
     const char* e_cpl = getenv("B200_ROI_ALIGN_BWD_CPL");       // channels per lane of the main kernel: 2 | 4 (A/B tests)
     const bool want4 = !(e_cpl && e_cpl[0] == '2');
     int rc;
     if (PW == 7) {
-        if (want4 && (C % 128) == 0) rc = (sr == 1) ? launch_rows<7, 1, 4, 12>(p, ws, bottom_diff, N, C, H, W, PH, stream)
-                                                     : launch_rows<7, 2, 4, 12>(p, ws, bottom_diff, N, C, H, W, PH, stream);
-        else rc = (sr == 1) ? launch_rows<7, 1, 2, 12>(p, ws, bottom_diff, N, C, H, W, PH, stream)
-                            : launch_rows<7, 2, 2, 12>(p, ws, bottom_diff, N, C, H, W, PH, stream);
+        if (want4 && (C % 128) == 0) rc = (sr == 1) ? launch_rows<7, 1, 4, 12>(p, ws, bottom_diff, N, R, C, H, W, PH, stream)
+                                                     : launch_rows<7, 2, 4, 12>(p, ws, bottom_diff, N, R, C, H, W, PH, stream);
+        else rc = (sr == 1) ? launch_rows<7, 1, 2, 12>(p, ws, bottom_diff, N, R, C, H, W, PH, stream)
+                            : launch_rows<7, 2, 2, 12>(p, ws, bottom_diff, N, R, C, H, W, PH, stream);
     } else {
-        rc = (sr == 1) ? launch_rows<14, 1, 2, 12>(p, ws, bottom_diff, N, C, H, W, PH, stream)
-                       : launch_rows<14, 2, 2, 12>(p, ws, bottom_diff, N, C, H, W, PH, stream);
+        rc = (sr == 1) ? launch_rows<14, 1, 2, 12>(p, ws, bottom_diff, N, R, C, H, W, PH, stream)
+                       : launch_rows<14, 2, 2, 12>(p, ws, bottom_diff, N, R, C, H, W, PH, stream);
     }
     if (rc != B200_ROI_OK) return rc;
-    return finish_launch(3);
+    return finish_launch(2);
 }
 
 }  // namespace b200
