@@ -6,21 +6,23 @@
 // WARP owns the item's accumulator ([cell][channel] in shared memory, lane = 2 / 4 adjacent channels), visits every
 // bilinear tap that lands in it and read-modify-writes the accumulator with plain 64/128-bit shared accesses.  Each
 // dX element is produced by exactly one warp and written exactly once with coalesced 128-byte stores, so there is
-// no memset, no atomic and no scratch image; accumulation order inside an item is sequential and fixed.
+// no memset of dX, no floating-point atomic and no scratch image; accumulation inside an item is sequential.
 //
 //   tables (1 launch, parallel)  per-RoI axis sample tables (all IEEE divisions) and, in the same launch,
 //                                dY (R, C, PH, PW) -> dYt (R, PH, PW, C) / count: channel-innermost, so that a
 //                                warp reads the gradient of a bin for its channels with one coalesced access.
-//   main   (persistent warps)    item <- atomic counter; zero accumulator; scan the RoI headers (lanes = RoIs) for
-//                                those that overlap the row and the x-tile; for each, lanes = y-samples find the
-//                                samples whose low / high cell is this row: every hit is a "unit" (RoI, y-sample,
-//                                weight hy or ly), collected in a small per-warp list.  Per unit: lanes j < PW*sr
-//                                build the tap records of x-sample j (cell offset, wy * wx), staged in shared
-//                                memory; the gradients of the needed bins are loaded to registers (software
-//                                pipelined one unit ahead); taps are applied with LDS / FFMA2 / STS (taps outside
-//                                the tile land in a scratch cell instead of being branched around).  Finally the
-//                                row segment is transposed to NCHW on the way out.  Units are visited in RoI
-//                                order, so the result is deterministic (bitwise reproducible run to run).
+//                                Every valid y-sample of every RoI contributes two "units" (row of its low cell
+//                                with weight hy, row of its high cell with weight ly); the table threads append
+//                                them to fixed-capacity per-row lists (one atomicAdd on the row's counter each;
+//                                units beyond the capacity go to one overflow list that every row scans --
+//                                correct for any input, fast for all but pathological RoI pile-ups).
+//   main   (persistent warps)    item <- atomic counter; zero accumulator; for each unit of the row whose RoI
+//                                overlaps the x-tile: lanes j < PW*sr build the tap records of x-sample j (cell
+//                                offset, wy * wx), staged in shared memory; the gradients of the needed bins are
+//                                loaded to registers (software pipelined one unit ahead); taps are applied with
+//                                LDS / FFMA2 / STS (taps outside the tile land in a scratch cell instead of
+//                                being branched around).  Finally the row segment is transposed to NCHW on the
+//                                way out.
 //
 // Numerics: per tap the term is (dY / count) * (wy * wx) with count = sr^2 in {1, 4}: the division is an exact
 // scaling, so the term equals the reference's FMUL(dY, w) / count bit for bit (barring underflow); only the order
@@ -35,7 +37,6 @@ namespace b200 {
 constexpr int kRowCells = 32;             // cells per x-tile = lanes of the write-out
 constexpr int kTableThreads = 256;
 constexpr int kTransposeChannels = 64;    // channels per transpose CTA
-constexpr int kListCap = 128;             // units a warp collects before it processes them
 
 struct __align__(16) BwdRoi {
     int batch;                            // -1: batch index out of range (contributes nothing)
@@ -48,8 +49,8 @@ __device__ __forceinline__ unsigned smem_u32addr(const void* p) { return (unsign
 __device__ __forceinline__ AxisEntry make_axis_zero() { AxisEntry e; e.low = 0; e.valid = 0; e.l = 0.f; e.h = 0.f; return e; }
 
 struct RowsPlan {
-    int ny, nx, tiles_x, rows;
-    size_t roi_off, xtab_off, ytab_off, counter_off, dyt_off, ws_bytes;
+    int ny, nx, tiles_x, rows, row_cap;
+    size_t roi_off, xtab_off, zero_off, zero_bytes, row_list_off, ovf_off, dyt_off, ws_bytes;
 };
 
 static bool rows_plan(int N, int R, int C, int H, int W, int PH, int PW, int sr, RowsPlan* p) {
@@ -61,8 +62,17 @@ static bool rows_plan(int N, int R, int C, int H, int W, int PH, int PW, int sr,
     size_t off = 0;
     p->roi_off = off;      off = align_up(off + (size_t)R * sizeof(BwdRoi), 256);
     p->xtab_off = off;     off = align_up(off + (size_t)R * p->nx * sizeof(AxisEntry), 256);
-    p->ytab_off = off;     off = align_up(off + (size_t)R * p->ny * sizeof(AxisEntry), 256);
-    p->counter_off = off;  off = align_up(off + 64, 256);
+    // zeroed per call: [0] item counter, [1] overflow count, [4 ..] units per row
+    p->zero_off = off;     p->zero_bytes = align_up(((size_t)p->rows + 4) * sizeof(int), 256); off += p->zero_bytes;
+    const long long total_units = 2LL * R * p->ny;
+    long long cap = 8 * ((total_units + p->rows - 1) / p->rows);            // 8x the mean row population
+    if (cap < 64) cap = 64;
+    if (cap > total_units) cap = total_units;
+    if (cap * p->rows * 8 > (64LL << 20)) cap = (64LL << 20) / (8LL * p->rows);
+    if (cap < 32) return false;
+    p->row_cap = (int)cap;
+    p->row_list_off = off; off = align_up(off + (size_t)p->rows * p->row_cap * sizeof(uint2), 256);
+    p->ovf_off = off;      off = align_up(off + (size_t)total_units * sizeof(uint4), 256);
     p->dyt_off = off;      off = align_up(off + (size_t)R * PH * PW * C * sizeof(float), 256);
     p->ws_bytes = off;
     return true;
@@ -74,7 +84,8 @@ static bool rows_plan(int N, int R, int C, int H, int W, int PH, int PW, int sr,
 __global__ void __launch_bounds__(kTableThreads)
 roi_align_bwd_rows_tables(const float* __restrict__ rois, const float* __restrict__ dy, float scale, int N, int R, int C, int H,
                           int W, int PH, int PW, int sr, int table_ctas, BwdRoi* __restrict__ roi_out,
-                          AxisEntry* __restrict__ xtab, AxisEntry* __restrict__ ytab, float* __restrict__ dyt) {
+                          AxisEntry* __restrict__ xtab, int* __restrict__ zeroed, uint2* __restrict__ row_list, int row_cap,
+                          uint4* __restrict__ ovf, float* __restrict__ dyt) {
     extern __shared__ __align__(16) float s_tr[];
     const int tid = threadIdx.x;
     const int ny = PH * sr, nx = PW * sr;
@@ -87,9 +98,20 @@ roi_align_bwd_rows_tables(const float* __restrict__ rois, const float* __restric
         const bool isy = s < ny;
         const AxisEntry e = tiled_axis_entry(g, isy, isy ? s : s - ny, sr, H, W);
         if (isy) {                                                              // lows are monotone along an axis
-            ytab[(size_t)r * ny + s] = e;
-            if (s == 0) { roi_out[r].batch = (g.batch >= 0 && g.batch < N) ? g.batch : -1; roi_out[r].y_lo = e.low; }
+            const bool batch_ok = g.batch >= 0 && g.batch < N;
+            if (s == 0) { roi_out[r].batch = batch_ok ? g.batch : -1; roi_out[r].y_lo = e.low; }
             if (s == ny - 1) roi_out[r].y_hi = min(e.low + 1, H - 1);
+            if (batch_ok && e.valid) {
+                const unsigned key = (unsigned)r | ((unsigned)s << 16);
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {                       // row of the low cell: hy; of the high cell: ly
+                    const int row = g.batch * H + (which ? min(e.low + 1, H - 1) : e.low);
+                    const uint2 u = make_uint2(key | (which ? 0x80000000u : 0u), __float_as_uint(which ? e.l : e.h));
+                    const int pos = atomicAdd(&zeroed[4 + row], 1);
+                    if (pos < row_cap) row_list[(size_t)row * row_cap + pos] = u;
+                    else ovf[atomicAdd(&zeroed[1], 1)] = make_uint4(u.x, u.y, (unsigned)row, 0u);
+                }
+            }
         } else {
             xtab[(size_t)r * nx + (s - ny)] = e;
             if (s == ny) roi_out[r].x_lo = e.low;
@@ -144,15 +166,13 @@ template <int NX> __host__ __device__ constexpr int rows_stage_bytes() { return 
 template <int CPL> __host__ __device__ constexpr int rows_acc_bytes() {                              // 32 cells + 1 scratch cell, 16-byte multiple
     return (((kRowCells + 1) * rows_acc_stride<CPL>() * 4 + 15) / 16) * 16;
 }
-template <int CPL, int NX> __host__ __device__ constexpr int rows_warp_smem() {
-    return rows_acc_bytes<CPL>() + 2 * rows_stage_bytes<NX>() + kListCap * 8;
-}
+template <int CPL, int NX> __host__ __device__ constexpr int rows_warp_smem() { return rows_acc_bytes<CPL>() + 2 * rows_stage_bytes<NX>(); }
 
 template <int PW, int SR, int CPL, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restrict__ xtab, const AxisEntry* __restrict__ ytab,
-                   int* __restrict__ counter, const float* __restrict__ dyt, float* __restrict__ dx, int N, int R, int C,
-                   int H, int W, int PH, int tiles_x) {
+roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restrict__ xtab, int* __restrict__ zeroed,
+                   const uint2* __restrict__ row_list, int row_cap, const uint4* __restrict__ ovf, const float* __restrict__ dyt,
+                   float* __restrict__ dx, int N, int C, int H, int W, int PH, int tiles_x) {
     constexpr int NX = PW * SR;
     constexpr int S = rows_acc_stride<CPL>();
     constexpr int CHB = 32 * CPL;                       // channels per item
@@ -164,8 +184,6 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned acc_s = smem_u32addr(smem_raw) + (unsigned)warp * rows_warp_smem<CPL, NX>();
     const unsigned stage_s = acc_s + rows_acc_bytes<CPL>();
-    const unsigned list_s = stage_s + 2 * SB;
-    const int ny = PH * SR;
     const unsigned lane_acc = acc_s + lane * (CPL * 4);
     const int cblocks = C / CHB;
     const int items_per_row = tiles_x * cblocks;
@@ -173,7 +191,7 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
 
     for (;;) {
         int item = 0;
-        if (lane == 0) item = atomicAdd(counter, 1);
+        if (lane == 0) item = atomicAdd(&zeroed[0], 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= total) break;
         const int row = item / items_per_row;
@@ -244,97 +262,60 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
             }
         };
 
-        // Process the first `count` units of the per-warp list.  Software pipeline, two register sets for the gradients:
+        // One batch of <= 32 units (lane = unit; `m` marks the lanes whose RoI overlaps this x-tile).  Software pipeline,
+        // two register sets for the gradients:
         //   x-table entry of unit k+1 in flight | A(k): records + gradient loads | B(k-1): taps
-        auto process_list = [&](int count) {
+        auto process_batch = [&](unsigned ux, unsigned uy, unsigned m) {
+            u64x Ga[PW][HV], Gb[PW][HV];
+            unsigned bma = 0u, bmb = 0u;
+            unsigned key_n = 0u; float wy_n = 0.f; AxisEntry e_n = make_axis_zero();
+            auto fetch_next = [&]() -> bool {
+                if (m == 0u) return false;
+                const int l = __ffs(m) - 1; m &= m - 1u;
+                key_n = __shfl_sync(0xffffffffu, ux, l);
+                wy_n = __uint_as_float(__shfl_sync(0xffffffffu, uy, l));
+                if (lane < NX) e_n = xtab[(size_t)(key_n & 0xffffu) * NX + lane];
+                return true;
+            };
+            fetch_next();
+            unsigned key = key_n; float wy = wy_n; AxisEntry e = e_n;
+            bool more = fetch_next();
+            bma = stage_a(key, wy, e, 0, Ga);
             __syncwarp();
-            for (int base = 0; base < count; base += 32) {
-                unsigned ux = 0u, uy = 0u;
-                if (base + lane < count) asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(ux), "=r"(uy) : "r"(list_s + (base + lane) * 8));
-                unsigned m = (count - base >= 32) ? 0xffffffffu : ((1u << (count - base)) - 1u);
-                u64x Ga[PW][HV], Gb[PW][HV];
-                unsigned bma = 0u, bmb = 0u;
-                unsigned key_n = 0u; float wy_n = 0.f; AxisEntry e_n = make_axis_zero();
-                auto fetch_next = [&]() -> bool {
-                    if (m == 0u) return false;
-                    const int l = __ffs(m) - 1; m &= m - 1u;
-                    key_n = __shfl_sync(0xffffffffu, ux, l);
-                    wy_n = __uint_as_float(__shfl_sync(0xffffffffu, uy, l));
-                    if (lane < NX) e_n = xtab[(size_t)(key_n & 0xffffu) * NX + lane];
-                    return true;
-                };
-                fetch_next();
-                unsigned key = key_n; float wy = wy_n; AxisEntry e = e_n;
-                bool more = fetch_next();
-                bma = stage_a(key, wy, e, 0, Ga);
+            for (;;) {
+                if (!more) { stage_b(0, Ga, bma); break; }
+                key = key_n; wy = wy_n; e = e_n; more = fetch_next();
+                bmb = stage_a(key, wy, e, 1, Gb);
+                stage_b(0, Ga, bma);
                 __syncwarp();
-                for (;;) {
-                    if (!more) { stage_b(0, Ga, bma); break; }
-                    key = key_n; wy = wy_n; e = e_n; more = fetch_next();
-                    bmb = stage_a(key, wy, e, 1, Gb);
-                    stage_b(0, Ga, bma);
-                    __syncwarp();
-                    if (!more) { stage_b(1, Gb, bmb); break; }
-                    key = key_n; wy = wy_n; e = e_n; more = fetch_next();
-                    bma = stage_a(key, wy, e, 0, Ga);
-                    stage_b(1, Gb, bmb);
-                    __syncwarp();
-                }
+                if (!more) { stage_b(1, Gb, bmb); break; }
+                key = key_n; wy = wy_n; e = e_n; more = fetch_next();
+                bma = stage_a(key, wy, e, 0, Ga);
+                stage_b(1, Gb, bmb);
                 __syncwarp();
             }
+            __syncwarp();
         };
 
-        // Collect the units of this item: RoIs overlapping the row and the x-tile (lanes = RoIs), then the y-samples of
-        // each such RoI whose low / high cell is row y (lanes = samples; the next RoI's table entry is already in flight).
-        const unsigned lt_mask = (1u << lane) - 1u;
-        int scan_base = 0, batch_base = 0;              // next header batch / batch the mask `m` refers to
-        unsigned m = 0u;
-        int rr_n = -1;                                  // next RoI (its y-table entry is in flight), -1: none left
-        AxisEntry ey_n = make_axis_zero();
-        auto advance_next = [&]() {
-            for (;;) {
-                if (m) {
-                    rr_n = batch_base + __ffs(m) - 1; m &= m - 1u;
-                    if (lane < ny) ey_n = ytab[(size_t)rr_n * ny + lane];
-                    return;
-                }
-                if (scan_base >= R) { rr_n = -1; return; }
-                bool ov = false;
-                if (scan_base + lane < R) {
-                    const int4 h = *reinterpret_cast<const int4*>(&roi_in[scan_base + lane]);     // batch, x_lo, x_hi, y_lo
-                    const int y_hi = roi_in[scan_base + lane].y_hi;
-                    ov = h.x == n && h.y <= x0 + kRowCells - 1 && h.z >= x0 && h.w <= y && y_hi >= y;
-                }
-                m = __ballot_sync(0xffffffffu, ov);
-                batch_base = scan_base; scan_base += 32;
+        // the row's own list, then (only when some row ran over its capacity) the shared overflow list
+        const int row_cnt = min(zeroed[4 + row], row_cap), ovf_cnt = zeroed[1];
+        const int row_pad = (row_cnt + 31) & ~31;                   // batches do not straddle the two lists
+        const uint2* mine = row_list + (size_t)row * row_cap;
+        for (int base = 0; base < row_pad + ovf_cnt; base += 32) {
+            const int k = base + lane;
+            uint2 u = make_uint2(0u, 0u);
+            bool ov = false;
+            if (k < row_cnt) { u = mine[k]; ov = true; }
+            else if (k >= row_pad && k - row_pad < ovf_cnt) {
+                const uint4 o = ovf[k - row_pad];
+                u = make_uint2(o.x, o.y); ov = (int)o.z == row;
             }
-        };
-        advance_next();
-        int rr_c = -1;
-        AxisEntry ey_c = make_axis_zero();
-        bool pending = false;                           // rr_c did not fit into the list: first unit(s) of the next round
-        for (;;) {
-            int cnt = 0;
-            for (;;) {
-                if (!pending) {
-                    rr_c = rr_n; ey_c = ey_n;
-                    if (rr_c < 0) break;
-                    advance_next();
-                }
-                pending = false;
-                const bool hit_lo = lane < ny && ey_c.valid && ey_c.low == y;
-                const bool hit_hi = lane < ny && ey_c.valid && min(ey_c.low + 1, H - 1) == y;
-                const unsigned ml = __ballot_sync(0xffffffffu, hit_lo), mh = __ballot_sync(0xffffffffu, hit_hi);
-                if ((ml | mh) == 0u) continue;
-                const int nl = __popc(ml), nh = __popc(mh);
-                if (cnt + nl + nh > kListCap) { pending = true; break; }
-                const unsigned key = (unsigned)rr_c | ((unsigned)lane << 16);
-                if (hit_lo) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(list_s + (cnt + __popc(ml & lt_mask)) * 8), "r"(key), "r"(__float_as_int(ey_c.h)) : "memory");
-                if (hit_hi) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(list_s + (cnt + nl + __popc(mh & lt_mask)) * 8), "r"(key | 0x80000000u), "r"(__float_as_int(ey_c.l)) : "memory");
-                cnt += nl + nh;
+            if (ov) {
+                const int4 h = *reinterpret_cast<const int4*>(&roi_in[u.x & 0xffffu]);        // batch, x_lo, x_hi, y_lo
+                ov = h.y <= x0 + kRowCells - 1 && h.z >= x0;
             }
-            process_list(cnt);
-            if (!pending) break;
+            const unsigned m = __ballot_sync(0xffffffffu, ov);
+            if (m) process_batch(u.x, u.y, m);
         }
 
         {   // write-out: lane = cell; CPL channels per shared load, one coalesced 128-byte row segment per channel
@@ -365,7 +346,7 @@ size_t roi_align_bwd_rows_workspace_bytes(int N, int R, int C, int H, int W, int
 }
 
 template <int PW, int SR, int CPL, int WARPS>
-static int launch_rows(const RowsPlan& p, unsigned char* ws, float* dx, int N, int R, int C, int H, int W, int PH, cudaStream_t stream) {
+static int launch_rows(const RowsPlan& p, unsigned char* ws, float* dx, int N, int C, int H, int W, int PH, cudaStream_t stream) {
     constexpr int NX = PW * SR;
     const size_t smem = (size_t)WARPS * rows_warp_smem<CPL, NX>();
     auto kern = roi_align_bwd_rows<PW, SR, CPL, WARPS>;
@@ -381,8 +362,8 @@ static int launch_rows(const RowsPlan& p, unsigned char* ws, float* dx, int N, i
     if (grid * WARPS > warps_needed) grid = (warps_needed + WARPS - 1) / WARPS;
     kern<<<grid, WARPS * 32, smem, stream>>>(
         reinterpret_cast<const BwdRoi*>(ws + p.roi_off), reinterpret_cast<const AxisEntry*>(ws + p.xtab_off),
-        reinterpret_cast<const AxisEntry*>(ws + p.ytab_off), reinterpret_cast<int*>(ws + p.counter_off),
-        reinterpret_cast<const float*>(ws + p.dyt_off), dx, N, R, C, H, W, PH, p.tiles_x);
+        reinterpret_cast<int*>(ws + p.zero_off), reinterpret_cast<const uint2*>(ws + p.row_list_off), p.row_cap,
+        reinterpret_cast<const uint4*>(ws + p.ovf_off), reinterpret_cast<const float*>(ws + p.dyt_off), dx, N, C, H, W, PH, p.tiles_x);
     return B200_ROI_OK;
 }
 
@@ -399,25 +380,26 @@ int roi_align_backward_rows(const float* top_diff, float scale, int N, int R, in
     cudaError_t err = cudaSuccess;
     if (smem_tr > 48 * 1024) err = cudaFuncSetAttribute(roi_align_bwd_rows_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tr);
     if (err != cudaSuccess) return (int)err;
-    err = cudaMemsetAsync(ws + p.counter_off, 0, 64, stream);           // the main kernel's item counter
+    err = cudaMemsetAsync(ws + p.zero_off, 0, p.zero_bytes, stream);    // item counter, overflow count, units per row
     if (err != cudaSuccess) return (int)err;
     const int cblocks = (C + kTransposeChannels - 1) / kTransposeChannels;
     const int table_ctas = (R * (p.ny + p.nx) + kTableThreads - 1) / kTableThreads;
     roi_align_bwd_rows_tables<<<table_ctas + R * cblocks, kTableThreads, smem_tr, stream>>>(
         rois, top_diff, scale, N, R, C, H, W, PH, PW, sr, table_ctas, reinterpret_cast<BwdRoi*>(ws + p.roi_off),
-        reinterpret_cast<AxisEntry*>(ws + p.xtab_off), reinterpret_cast<AxisEntry*>(ws + p.ytab_off),
+        reinterpret_cast<AxisEntry*>(ws + p.xtab_off), reinterpret_cast<int*>(ws + p.zero_off),
+        reinterpret_cast<uint2*>(ws + p.row_list_off), p.row_cap, reinterpret_cast<uint4*>(ws + p.ovf_off),
         reinterpret_cast<float*>(ws + p.dyt_off));
     const char* e_cpl = getenv("B200_ROI_ALIGN_BWD_CPL");       // channels per lane of the main kernel: 2 | 4 (A/B tests)
     const bool want4 = !(e_cpl && e_cpl[0] == '2');
     int rc;
     if (PW == 7) {
-        if (want4 && (C % 128) == 0) rc = (sr == 1) ? launch_rows<7, 1, 4, 12>(p, ws, bottom_diff, N, R, C, H, W, PH, stream)
-                                                     : launch_rows<7, 2, 4, 12>(p, ws, bottom_diff, N, R, C, H, W, PH, stream);
-        else rc = (sr == 1) ? launch_rows<7, 1, 2, 12>(p, ws, bottom_diff, N, R, C, H, W, PH, stream)
-                            : launch_rows<7, 2, 2, 12>(p, ws, bottom_diff, N, R, C, H, W, PH, stream);
+        if (want4 && (C % 128) == 0) rc = (sr == 1) ? launch_rows<7, 1, 4, 12>(p, ws, bottom_diff, N, C, H, W, PH, stream)
+                                                     : launch_rows<7, 2, 4, 12>(p, ws, bottom_diff, N, C, H, W, PH, stream);
+        else rc = (sr == 1) ? launch_rows<7, 1, 2, 12>(p, ws, bottom_diff, N, C, H, W, PH, stream)
+                            : launch_rows<7, 2, 2, 12>(p, ws, bottom_diff, N, C, H, W, PH, stream);
     } else {
-        rc = (sr == 1) ? launch_rows<14, 1, 2, 12>(p, ws, bottom_diff, N, R, C, H, W, PH, stream)
-                       : launch_rows<14, 2, 2, 12>(p, ws, bottom_diff, N, R, C, H, W, PH, stream);
+        rc = (sr == 1) ? launch_rows<14, 1, 2, 12>(p, ws, bottom_diff, N, C, H, W, PH, stream)
+                       : launch_rows<14, 2, 2, 12>(p, ws, bottom_diff, N, C, H, W, PH, stream);
     }
     if (rc != B200_ROI_OK) return rc;
     return finish_launch(2);

@@ -153,6 +153,21 @@ def test_roi_align_backward_rows_path(name, cpl, monkeypatch):
     np.testing.assert_allclose(dx2, dx, **GRAD_TOL)
 
 
+def test_roi_align_backward_rows_path_row_overflow(monkeypatch):
+    """400 tiny RoIs piled onto the same few rows of a tall map: the per-row unit lists (capacity = 8x the mean row
+    population) run over and the shared overflow list is exercised."""
+    monkeypatch.setenv("B200_ROI_ALIGN_BWD_PATH", "rows")
+    shape, s, P, sr = (1, 64, 200, 40), 1.0 / 4, 7, 2
+    rng = np.random.RandomState(5)
+    n = 400
+    x1 = rng.uniform(0, 120, n); y1 = rng.uniform(396, 404, n)
+    r = np.stack([np.zeros(n), x1, y1, x1 + rng.uniform(2, 30, n), y1 + rng.uniform(0.5, 3, n)], axis=1).astype(np.float32)
+    dy = rng.standard_normal((n, shape[1], P, P)).astype(np.float32)
+    f = S.make_features(shape, seed=1)
+    _, dx = run_fwd_bwd(RoIAlignFunction(P, P, s, sr), f, r, dy)
+    np.testing.assert_allclose(dx, O.roi_align_backward(dy, r, shape, P, P, s, sr, acc64=True), rtol=1e-5, atol=2e-5)
+
+
 def test_roi_align_forward_linearity_and_determinism(fwd_path):
     cfg = S.CFG2
     P, s, sr = cfg["pooled"], cfg["scale"], cfg["sampling_ratio"]
