@@ -165,7 +165,9 @@ def test_roi_align_backward_rows_path_row_overflow(monkeypatch):
     dy = rng.standard_normal((n, shape[1], P, P)).astype(np.float32)
     f = S.make_features(shape, seed=1)
     _, dx = run_fwd_bwd(RoIAlignFunction(P, P, s, sr), f, r, dy)
-    np.testing.assert_allclose(dx, O.roi_align_backward(dy, r, shape, P, P, s, sr, acc64=True), rtol=1e-5, atol=2e-5)
+    # thousands of addends per cell: fp32 accumulation (ours, and the reference's atomicAdd alike) is only good to
+    # ~n * eps * sum|terms| against the fp64 oracle, hence the wider tolerance of this stress case
+    np.testing.assert_allclose(dx, O.roi_align_backward(dy, r, shape, P, P, s, sr, acc64=True), rtol=1e-4, atol=1e-4)
 
 
 def test_roi_align_forward_linearity_and_determinism(fwd_path):
