@@ -37,6 +37,7 @@ namespace b200 {
 constexpr int kRowCells = 32;             // cells per x-tile = lanes of the write-out
 constexpr int kTableThreads = 256;
 constexpr int kTransposeChannels = 64;    // channels per transpose CTA
+constexpr int kRankRows = 1024;           // N * H up to which the main kernel orders the rows by weight
 
 struct __align__(16) BwdRoi {
     int batch;                            // -1: batch index out of range (contributes nothing)
@@ -169,7 +170,7 @@ template <int CPL> __host__ __device__ constexpr int rows_acc_bytes() {         
 template <int CPL, int NX> __host__ __device__ constexpr int rows_warp_smem() { return rows_acc_bytes<CPL>() + 2 * rows_stage_bytes<NX>(); }
 
 template <int PW, int SR, int CPL, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, (CPL == 2) ? 2 : 1)
 roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restrict__ xtab, int* __restrict__ zeroed,
                    const uint2* __restrict__ row_list, int row_cap, const uint4* __restrict__ ovf, const float* __restrict__ dyt,
                    float* __restrict__ dx, int N, int C, int H, int W, int PH, int tiles_x) {
@@ -189,13 +190,40 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
     const int items_per_row = tiles_x * cblocks;
     const int total = N * H * items_per_row;
 
+    // Rows are handed out heaviest first (fewer stragglers at the end): every CTA derives the same order from the
+    // per-row unit counts with a counting sort in shared memory (the accumulators are not in use yet).
+    __shared__ unsigned short s_order[kRankRows];
+    const int rows = N * H;
+    const bool ranked = rows <= kRankRows;
+    if (ranked) {
+        int* hist = reinterpret_cast<int*>(smem_raw);               // [1024] bins by descending (clamped) count
+        for (int k = threadIdx.x; k < 1024; k += WARPS * 32) hist[k] = 0;
+        __syncthreads();
+        for (int k = threadIdx.x; k < rows; k += WARPS * 32) atomicAdd(&hist[1023 - min(zeroed[4 + k], 1023)], 1);
+        __syncthreads();
+        if (warp == 0) {                                            // exclusive prefix, 32 bins per lane
+            int sum = 0;
+            for (int k = 0; k < 32; ++k) sum += hist[lane * 32 + k];
+            int incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+            int run = incl - sum;
+            for (int k = 0; k < 32; ++k) { const int c = hist[lane * 32 + k]; hist[lane * 32 + k] = run; run += c; }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < rows; k += WARPS * 32)
+            s_order[atomicAdd(&hist[1023 - min(zeroed[4 + k], 1023)], 1)] = (unsigned short)k;
+        __syncthreads();
+    }
+
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(&zeroed[0], 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= total) break;
-        const int row = item / items_per_row;
-        const int rem = item - row * items_per_row;
+        const int slot = item / items_per_row;
+        const int row = ranked ? (int)s_order[slot] : slot;
+        const int rem = item - slot * items_per_row;
         const int cb = rem / tiles_x, tx = rem - cb * tiles_x;
         const int n = row / H, y = row - n * H;
         const int x0 = tx * kRowCells;
@@ -218,7 +246,8 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
             if (lane < NX && e.valid) {
                 const int lo = e.low - x0, hi = min(e.low + 1, W - 1) - x0;
                 if ((unsigned)lo < (unsigned)kRowCells) { off_lo = lo * kCellBytes; any = true; }
-                if ((unsigned)hi < (unsigned)kRowCells) { off_hi = hi * kCellBytes; any = true; }
+                // clamped at the last column (hi == lo): the high tap's weight is exactly 0 (xfrom_axis), drop it
+                if ((unsigned)hi < (unsigned)kRowCells && hi != lo) { off_hi = hi * kCellBytes; any = true; }
                 w_lo = __fmul_rn(wy, e.h);
                 w_hi = __fmul_rn(wy, e.l);
             }
@@ -244,21 +273,13 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
                 const unsigned a_lo = lane_acc + off_lo, a_hi = lane_acc + off_hi;
                 const u64x w_lo = pack2(__int_as_float(wl), __int_as_float(wl)), w_hi = pack2(__int_as_float(wh), __int_as_float(wh));
                 u64x v[HV], t[HV];
-                if (off_lo != off_hi) {                 // two distinct cells: both read-modify-writes in flight together
-                    Acc<CPL>::ld(a_lo, v);
-                    Acc<CPL>::ld(a_hi, t);
+                // the two cells are distinct (or both the scratch cell): both read-modify-writes in flight together
+                Acc<CPL>::ld(a_lo, v);
+                Acc<CPL>::ld(a_hi, t);
 #pragma unroll
-                    for (int q = 0; q < HV; ++q) { v[q] = fma2(G[j / SR][q], w_lo, v[q]); t[q] = fma2(G[j / SR][q], w_hi, t[q]); }
-                    Acc<CPL>::st(a_lo, v);
-                    Acc<CPL>::st(a_hi, t);
-                } else {                                // clamped at the last column: same cell twice, in order
-                    Acc<CPL>::ld(a_lo, v);
-#pragma unroll
-                    for (int q = 0; q < HV; ++q) v[q] = fma2(G[j / SR][q], w_lo, v[q]);
-#pragma unroll
-                    for (int q = 0; q < HV; ++q) v[q] = fma2(G[j / SR][q], w_hi, v[q]);
-                    Acc<CPL>::st(a_lo, v);
-                }
+                for (int q = 0; q < HV; ++q) { v[q] = fma2(G[j / SR][q], w_lo, v[q]); t[q] = fma2(G[j / SR][q], w_hi, t[q]); }
+                Acc<CPL>::st(a_lo, v);
+                Acc<CPL>::st(a_hi, t);
             }
         };
 
