@@ -211,8 +211,20 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
             for (int k = 0; k < 32; ++k) { const int c = hist[lane * 32 + k]; hist[lane * 32 + k] = run; run += c; }
         }
         __syncthreads();
-        for (int k = threadIdx.x; k < rows; k += WARPS * 32)
-            s_order[atomicAdd(&hist[1023 - min(zeroed[4 + k], 1023)], 1)] = (unsigned short)k;
+        // stable placement by one warp (the order must be the same in every CTA): rows in index order, 32 at a time
+        if (warp == 0) {
+            for (int base = 0; base < rows; base += 32) {
+                const int k = base + lane;
+                const bool valid = k < rows;
+                const int b = valid ? 1023 - min(zeroed[4 + k], 1023) : 1024 + lane;
+                const unsigned peers = __match_any_sync(0xffffffffu, b);
+                const int start = valid ? hist[b] : 0;
+                __syncwarp();
+                if (valid && (peers & ((1u << lane) - 1u)) == 0u) hist[b] = start + __popc(peers);
+                __syncwarp();
+                if (valid) s_order[start + __popc(peers & ((1u << lane) - 1u))] = (unsigned short)k;
+            }
+        }
         __syncthreads();
     }
 
