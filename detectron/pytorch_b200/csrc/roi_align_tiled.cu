@@ -144,42 +144,6 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
     const int cs = lane >> 3, bb = lane & 7;              // flush mapping:   (channel within a group of 4, staged bin)
     const size_t plane = (size_t)H * W;
 
-    // Tiles are handed out heaviest first (the persistent CTAs finish closer together): every CTA derives the same
-    // order from the per-tile list lengths with a counting sort in shared memory (the tile buffer is not in use yet);
-    // the placement is done by one warp in index order so that all CTAs agree.
-    unsigned short* order = reinterpret_cast<unsigned short*>(misc + 16);
-    const int n_tiles = n_work / n_cgroups;
-    const bool ranked = n_tiles <= kRankTiles;
-    if (ranked) {
-        int* hist = reinterpret_cast<int*>(smem_raw);     // [1024] bins by descending (clamped) list length
-        for (int k = tid; k < 1024; k += kTiledThreads) hist[k] = 0;
-        __syncthreads();
-        for (int k = tid; k < n_tiles; k += kTiledThreads) atomicAdd(&hist[1023 - min(tile_count[k], 1023)], 1);
-        __syncthreads();
-        if (warp == 0) {
-            int sum = 0;
-            for (int k = 0; k < 32; ++k) sum += hist[lane * 32 + k];
-            int incl = sum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-            int run = incl - sum;
-            for (int k = 0; k < 32; ++k) { const int c = hist[lane * 32 + k]; hist[lane * 32 + k] = run; run += c; }
-            __syncwarp();
-            for (int base = 0; base < n_tiles; base += 32) {
-                const int k = base + lane;
-                const bool valid = k < n_tiles;
-                const int b = valid ? 1023 - min(tile_count[k], 1023) : 1024 + lane;
-                const unsigned peers = __match_any_sync(0xffffffffu, b);
-                const int start = valid ? hist[b] : 0;
-                __syncwarp();
-                if (valid && (peers & ((1u << lane) - 1u)) == 0u) hist[b] = start + __popc(peers);
-                __syncwarp();
-                if (valid) order[start + __popc(peers & ((1u << lane) - 1u))] = (unsigned short)k;
-            }
-        }
-        __syncthreads();
-    }
-
     if (tid == 0) misc[0] = atomicAdd(work_counter, 1);
     for (;;) {
         __syncthreads();                                  // misc[0] published; previous item fully consumed
@@ -191,9 +155,8 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
         unsigned long long* const timing = B200_TIMING_PTR;
         long long t_start = 0, t_staged = 0, t_done = 0;
         if (timing) t_start = clock64();
-        const int tile_slot = work / n_cgroups;           // consecutive items share a tile (same list, tables hit L2)
-        const int c0 = (work - tile_slot * n_cgroups) * kCG;
-        const int tile_id = ranked ? (int)order[tile_slot] : tile_slot;
+        const int tile_id = work / n_cgroups;             // consecutive items share a tile (same list, tables hit L2)
+        const int c0 = (work - tile_id * n_cgroups) * kCG;
         const int n_list = tile_count[tile_id];
         if (n_list == 0) {                                // uniform: nothing samples this tile
             __syncthreads();

@@ -46,12 +46,10 @@ struct TiledPlan {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-constexpr int kRankTiles = 1024;        // up to this many tiles the forward hands the tiles out heaviest first
-
-// shared memory of a work item: [tile][per-warp axis tables (ny + nx entries)][per-warp staging][misc][tile order]
+// shared memory of a work item: [tile][per-warp axis tables (ny + nx entries)][per-warp staging][misc]
 __host__ __device__ inline size_t tiled_smem_bytes(int tile_h, int ny, int nx) {
     return (size_t)kTX * tile_h * kCellWords * 4 + (size_t)kWarps * (ny + nx) * 16 +
-           (size_t)kWarps * kCG * kStageWords * 4 + 64 + kRankTiles * 2;
+           (size_t)kWarps * kCG * kStageWords * 4 + 64;
 }
 
 // Tile geometry + workspace layout.  `backward` adds the per-row unit lists.
