@@ -23,11 +23,11 @@ if [ "$MODE" = "full" ]; then
 fi
 echo "== phase probe (needs B200_NVCC_EXTRA=-DB200_FWD_TIMING build)"
 echo "== ubench"; true
-echo "== ncu nms"; ncu --set full --clock-control none --import-source on -k regex:nms_scan -s 2 -c 1 -o "$OUT/prof_nms" -f python tools/nms_probe.py > "$OUT/ncu_nms.log" 2>&1; tail -2 "$OUT/ncu_nms.log"
+echo "== ncu nms"; ncu --set full --clock-control none --import-source on -k regex:nms_ -s 4 -c 2 -o "$OUT/prof_nms" -f python tools/nms_probe.py > "$OUT/ncu_nms.log" 2>&1; tail -2 "$OUT/ncu_nms.log"
 echo "== ncu launch list"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" \
-    python bench.py --steps 4 --warmup 3 --no-graph > "$OUT/ncu_launches.log" 2>&1; echo "ncu-list rc=$?" | tee -a "$OUT/status.txt"
+    python bench.py --steps 4 --warmup 3 --no-graph --cpu-seconds 1 > "$OUT/ncu_launches.log" 2>&1; echo "ncu-list rc=$?" | tee -a "$OUT/status.txt"
 echo "== ncu full (our kernels)"
-ncu --set full --clock-control none --import-source on -k regex:'roi_align|nms_scan|nhwc' -s 10 -c 8 -o "$OUT/prof" -f \
-    python bench.py --steps 4 --warmup 3 --no-graph > "$OUT/ncu_full.log" 2>&1; echo "ncu-full rc=$?" | tee -a "$OUT/status.txt"
+ncu --set full --clock-control none --import-source on -k regex:'roi_align_tiled|roi_align_bwd_rows' -s 8 -c 5 -o "$OUT/prof" -f \
+    python bench.py --steps 4 --warmup 3 --no-graph --cpu-seconds 1 > "$OUT/ncu_full.log" 2>&1; echo "ncu-full rc=$?" | tee -a "$OUT/status.txt"
 ls -la "$OUT"
