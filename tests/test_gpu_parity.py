@@ -55,6 +55,20 @@ def run_fwd_bwd(fn, f, r, dy):
     return out.detach().cpu().numpy(), F.grad.cpu().numpy()
 
 
+def test_roi_crop_through_affine_grid_gen_matches_grid_sample():
+    """The RoICrop pooling mode as model_builder.py:280-288 chains it: affine_grid_gen -> (y, x) swap -> RoICropFunction.
+    For boxes inside the map this is bilinear grid sampling with corner alignment; torch's grid_sample is an independent
+    implementation of the same arithmetic."""
+    from detectron.pytorch_b200.utils.net import affine_grid_gen
+    feat = dev(S.make_features((1, 6, 30, 44), seed=4))
+    rois = torch.tensor([[0, 16.0, 32.0, 300.0, 200.0], [0, 100.0, 50.0, 600.0, 400.0], [0, 0.0, 0.0, 688.0, 464.0]]).cuda()
+    grid_xy = affine_grid_gen(rois, feat.shape[2:], 7)
+    grid_yx = torch.stack([grid_xy[:, :, :, 1], grid_xy[:, :, :, 0]], 3).contiguous()
+    out = RoICropFunction()(feat, grid_yx)
+    ref = torch.nn.functional.grid_sample(feat.expand(3, -1, -1, -1), grid_xy, mode="bilinear", padding_mode="zeros", align_corners=True)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+
+
 # ---------------------------------------------------------------------------------------- RoIAlign
 def assert_fwd_matches(out, ref, path):
     """generic path: bit-exact.  tiled path: bit-exact except bins whose samples straddle two tiles,
