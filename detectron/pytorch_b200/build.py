@@ -12,7 +12,7 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libb200_roi_ops.so")
+LIB_PATH = os.environ.get("B200_ROI_OPS_LIB") or os.path.join(PKG_DIR, "libb200_roi_ops.so")     # override: A/B builds
 INCLUDE = os.path.join(os.path.dirname(os.path.dirname(PKG_DIR)), "include")
 
 NVCC_FLAGS = [

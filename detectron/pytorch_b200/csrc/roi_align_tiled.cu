@@ -121,7 +121,7 @@ roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int R, 
 // main kernel (persistent)
 // ------------------------------------------------------------------------------------------------
 template <int SR>
-__global__ void __launch_bounds__(kTiledThreads, 2)
+__global__ void __launch_bounds__(kTiledThreads, kTiledCtasPerSM)
 roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restrict__ g_ytab, const AxisEntry* __restrict__ g_xtab,
                     int* __restrict__ work_counter, const int* __restrict__ tile_count,
                     const unsigned* __restrict__ tile_list, int list_stride, float* __restrict__ out,
@@ -185,16 +185,17 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
             const float* p2 = base + (size_t)min(cq + 2, C - 1) * plane;
             const float* p3 = base + (size_t)min(cq + 3, C - 1) * plane;
             float* dst = tile + (size_t)lane * kCellWords + 4 * (warp & 7);
-            for (int k0 = (warp >> 3); k0 < tile_h; k0 += 2 * kRowsPerBatch) {
+            constexpr int kPar = kWarps / 8;              // row parities staged concurrently
+            for (int k0 = (warp >> 3); k0 < tile_h; k0 += kPar * kRowsPerBatch) {
                 float4 v[kRowsPerBatch];
 #pragma unroll
                 for (int bq = 0; bq < kRowsPerBatch; ++bq) {
-                    const size_t off = (size_t)min(y0 + k0 + 2 * bq, H - 1) * W;
+                    const size_t off = (size_t)min(y0 + k0 + kPar * bq, H - 1) * W;
                     v[bq].x = __ldg(p0 + off); v[bq].y = __ldg(p1 + off); v[bq].z = __ldg(p2 + off); v[bq].w = __ldg(p3 + off);
                 }
 #pragma unroll
                 for (int bq = 0; bq < kRowsPerBatch; ++bq) {
-                    const int row = k0 + 2 * bq;
+                    const int row = k0 + kPar * bq;
                     if (row < tile_h) {
                         const bool ok = x_ok && (y0 + row < H);
                         float4 o;
@@ -370,10 +371,10 @@ int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int 
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1000;
     if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(roi_align_tiled_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_tiled_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_tiled_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_tiled_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(roi_align_tiled_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (228 * 1024 - kTiledCtasPerSM * 1024) / kTiledCtasPerSM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_tiled_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (228 * 1024 - kTiledCtasPerSM * 1024) / kTiledCtasPerSM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_tiled_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (228 * 1024 - kTiledCtasPerSM * 1024) / kTiledCtasPerSM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_tiled_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (228 * 1024 - kTiledCtasPerSM * 1024) / kTiledCtasPerSM);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
         attr_set[dev] = true;
@@ -384,7 +385,7 @@ int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int 
                                                p.tiles_y, p.tiles_x, hdr, ytab, xtab, tile_count, tile_list, p.groups_max, top);
     const int n_cgroups = (C + kCG - 1) / kCG;
     const int n_work = p.tiles_total * n_cgroups;
-    const int grid = n_work < 2 * sm_count[dev] ? n_work : 2 * sm_count[dev];      // persistent: two CTAs per SM
+    const int grid = n_work < kTiledCtasPerSM * sm_count[dev] ? n_work : kTiledCtasPerSM * sm_count[dev];      // persistent CTAs
 #define B200_LAUNCH_TILED(SRV)                                                                                              \
     roi_align_tiled_fwd<SRV><<<grid, kTiledThreads, p.smem_bytes, stream>>>(bottom, ytab, xtab, work_counter, tile_count,   \
         tile_list, R * p.groups_max, top, N, R, C, H, W, PH, PW, p.ny, p.nx, p.core_h, p.core_w, p.tile_h, p.tiles_y, p.tiles_x, \

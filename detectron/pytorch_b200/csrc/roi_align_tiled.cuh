@@ -9,8 +9,13 @@ namespace b200 {
 constexpr int kTX = 32;                 // tile width in cells (one warp-wide row access)
 constexpr int kCG = 32;                 // channels per work item
 constexpr int kCellWords = kCG + 4;     // 36 words = 144 B per cell: the pad makes the transposing 128-bit shared accesses conflict-free
-constexpr int kTiledThreads = 512;      // 16 warps; two CTAs per SM = 32 resident warps (<= 64 registers / thread)
-constexpr int kWarps = kTiledThreads / 32;
+#ifndef B200_FWD_WARPS
+#define B200_FWD_WARPS 16               // warps per forward CTA: 16 (two CTAs per SM) or 8 (four CTAs per SM, smaller tiles)
+#endif
+constexpr int kWarps = B200_FWD_WARPS;
+constexpr int kTiledThreads = 32 * kWarps;      // 32 resident warps per SM either way (<= 64 registers / thread)
+constexpr int kTiledCtasPerSM = 32 / kWarps;
+static_assert(kWarps == 8 || kWarps == 16, "the staging loop deals the channel quads to 8 warps per row parity");
 constexpr int kAxisMax = 32;            // P * sampling_ratio per axis supported by the tiled paths
 constexpr int kStageBins = 8;           // bins staged per warp between compute and global memory
 constexpr int kStageWords = kStageBins + 1;
@@ -58,7 +63,7 @@ static inline bool roi_align_tiled_plan(int N, int R, int H, int W, int C, int P
     if (R <= 0 || R > 65535 || C <= 0 || N <= 0 || H <= 0 || W <= 0) return false;
     if ((long long)R * C * PH * PW >= (1LL << 31) || (long long)N * C * H * W >= (1LL << 31)) return false;
     p->ny = PH * sr; p->nx = PW * sr;
-    const size_t budget = 113 * 1024;               // two work items resident per SM: (228 KB - 2 x 1 KB) / 2
+    const size_t budget = (228 * 1024 - kTiledCtasPerSM * 1024) / kTiledCtasPerSM;      // resident work items share the SM's 228 KB
     int th = 64;
     while (th > 4 && tiled_smem_bytes(th, p->ny, p->nx) > budget) --th;
     if (th <= 4) return false;
