@@ -30,6 +30,12 @@ _SIGNATURES = {
     "b200_roi_align_backward_ws": (ctypes.c_int, [_c_float_p, ctypes.c_float] + [ctypes.c_int] * 8 +
                                    [_c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t, _stream_t]),
     "b200_roi_align_backward": (ctypes.c_int, [_c_float_p, ctypes.c_float] + [ctypes.c_int] * 8 + [_c_float_p, _c_float_p, _stream_t]),
+    # (bottom, scale, N, R, H, W, C, PH, PW, sr, rois, top_rows, top, workspace, workspace_bytes, stream)
+    "b200_roi_align_forward_indexed": (ctypes.c_int, [_c_float_p, ctypes.c_float] + [ctypes.c_int] * 8 +
+                                       [_c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t, _stream_t]),
+    # (top_diff, top_rows, scale, N, R, H, W, C, PH, PW, sr, rois, bottom_diff, workspace, workspace_bytes, stream)
+    "b200_roi_align_backward_indexed": (ctypes.c_int, [_c_float_p, ctypes.c_void_p, ctypes.c_float] + [ctypes.c_int] * 8 +
+                                        [_c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t, _stream_t]),
     # (bottom, scale, N, R, H, W, C, PH, PW, rois, top, stream)
     "b200_roi_align_legacy_forward": (ctypes.c_int, [_c_float_p, ctypes.c_float] + [ctypes.c_int] * 7 + [_c_float_p, _c_float_p, _stream_t]),
     "b200_roi_align_legacy_backward": (ctypes.c_int, [_c_float_p, ctypes.c_float] + [ctypes.c_int] * 7 + [_c_float_p, _c_float_p, _stream_t]),

@@ -6,8 +6,8 @@
 namespace b200 {
 unsigned long long g_launch_count = 0;
 
-int roi_align_forward_generic(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, cudaStream_t);
-int roi_align_backward_generic(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, cudaStream_t);
+int roi_align_forward_generic(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, cudaStream_t);
+int roi_align_backward_generic(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, cudaStream_t);
 int roi_align_legacy_forward(const float*, float, int, int, int, int, int, int, int, const float*, float*, cudaStream_t);
 int roi_align_legacy_backward(const float*, float, int, int, int, int, int, int, int, const float*, float*, cudaStream_t);
 int roi_pool_forward(const float*, float, int, int, int, int, int, int, int, const float*, float*, int*, cudaStream_t);
@@ -18,7 +18,7 @@ size_t nms_workspace_bytes(int);
 size_t roi_align_tiled_workspace_bytes(int, int, int, int, int, int, int);
 void roi_align_tiled_set_timing_buffer(unsigned long long*);
 void nms_set_timing_buffer(unsigned long long*);
-int roi_align_forward_tiled(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, void*, size_t, cudaStream_t);
+int roi_align_forward_tiled(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
 
 // B200_ROI_ALIGN_PATH=generic|tiled|auto (default auto) -- test/benchmark override of the forward dispatch
 static int forward_path_mode() {
@@ -35,10 +35,10 @@ static bool tiled_pays_off(int R, int C, int H, int W, int PH, int PW) {
 }
 int nms(const float*, int, int, float, int*, int*, void*, size_t, cudaStream_t);
 size_t roi_align_bwd_nhwc_workspace_bytes(int, int, int, int);
-int roi_align_backward_nhwc(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, void*, size_t, cudaStream_t);
+int roi_align_backward_nhwc(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
 
 size_t roi_align_bwd_rows_workspace_bytes(int, int, int, int, int, int, int, int);
-int roi_align_backward_rows(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, void*, size_t, cudaStream_t);
+int roi_align_backward_rows(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
 
 // B200_ROI_ALIGN_BWD_PATH=generic|nhwc|rows|auto
 static int backward_path_mode() {
@@ -104,18 +104,27 @@ int b200_roi_align_forward_ws(const float* bottom_data, float spatial_scale, int
                               int width, int channels, int aligned_height, int aligned_width, int sampling_ratio,
                               const float* bottom_rois, float* top_data, void* workspace, size_t workspace_bytes,
                               b200_stream_t stream) {
+    return b200_roi_align_forward_indexed(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
+                                          aligned_height, aligned_width, sampling_ratio, bottom_rois, nullptr, top_data,
+                                          workspace, workspace_bytes, stream);
+}
+
+int b200_roi_align_forward_indexed(const float* bottom_data, float spatial_scale, int batch_size, int num_rois, int height,
+                                   int width, int channels, int aligned_height, int aligned_width, int sampling_ratio,
+                                   const float* bottom_rois, const int* top_rows, float* top_data, void* workspace,
+                                   size_t workspace_bytes, b200_stream_t stream) {
     if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
     if (num_rois > 0 && channels > 0 && (!bottom_data || !bottom_rois || !top_data)) return B200_ROI_EINVAL;
     const int mode = forward_path_mode();
     if (mode != 1 && workspace != nullptr &&
         (mode == 2 || tiled_pays_off(num_rois, channels, height, width, aligned_height, aligned_width))) {
         const int rc = roi_align_forward_tiled(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
-                                               aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data,
+                                               aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data, top_rows,
                                                workspace, workspace_bytes, (cudaStream_t)stream);
         if (rc != 1000) return rc;
     }
     return roi_align_forward_generic(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
-                                     aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data,
+                                     aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data, top_rows,
                                      (cudaStream_t)stream);
 }
 
@@ -139,7 +148,7 @@ int b200_roi_align_forward(const float* bottom_data, float spatial_scale, int ba
         (void)cudaGetLastError();
     }
     return roi_align_forward_generic(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
-                                     aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data,
+                                     aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data, nullptr,
                                      (cudaStream_t)stream);
 }
 
@@ -156,6 +165,15 @@ int b200_roi_align_backward_ws(const float* top_diff, float spatial_scale, int b
                                int width, int channels, int aligned_height, int aligned_width, int sampling_ratio,
                                const float* bottom_rois, float* bottom_diff, void* workspace, size_t workspace_bytes,
                                b200_stream_t stream) {
+    return b200_roi_align_backward_indexed(top_diff, nullptr, spatial_scale, batch_size, num_rois, height, width, channels,
+                                           aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff, workspace,
+                                           workspace_bytes, stream);
+}
+
+int b200_roi_align_backward_indexed(const float* top_diff, const int* top_rows, float spatial_scale, int batch_size,
+                                    int num_rois, int height, int width, int channels, int aligned_height, int aligned_width,
+                                    int sampling_ratio, const float* bottom_rois, float* bottom_diff, void* workspace,
+                                    size_t workspace_bytes, b200_stream_t stream) {
     if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
     if ((size_t)batch_size * channels == 0) return B200_ROI_OK;
     if (!bottom_diff || (num_rois > 0 && (!top_diff || !bottom_rois))) return B200_ROI_EINVAL;
@@ -163,18 +181,18 @@ int b200_roi_align_backward_ws(const float* top_diff, float spatial_scale, int b
     if (path == 3) {
         const int rc = roi_align_backward_rows(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
                                                aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff,
-                                               workspace, workspace_bytes, (cudaStream_t)stream);
+                                               top_rows, workspace, workspace_bytes, (cudaStream_t)stream);
         if (rc != 1000) return rc;
         path = 2;                                   // workspace too small for the gather path: try the NHWC one
     }
     if (path == 2) {
         const int rc = roi_align_backward_nhwc(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
                                                aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff,
-                                               workspace, workspace_bytes, (cudaStream_t)stream);
+                                               top_rows, workspace, workspace_bytes, (cudaStream_t)stream);
         if (rc != 1000) return rc;
     }
     return roi_align_backward_generic(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
-                                      aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff,
+                                      aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff, top_rows,
                                       (cudaStream_t)stream);
 }
 
@@ -198,7 +216,7 @@ int b200_roi_align_backward(const float* top_diff, float spatial_scale, int batc
         (void)cudaGetLastError();
     }
     return roi_align_backward_generic(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
-                                      aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff,
+                                      aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff, nullptr,
                                       (cudaStream_t)stream);
 }
 

@@ -40,7 +40,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 template <int SR>
 __global__ void __launch_bounds__(kBwThreads)
 roi_align_bwd_nhwc_scatter(const float* __restrict__ top_diff, const float* __restrict__ rois, float* __restrict__ scratch,
-                           float scale, int N, int C, int H, int W, int PH, int PW, int c_pad) {
+                           float scale, int N, int C, int H, int W, int PH, int PW, int c_pad, const int* __restrict__ row_map) {
     extern __shared__ __align__(16) float s_dy[];          // [bins][c_pad]   (c_pad = chunk + 4, multiple of 4)
     __shared__ BwAxis s_y[kBwAxisMax], s_x[kBwAxisMax];
     const int r = blockIdx.x;
@@ -61,7 +61,7 @@ roi_align_bwd_nhwc_scatter(const float* __restrict__ top_diff, const float* __re
         if (isy) s_y[s] = e; else s_x[s] = e;
     }
     // stage dY[r, c0:c0+cc, :, :] (contiguous cc*bins floats) transposed to [bin][channel]
-    const float* src = top_diff + ((size_t)r * C + c0) * bins;
+    const float* src = top_diff + ((size_t)(row_map ? row_map[r] : r) * C + c0) * bins;
     for (int idx = tid; idx < cc * bins; idx += kBwThreads) {
         const int c = idx / bins, b = idx - c * bins;
         s_dy[b * c_pad + c] = __ldg(src + idx);
@@ -138,7 +138,7 @@ size_t roi_align_bwd_nhwc_workspace_bytes(int N, int C, int H, int W) {
 
 // returns 1000 when the path does not apply (caller falls back to the generic scalar-atomic kernel)
 int roi_align_backward_nhwc(const float* top_diff, float scale, int N, int R, int H, int W, int C, int PH, int PW, int sr,
-                            const float* rois, float* bottom_diff, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                            const float* rois, float* bottom_diff, const int* row_map, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     if (sr < 1 || sr > 4 || PH * sr > kBwAxisMax || PW * sr > kBwAxisMax) return 1000;
     if (workspace == nullptr || workspace_bytes < roi_align_bwd_nhwc_workspace_bytes(N, C, H, W)) return 1000;
     if (R <= 0 || C <= 0 || N <= 0) return 1000;
@@ -156,7 +156,7 @@ int roi_align_backward_nhwc(const float* top_diff, float scale, int N, int R, in
             err = cudaFuncSetAttribute(roi_align_bwd_nhwc_scatter<SRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (err != cudaSuccess) return (int)err;                                                                     \
         }                                                                                                                \
-        roi_align_bwd_nhwc_scatter<SRV><<<grid, kBwThreads, smem, stream>>>(top_diff, rois, scratch, scale, N, C, H, W, PH, PW, c_pad); \
+        roi_align_bwd_nhwc_scatter<SRV><<<grid, kBwThreads, smem, stream>>>(top_diff, rois, scratch, scale, N, C, H, W, PH, PW, c_pad, row_map); \
     } while (0)
     switch (sr) {
         case 1: B200_LAUNCH_BW(1); break;

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kTableThreads)
 roi_align_bwd_rows_tables(const float* __restrict__ rois, const float* __restrict__ dy, float scale, int N, int R, int C, int H,
                           int W, int PH, int PW, int sr, int table_ctas, BwdRoi* __restrict__ roi_out,
                           AxisEntry* __restrict__ xtab, int* __restrict__ zeroed, uint2* __restrict__ row_list, int row_cap,
-                          uint4* __restrict__ ovf, float* __restrict__ dyt) {
+                          uint4* __restrict__ ovf, float* __restrict__ dyt, const int* __restrict__ row_map) {
     extern __shared__ __align__(16) float s_tr[];
     const int tid = threadIdx.x;
     const int ny = PH * sr, nx = PW * sr;
@@ -129,7 +129,7 @@ roi_align_bwd_rows_tables(const float* __restrict__ rois, const float* __restric
     const int stride = bins | 1;                            // odd: the transposed read below is bank-conflict free
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kTableThreads / 32;
-    const float* src = dy + ((size_t)r * C + c0) * bins;
+    const float* src = dy + ((size_t)(row_map ? row_map[r] : r) * C + c0) * bins;
     const float inv = 1.f / (float)(sr * sr);               // count in {1, 4}: multiplying by the reciprocal is the exact division
     if (stride == bins) {                                   // odd bin count: the block is copied linearly
         for (int k = tid; k < cc * bins; k += kTableThreads) s_tr[k] = __fmul_rn(src[k], inv);
@@ -402,7 +402,7 @@ static int launch_rows(const RowsPlan& p, unsigned char* ws, float* dx, int N, i
 
 // returns 1000 when the path does not apply (caller falls back to another backward path)
 int roi_align_backward_rows(const float* top_diff, float scale, int N, int R, int H, int W, int C, int PH, int PW, int sr,
-                            const float* rois, float* bottom_diff, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                            const float* rois, float* bottom_diff, const int* row_map, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     RowsPlan p;
     if (!rows_plan(N, R, C, H, W, PH, PW, sr, &p)) return 1000;
     if (workspace == nullptr || workspace_bytes < p.ws_bytes) return 1000;
@@ -421,7 +421,7 @@ int roi_align_backward_rows(const float* top_diff, float scale, int N, int R, in
         rois, top_diff, scale, N, R, C, H, W, PH, PW, sr, table_ctas, reinterpret_cast<BwdRoi*>(ws + p.roi_off),
         reinterpret_cast<AxisEntry*>(ws + p.xtab_off), reinterpret_cast<int*>(ws + p.zero_off),
         reinterpret_cast<uint2*>(ws + p.row_list_off), p.row_cap, reinterpret_cast<uint4*>(ws + p.ovf_off),
-        reinterpret_cast<float*>(ws + p.dyt_off));
+        reinterpret_cast<float*>(ws + p.dyt_off), row_map);
     const char* e_cpl = getenv("B200_ROI_ALIGN_BWD_CPL");       // channels per lane of the main kernel: 2 | 4 (A/B tests)
     const bool want4 = !(e_cpl && e_cpl[0] == '2');
     int rc;

@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(kGenThreads)
 roi_align_generic_kernel(const float* __restrict__ in,      // fwd: bottom_data   bwd: top_diff
                          const float* __restrict__ rois,
                          float* __restrict__ out,           // fwd: top_data      bwd: bottom_diff (pre-zeroed)
-                         float scale, int N, int C, int H, int W, int PH, int PW, int sr, int c_per_cta) {
+                         float scale, int N, int C, int H, int W, int PH, int PW, int sr, int c_per_cta,
+                         const int* __restrict__ row_map) {                 // RoI -> row of top_data / top_diff (null: identity)
     __shared__ TabEntry ytab[kTabMax];
     __shared__ TabEntry xtab[kTabMax];
 
@@ -62,7 +63,7 @@ roi_align_generic_kernel(const float* __restrict__ in,      // fwd: bottom_data 
         const int c = c0 + idx / bins;
         const int bin = idx % bins;
         const int ph = bin / PW, pw = bin % PW;
-        const size_t oidx = ((size_t)n * C + c) * bins + bin;       // (n, c, ph, pw)
+        const size_t oidx = ((size_t)(row_map ? row_map[n] : n) * C + c) * bins + bin;       // (row, c, ph, pw)
         if (!batch_ok) {                                            // reference would read out of bounds
             if (!BACKWARD) out[oidx] = 0.f;
             continue;
@@ -108,22 +109,22 @@ static int pick_c_per_cta(int num_rois, int C, int bins) {
 }
 
 int roi_align_forward_generic(const float* bottom, float scale, int N, int R, int H, int W, int C, int PH, int PW,
-                              int sr, const float* rois, float* top, cudaStream_t stream) {
+                              int sr, const float* rois, float* top, const int* row_map, cudaStream_t stream) {
     if (R == 0 || C == 0) return B200_ROI_OK;
     const int cpc = pick_c_per_cta(R, C, PH * PW);
     dim3 grid(R, (C + cpc - 1) / cpc);
-    roi_align_generic_kernel<false><<<grid, kGenThreads, 0, stream>>>(bottom, rois, top, scale, N, C, H, W, PH, PW, sr, cpc);
+    roi_align_generic_kernel<false><<<grid, kGenThreads, 0, stream>>>(bottom, rois, top, scale, N, C, H, W, PH, PW, sr, cpc, row_map);
     return finish_launch();
 }
 
 int roi_align_backward_generic(const float* top_diff, float scale, int N, int R, int H, int W, int C, int PH, int PW,
-                               int sr, const float* rois, float* bottom_diff, cudaStream_t stream) {
+                               int sr, const float* rois, float* bottom_diff, const int* row_map, cudaStream_t stream) {
     cudaError_t err = cudaMemsetAsync(bottom_diff, 0, sizeof(float) * (size_t)N * C * H * W, stream);
     if (err != cudaSuccess) return (int)err;
     if (R == 0 || C == 0) return B200_ROI_OK;
     const int cpc = pick_c_per_cta(R, C, PH * PW);
     dim3 grid(R, (C + cpc - 1) / cpc);
-    roi_align_generic_kernel<true><<<grid, kGenThreads, 0, stream>>>(top_diff, rois, bottom_diff, scale, N, C, H, W, PH, PW, sr, cpc);
+    roi_align_generic_kernel<true><<<grid, kGenThreads, 0, stream>>>(top_diff, rois, bottom_diff, scale, N, C, H, W, PH, PW, sr, cpc, row_map);
     return finish_launch();   // (the cudaMemsetAsync is not one of our kernels)
 }
 

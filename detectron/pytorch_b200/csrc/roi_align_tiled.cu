@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(128)
 roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int R, int C, int H, int W, int PH, int PW, int sr,
                      int ny, int nx, int core_h, int core_w, int tiles_y, int tiles_x,
                      RoiHeader* __restrict__ hdr, AxisEntry* __restrict__ ytab, AxisEntry* __restrict__ xtab,
-                     int* __restrict__ tile_count, unsigned* __restrict__ tile_list, int groups_max, float* __restrict__ out) {
+                     int* __restrict__ tile_count, unsigned* __restrict__ tile_list, int groups_max, float* __restrict__ out,
+                     const int* __restrict__ row_map) {
     __shared__ int s_ty[kAxisMax], s_tx[kAxisMax];
     __shared__ int s_nbin_y[kAxisMax], s_nbin_x[kAxisMax];     // bin rows / cols this RoI has in tile row ty0+k / col tx0+k
     __shared__ unsigned short s_split[kAxisMax * kAxisMax];
@@ -110,7 +111,7 @@ roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int R, 
     }
     __syncthreads();
     const int nsplit = s_nsplit;
-    float* out_r = out + (size_t)r * C * bins;
+    float* out_r = out + (size_t)(row_map ? row_map[r] : r) * C * bins;
     for (int idx = t; idx < C * nsplit; idx += blockDim.x) {
         const int c = idx / nsplit, k = idx - c * nsplit;
         out_r[(size_t)c * bins + s_split[k]] = 0.f;
@@ -126,7 +127,8 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
                     int* __restrict__ work_counter, const int* __restrict__ tile_count,
                     const unsigned* __restrict__ tile_list, int list_stride, float* __restrict__ out,
                     int N, int R, int C, int H, int W, int PH, int PW, int ny, int nx,
-                    int core_h, int core_w, int tile_h, int tiles_y, int tiles_x, int n_cgroups, int n_work) {
+                    int core_h, int core_w, int tile_h, int tiles_y, int tiles_x, int n_cgroups, int n_work,
+                    const int* __restrict__ row_map) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);
     AxisEntry* wtab_all = reinterpret_cast<AxisEntry*>(smem_raw + (size_t)kTX * tile_h * kCellWords * 4);
@@ -261,7 +263,7 @@ roi_align_tiled_fwd(const float* __restrict__ bottom, const AxisEntry* __restric
             const int pw0 = (__ffs(mx) - 1) / SR, pw1 = (31 - __clz(mx)) / SR + 1;
             const int npw = pw1 - pw0, nb = (ph1 - ph0) * npw;
             const unsigned div_m = 65536u / (unsigned)npw + 1u;          // b / npw == (b * div_m) >> 16 for b < 1024
-            float* out_r = out + (size_t)r_cur * C * bins + (size_t)c0 * bins;
+            float* out_r = out + (size_t)(row_map ? row_map[r_cur] : r_cur) * C * bins + (size_t)c0 * bins;
             const float* tbase = tile + 4 * i;
             ++n_items;
             if (kb < nb) {                                   // always true for entries the prepass wrote
@@ -353,7 +355,7 @@ size_t roi_align_tiled_workspace_bytes(int N, int R, int H, int W, int PH, int P
 
 // returns B200_ROI_OK when the fast path ran; 1000 when it does not apply (caller falls back)
 int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int H, int W, int C, int PH, int PW, int sr,
-                            const float* rois, float* top, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                            const float* rois, float* top, const int* row_map, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     TiledPlan p;
     if (!roi_align_tiled_plan(N, R, H, W, C, PH, PW, sr, false, &p)) return 1000;
     if (workspace == nullptr || workspace_bytes < p.ws_bytes) return 1000;
@@ -382,14 +384,14 @@ int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int 
     cudaError_t err = cudaMemsetAsync(zero, 0, p.zero_bytes, stream);
     if (err != cudaSuccess) return (int)err;
     roi_align_tiled_prep<<<R, 128, 0, stream>>>(rois, scale, N, R, C, H, W, PH, PW, sr, p.ny, p.nx, p.core_h, p.core_w,
-                                               p.tiles_y, p.tiles_x, hdr, ytab, xtab, tile_count, tile_list, p.groups_max, top);
+                                               p.tiles_y, p.tiles_x, hdr, ytab, xtab, tile_count, tile_list, p.groups_max, top, row_map);
     const int n_cgroups = (C + kCG - 1) / kCG;
     const int n_work = p.tiles_total * n_cgroups;
     const int grid = n_work < kTiledCtasPerSM * sm_count[dev] ? n_work : kTiledCtasPerSM * sm_count[dev];      // persistent CTAs
 #define B200_LAUNCH_TILED(SRV)                                                                                              \
     roi_align_tiled_fwd<SRV><<<grid, kTiledThreads, p.smem_bytes, stream>>>(bottom, ytab, xtab, work_counter, tile_count,   \
         tile_list, R * p.groups_max, top, N, R, C, H, W, PH, PW, p.ny, p.nx, p.core_h, p.core_w, p.tile_h, p.tiles_y, p.tiles_x, \
-        n_cgroups, n_work)
+        n_cgroups, n_work, row_map)
     switch (sr) {
         case 1: B200_LAUNCH_TILED(1); break;
         case 2: B200_LAUNCH_TILED(2); break;

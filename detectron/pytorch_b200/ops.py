@@ -85,6 +85,96 @@ class _RoIAlign(Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# RoIAlign over an FPN pyramid, results written in restored order
+# ------------------------------------------------------------------------------------------------
+class _RoIAlignFPN(Function):
+    """One autograd node for the reference's per-level loop + torch.cat + `xform_shuffled[restore_bl]`
+    (lib/modeling/model_builder.py:264-303): level l's RoI r is row offset_l + r of the concatenated tensor, which the
+    gather moves to every output row j with restore[j] == offset_l + r.  `restore` is a permutation, so each RoI has
+    exactly one destination row, and the per-level kernels write it directly (b200_roi_align_forward_indexed); the
+    backward reads the gradient rows of the shared tensor in place (b200_roi_align_backward_indexed)."""
+
+    @staticmethod
+    def forward(ctx, restore, aligned_height, aligned_width, sampling_ratio, scales, num_levels, *tensors):
+        feats, rois = tensors[:num_levels], tensors[num_levels:]
+        P = (int(aligned_height), int(aligned_width)); sr = int(sampling_ratio)
+        dev = feats[0].device
+        counts = [int(r.size(0)) for r in rois]
+        total = sum(counts)
+        if restore.numel() != total:
+            raise ValueError("restore index has %d entries for %d RoIs" % (restore.numel(), total))
+        C = feats[0].size(1)
+        inv = torch.empty((total,), dtype=torch.int32, device=dev)
+        inv[restore.to(device=dev, dtype=torch.long)] = torch.arange(total, dtype=torch.int32, device=dev)
+        out = torch.empty((total, C, P[0], P[1]), dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        off = 0
+        kept = []
+        with torch.cuda.device(dev):
+            for f, r, sc, n_l in zip(feats, rois, scales, counts):
+                if n_l:
+                    _need_cuda_f32(f, "features"); _need_cuda_f32(r, "rois"); _rois_ok(r)
+                    if f.size(1) != C:
+                        raise ValueError("every pyramid level must have the same number of channels")
+                    f = f.contiguous(); r = r.contiguous()
+                    N, _, H, W = f.shape
+                    ws_bytes = int(lib.b200_roi_align_workspace_bytes(N, n_l, H, W, P[0], P[1], sr))
+                    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+                    rows = inv[off:off + n_l]
+                    _lib.check(lib.b200_roi_align_forward_indexed(f.data_ptr(), float(sc), N, n_l, H, W, C, P[0], P[1], sr,
+                                                                  r.data_ptr(), rows.data_ptr(), out.data_ptr(),
+                                                                  ws.data_ptr() if ws is not None else None, ws_bytes, _stream()),
+                               "b200_roi_align_forward_indexed")
+                    kept.append(r)
+                else:
+                    kept.append(r)
+                off += n_l
+        ctx.meta = (P, sr, [float(sc) for sc in scales], counts, [tuple(f.shape) for f in feats], num_levels)
+        ctx.save_for_backward(inv, *kept)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        P, sr, scales, counts, shapes, num_levels = ctx.meta
+        inv, rois = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+        assert grad_output.is_cuda
+        grad_output = grad_output.contiguous()
+        dev = grad_output.device
+        lib = _lib.load()
+        grads = []
+        off = 0
+        with torch.cuda.device(dev):
+            for r, sc, n_l, shape in zip(rois, scales, counts, shapes):
+                N, C, H, W = shape
+                if n_l == 0:
+                    grads.append(torch.zeros(shape, dtype=torch.float32, device=dev))
+                    continue
+                g = torch.empty(shape, dtype=torch.float32, device=dev)
+                ws_bytes = int(lib.b200_roi_align_backward_workspace_bytes(N, n_l, C, H, W, P[0], P[1], sr))
+                ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+                rows = inv[off:off + n_l]
+                _lib.check(lib.b200_roi_align_backward_indexed(grad_output.data_ptr(), rows.data_ptr(), sc, N, n_l, H, W, C,
+                                                               P[0], P[1], sr, r.data_ptr(), g.data_ptr(),
+                                                               ws.data_ptr() if ws is not None else None, ws_bytes, _stream()),
+                           "b200_roi_align_backward_indexed")
+                grads.append(g)
+                off += n_l
+        return (None, None, None, None, None, None) + tuple(grads) + (None,) * num_levels
+
+
+def roi_align_fpn(features, rois, restore, aligned_height, aligned_width, spatial_scales, sampling_ratio):
+    """features: list of (N, C, H_l, W_l) CUDA tensors; rois: list of (R_l, 5) CUDA tensors (same order); restore: the
+    reference's `*_idx_restore_int32` (any integer tensor / array of length sum R_l); spatial_scales: one per level.
+    Returns (sum R_l, C, PH, PW) in restored order == torch.cat([RoIAlign_l(...)])[restore]."""
+    if len(features) != len(rois) or len(features) != len(spatial_scales):
+        raise ValueError("features, rois and spatial_scales must have one entry per pyramid level")
+    restore = torch.as_tensor(restore)
+    return _RoIAlignFPN.apply(restore, aligned_height, aligned_width, sampling_ratio, tuple(spatial_scales), len(features),
+                              *features, *rois)
+
+
+# ------------------------------------------------------------------------------------------------
 # RoIAlign (legacy, lattice-corner samples)
 # ------------------------------------------------------------------------------------------------
 def roi_align_legacy_forward(features, rois, aligned_height, aligned_width, spatial_scale):

@@ -93,6 +93,21 @@ B200_API int b200_roi_align_backward_ws(const float* top_diff, float spatial_sca
                                int sampling_ratio, const float* bottom_rois, float* bottom_diff,
                                void* workspace, size_t workspace_bytes, b200_stream_t stream);
 
+/* Indexed variants (the FPN per-level loop + torch.cat + restore gather of
+ * Generalized_RCNN.roi_feature_transform, lib/modeling/model_builder.py:264-303): RoI r reads / writes row
+ * top_rows[r] of top_data / top_diff instead of row r, so the pooled features of every pyramid level land directly
+ * in the restored order of one shared output tensor (and the backward picks its gradient rows out of the shared
+ * tensor) -- no concatenated intermediate, no gather pass.  top_rows == NULL is the identity (= the _ws variants).
+ * The forward writes exactly the rows named by top_rows; the caller sizes top_data. */
+B200_API int b200_roi_align_forward_indexed(const float* bottom_data, float spatial_scale, int batch_size, int num_rois,
+                                   int height, int width, int channels, int aligned_height, int aligned_width,
+                                   int sampling_ratio, const float* bottom_rois, const int* top_rows, float* top_data,
+                                   void* workspace, size_t workspace_bytes, b200_stream_t stream);
+B200_API int b200_roi_align_backward_indexed(const float* top_diff, const int* top_rows, float spatial_scale, int batch_size,
+                                    int num_rois, int height, int width, int channels, int aligned_height,
+                                    int aligned_width, int sampling_ratio, const float* bottom_rois, float* bottom_diff,
+                                    void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
 /* ---- RoIAlign, legacy variant (one bilinear sample per lattice corner, fp64 interpolation) -----
  * replaces ROIAlignForwardLaucher / ROIAlignBackwardLaucher,
  *   lib/model/roi_align/src/roi_align_kernel.cu:73-91, 145-162 (header roi_align_kernel.h). */

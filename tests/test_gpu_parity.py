@@ -184,6 +184,43 @@ def test_roi_align_backward_rows_path_row_overflow(monkeypatch):
     np.testing.assert_allclose(dx, O.roi_align_backward(dy, r, shape, P, P, s, sr, acc64=True), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("bwd", ["auto", "nhwc", "generic"])
+def test_roi_align_fpn_equals_per_level_loop_cat_and_restore(bwd, monkeypatch):
+    """RoIAlignFPNFunction == the reference flow (per-level RoIAlign, torch.cat, gather by the restore
+    index; model_builder.py:264-303), forward and backward, with an empty level, fast-path and generic-path levels."""
+    from detectron.pytorch_b200.modeling.roi_xfrom.roi_align.functions.roi_align_fpn import RoIAlignFPNFunction
+    if bwd != "auto":
+        monkeypatch.setenv("B200_ROI_ALIGN_BWD_PATH", bwd)
+    rng = np.random.RandomState(11)
+    shapes = [(2, 64, 48, 64), (2, 64, 24, 32), (2, 64, 12, 16), (2, 64, 6, 8)]
+    scales = [1.0 / 4, 1.0 / 8, 1.0 / 16, 1.0 / 32]
+    counts = [150, 40, 0, 9]
+    P, sr = 7, 2
+    feats = [S.make_features(sh, seed=20 + i) for i, sh in enumerate(shapes)]
+    rois = [S.make_rois(c, sh, sc, seed=30 + i).astype(np.float32) if c else np.zeros((0, 5), np.float32)
+            for i, (c, sh, sc) in enumerate(zip(counts, shapes, scales))]
+    total = sum(counts)
+    restore = rng.permutation(total).astype(np.int32)
+    dy = rng.standard_normal((total, 64, P, P)).astype(np.float32)
+
+    F1 = [dev(f).requires_grad_(True) for f in feats]
+    outs = [RoIAlignFunction(P, P, sc, sr)(f, dev(r)) for f, r, sc in zip(F1, rois, scales) if len(r)]
+    ref = torch.cat(outs, dim=0)[torch.from_numpy(restore.astype(np.int64)).cuda()]
+    ref.backward(dev(dy))
+
+    F2 = [dev(f).requires_grad_(True) for f in feats]
+    out = RoIAlignFPNFunction(P, P, scales, sr)(F2, [dev(r) for r in rois], restore)
+    out.backward(dev(dy))
+
+    torch.testing.assert_close(out, ref, rtol=1e-6, atol=1e-6)
+    assert float((out == ref).float().mean()) > 0.9
+    for a, b, c in zip(F2, F1, counts):
+        if c:
+            np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.cpu().numpy(), **GRAD_TOL)
+        else:
+            assert a.grad is not None and torch.count_nonzero(a.grad) == 0
+
+
 def test_roi_align_forward_linearity_and_determinism(fwd_path):
     cfg = S.CFG2
     P, s, sr = cfg["pooled"], cfg["scale"], cfg["sampling_ratio"]
