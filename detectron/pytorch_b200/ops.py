@@ -104,8 +104,13 @@ class _RoIAlignFPN(Function):
         if restore.numel() != total:
             raise ValueError("restore index has %d entries for %d RoIs" % (restore.numel(), total))
         C = feats[0].size(1)
-        inv = torch.empty((total,), dtype=torch.int32, device=dev)
-        inv[restore.to(device=dev, dtype=torch.long)] = torch.arange(total, dtype=torch.int32, device=dev)
+        if restore.is_cuda:
+            inv = torch.empty((total,), dtype=torch.int32, device=dev)
+            inv[restore.to(dtype=torch.long)] = torch.arange(total, dtype=torch.int32, device=dev)
+        else:                                       # the reference's restore index is a host array: invert it there
+            inv_h = torch.empty((total,), dtype=torch.int32)
+            inv_h[restore.to(dtype=torch.long)] = torch.arange(total, dtype=torch.int32)
+            inv = inv_h.to(dev, non_blocking=False)
         out = torch.empty((total, C, P[0], P[1]), dtype=torch.float32, device=dev)
         lib = _lib.load()
         off = 0
