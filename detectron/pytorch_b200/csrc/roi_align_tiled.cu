@@ -27,6 +27,7 @@
 //
 // Semantics: lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu (reference) :16-63, :65-121.
 #include "roi_align_tiled.cuh"
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -47,7 +48,7 @@ roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int R, 
                      int ny, int nx, int core_h, int core_w, int tiles_y, int tiles_x,
                      RoiHeader* __restrict__ hdr, AxisEntry* __restrict__ ytab, AxisEntry* __restrict__ xtab,
                      int* __restrict__ tile_count, unsigned* __restrict__ tile_list, int groups_max, float* __restrict__ out,
-                     const int* __restrict__ row_map) {
+                     const int* __restrict__ row_map, int zero_split) {
     __shared__ int s_ty[kAxisMax], s_tx[kAxisMax];
     __shared__ int s_nbin_y[kAxisMax], s_nbin_x[kAxisMax];     // bin rows / cols this RoI has in tile row ty0+k / col tx0+k
     __shared__ unsigned short s_split[kAxisMax * kAxisMax];
@@ -102,6 +103,7 @@ roi_align_tiled_prep(const float* __restrict__ rois, float scale, int N, int R, 
         }
     }
     // bins the main kernel accumulates into (their samples straddle tiles) or never visits (bad batch index)
+    if (!zero_split) return;                         // the host zero-filled the whole output instead
     const int bins = PH * PW;
     for (int bin = t; bin < bins; bin += blockDim.x) {
         const int ph = bin / PW, pw = bin % PW;
@@ -383,8 +385,16 @@ int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int 
     }
     cudaError_t err = cudaMemsetAsync(zero, 0, p.zero_bytes, stream);
     if (err != cudaSuccess) return (int)err;
+    // B200_FWD_ZERO=memset (A/B switch): zero the whole output with one memset instead of the prepass's per-bin stores
+    const char* e_zero = getenv("B200_FWD_ZERO");
+    const bool whole = e_zero && e_zero[0] == 'm' && row_map == nullptr;
+    if (whole) {
+        err = cudaMemsetAsync(top, 0, sizeof(float) * (size_t)R * C * PH * PW, stream);
+        if (err != cudaSuccess) return (int)err;
+    }
     roi_align_tiled_prep<<<R, 128, 0, stream>>>(rois, scale, N, R, C, H, W, PH, PW, sr, p.ny, p.nx, p.core_h, p.core_w,
-                                               p.tiles_y, p.tiles_x, hdr, ytab, xtab, tile_count, tile_list, p.groups_max, top, row_map);
+                                               p.tiles_y, p.tiles_x, hdr, ytab, xtab, tile_count, tile_list, p.groups_max, top, row_map,
+                                               whole ? 0 : 1);
     const int n_cgroups = (C + kCG - 1) / kCG;
     const int n_work = p.tiles_total * n_cgroups;
     const int grid = n_work < kTiledCtasPerSM * sm_count[dev] ? n_work : kTiledCtasPerSM * sm_count[dev];      // persistent CTAs
