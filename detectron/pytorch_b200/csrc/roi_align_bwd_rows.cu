@@ -239,7 +239,7 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
         const int cb = rem / tiles_x, tx = rem - cb * tiles_x;
         const int n = row / H, y = row - n * H;
         const int x0 = tx * kRowCells;
-        const float* dyt_lane = dyt + cb * CHB + lane * CPL;
+        const unsigned lane_ch = (unsigned)(cb * CHB + lane * CPL);     // all dYt offsets fit 32 bits (plan: R*C*PH*PW < 2^31)
 
         {   // zero the 32 cells of the accumulator: 32 * 33 lane-vectors
             u64x z[HV];
@@ -268,10 +268,10 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
                              "r"(__float_as_int(w_lo)), "r"(__float_as_int(w_hi)) : "memory");
             const unsigned bm = __ballot_sync(0xffffffffu, any);
             const int r = (int)(key & 0xffffu), i = (int)((key >> 16) & 0x7fffu);
-            const float* gsrc = dyt_lane + (size_t)((r * PH + i / SR) * PW) * C;
+            const unsigned g_off = (unsigned)((r * PH + i / SR) * PW) * (unsigned)C + lane_ch;
 #pragma unroll
             for (int pw = 0; pw < PW; ++pw)
-                if ((bm >> (pw * SR)) & ((1u << SR) - 1u)) Acc<CPL>::ldg(gsrc + (size_t)pw * C, G[pw]);
+                if ((bm >> (pw * SR)) & ((1u << SR) - 1u)) Acc<CPL>::ldg(dyt + (g_off + (unsigned)pw * (unsigned)C), G[pw]);
             return bm;
         };
         // B: apply the taps of one unit (records in stage buffer `slot`, gradients in G)
