@@ -321,60 +321,41 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
         long long t_spin = 0, t_fold = 0, folds = 0;
         for (int b = g; b < col_blocks; b += kFoldGroups) {
             const long long t0 = timing ? clock64() : 0;
-            const int ncols = col_blocks - (b + REACH);
-            constexpr int part_shift = 2;                                 // 4 row parts of 16 rows: <= 12 units for <= 96 columns
-            constexpr int rows_per = kNmsTile >> part_shift;
-            const int nchunks = ncols > 0 ? (ncols + 31) >> 5 : 0;
-            const int units = nchunks << part_shift;
-            // The warp's first unit is loaded SPECULATIVELY -- all 16 rows, kept or not -- before the block is resolved:
-            // the ~1300-cycle latency of mask words another kernel wrote overlaps the wait for the resolver, and the
-            // fold proper is a register OR.  (Rows past n are never kept and are not read.)
-            u64 v[16];
-            int j0 = 0; bool j0ok = false; int part0 = 0;
-            if (wi < units) {
-                const int cch = wi >> part_shift; part0 = wi & ((1 << part_shift) - 1);
-                j0 = b + REACH + cch * 32 + lane; j0ok = j0 < col_blocks;
-                const int row0 = b * kNmsTile + part0 * rows_per;
-                const u64* p = mask + (size_t)row0 * col_blocks + (j0ok ? j0 : 0);
-#pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                    v[t] = (j0ok && row0 + t < n) ? B200_FOLD_LD(p) : 0ULL;
-                    p += col_blocks;
-                }
-            }
             mbar_wait(&res_bar[b], 0);
             const long long t1 = timing ? clock64() : 0;
             const u64 kept = *reinterpret_cast<volatile u64*>(&kept_hist[b]);
-            if (wi < units && j0ok) {
-                const unsigned kb = (unsigned)(kept >> (part0 * rows_per)) & ((1u << rows_per) - 1u);
-                u64 acc = 0;
-#pragma unroll
-                for (int t = 0; t < 16; ++t) acc |= ((kb >> t) & 1u) ? v[t] : 0ULL;
-                const unsigned lo = (unsigned)acc, hi = (unsigned)(acc >> 32);
-                if (lo) atomicOr(&remv32[2 * j0], lo);
-                if (hi) atomicOr(&remv32[2 * j0 + 1], hi);
-            }
-            for (int u = wi + kFoldWarps; u < units; u += kFoldWarps) {  // more than 96 columns left: the rest after the fact
-                const int cch = u >> part_shift, part = u & ((1 << part_shift) - 1);
-                const unsigned kb = (unsigned)(kept >> (part * rows_per)) & ((1u << rows_per) - 1u);
-                const int j = b + REACH + cch * 32 + lane;
-                if (j < col_blocks) {
-                    const u64* p = mask + (size_t)(b * kNmsTile + part * rows_per) * col_blocks + j;
+            const int ncols = col_blocks - (b + REACH);
+            if (ncols > 0) {
+                const int nchunks = (ncols + 31) >> 5;
+                constexpr int part_shift = 2;                             // 4 row parts of 16 rows: <= 12 units for <= 96 columns
+                const int rows_per = kNmsTile >> part_shift;
+                const int units = nchunks << part_shift;
+                for (int u = wi; u < units; u += kFoldWarps) {
+                    const int cch = u >> part_shift, part = u & ((1 << part_shift) - 1);
+                    unsigned kb = (unsigned)(kept >> (part * rows_per));
+                    if (rows_per < 32) kb &= (1u << rows_per) - 1u;
+                    const int j = b + REACH + cch * 32 + lane;
+                    const bool jok = j < col_blocks;
+                    const u64* base = mask + (size_t)(b * kNmsTile + part * rows_per) * col_blocks + (jok ? j : 0);
                     u64 acc = 0;
-#pragma unroll 1
-                    for (int t0 = 0; t0 < 16; t0 += 8) {
-                        u64 w[8];
+                    if (jok) {
+                        // all 16 rows of the part in flight at once; the address walks down the rows so that it
+                        // lives in one register pair instead of sixteen
+                        u64 v[16];
+                        const u64* p = base;
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            w[t] = ((kb >> (t0 + t)) & 1u) ? B200_FOLD_LD(p) : 0ULL;
+                        for (int t = 0; t < 16; ++t) {
+                            v[t] = ((kb >> t) & 1u) ? B200_FOLD_LD(p) : 0ULL;
                             p += col_blocks;
                         }
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) acc |= w[t];
+                        for (int t = 0; t < 16; ++t) acc |= v[t];
                     }
-                    const unsigned lo = (unsigned)acc, hi = (unsigned)(acc >> 32);
-                    if (lo) atomicOr(&remv32[2 * j], lo);
-                    if (hi) atomicOr(&remv32[2 * j + 1], hi);
+                    if (jok) {
+                        const unsigned lo = (unsigned)acc, hi = (unsigned)(acc >> 32);
+                        if (lo) atomicOr(&remv32[2 * j], lo);
+                        if (hi) atomicOr(&remv32[2 * j + 1], hi);
+                    }
                 }
             }
             __syncwarp();
