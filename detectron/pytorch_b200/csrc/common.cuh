@@ -10,7 +10,7 @@ namespace b200 {
 extern unsigned long long g_launch_count;   // defined in api.cu
 
 inline int finish_launch(int n_launches = 1) {
-    g_launch_count += (unsigned long long)n_launches;
+    __atomic_fetch_add(&g_launch_count, (unsigned long long)n_launches, __ATOMIC_RELAXED);   // callers may be one thread per GPU
     cudaError_t err = cudaGetLastError();
     return (err == cudaSuccess) ? B200_ROI_OK : (int)err;
 }

@@ -24,17 +24,6 @@ constexpr int kFoldGroups = 2, kFoldWarps = 12;     // resolver scan: 2 blocks f
 
 typedef unsigned long long u64;
 
-// acq_rel fence at CTA scope (MEMBAR.ALL.CTA).  __threadfence_block() is membar.cta = fence.sc.cta, the much slower
-// sequentially-consistent flavour, which the flag handshakes below do not need.
-__device__ __forceinline__ void cta_fence() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
-__device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
-
-#ifdef B200_NMS_FOLD_CG
-#define B200_FOLD_LD(p) __ldcg(p)
-#else
-#define B200_FOLD_LD(p) (*(p))
-#endif
-
 // mbarrier handshakes (shared::cta): waiting warps are suspended by the hardware instead of polling shared memory
 // (24 polling warps saturate the LSU queue the resolver's own shared loads go through).  arrive = release,
 // try_wait = acquire at CTA scope, so no separate fences are needed around the flag.
@@ -345,7 +334,7 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
                         const u64* p = base;
 #pragma unroll
                         for (int t = 0; t < 16; ++t) {
-                            v[t] = ((kb >> t) & 1u) ? B200_FOLD_LD(p) : 0ULL;
+                            v[t] = ((kb >> t) & 1u) ? *p : 0ULL;
                             p += col_blocks;
                         }
 #pragma unroll

@@ -351,7 +351,7 @@ void roi_align_tiled_set_timing_buffer(unsigned long long* buf) {
 
 size_t roi_align_tiled_workspace_bytes(int N, int R, int H, int W, int PH, int PW, int sr) {
     TiledPlan p;
-    if (!roi_align_tiled_plan(N, R, H, W, 1, PH, PW, sr, false, &p)) return 0;
+    if (!roi_align_tiled_plan(N, R, H, W, 1, PH, PW, sr, &p)) return 0;
     return p.ws_bytes;
 }
 
@@ -359,7 +359,7 @@ size_t roi_align_tiled_workspace_bytes(int N, int R, int H, int W, int PH, int P
 int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int H, int W, int C, int PH, int PW, int sr,
                             const float* rois, float* top, const int* row_map, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     TiledPlan p;
-    if (!roi_align_tiled_plan(N, R, H, W, C, PH, PW, sr, false, &p)) return 1000;
+    if (!roi_align_tiled_plan(N, R, H, W, C, PH, PW, sr, &p)) return 1000;
     if (workspace == nullptr || workspace_bytes < p.ws_bytes) return 1000;
     unsigned char* ws = (unsigned char*)workspace;
     RoiHeader* hdr = (RoiHeader*)(ws + p.hdr_off);

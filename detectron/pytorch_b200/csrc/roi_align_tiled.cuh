@@ -1,6 +1,6 @@
 // roi_align_tiled.cuh -- shared definitions of the feature-map-stationary ("tiled") RoIAlign kernels:
-// tile geometry, the per-RoI sample tables and the per-tile work lists that the prepass kernels
-// build once per call (channel independent) and the main kernels consume.
+// tile geometry, the per-RoI sample tables and the per-tile work lists that the prepass kernel
+// builds once per call (channel independent) and the main kernels consume.
 #pragma once
 #include "common.cuh"
 
@@ -19,7 +19,6 @@ static_assert(kWarps == 8 || kWarps == 16, "the staging loop deals the channel q
 constexpr int kAxisMax = 32;            // P * sampling_ratio per axis supported by the tiled paths
 constexpr int kStageBins = 8;           // bins staged per warp between compute and global memory
 constexpr int kStageWords = kStageBins + 1;
-constexpr int kRowCap = 64;             // backward: units cached per (tile, row) list; the rest goes to the overflow list
 
 struct __align__(16) AxisEntry {        // one bilinear sample along one axis (channel independent)
     int   low;                          // low cell (clamped into the map even when invalid)
@@ -41,11 +40,9 @@ struct TiledPlan {
     size_t smem_bytes;
     // workspace sections (byte offsets)
     size_t hdr_off, ytab_off, xtab_off;
-    size_t zero_off, zero_bytes;        // block that must be zero at kernel start: [work counter][overflow count][tile counts][row counts]
+    size_t zero_off, zero_bytes;        // block that must be zero at kernel start: [work counter][3 spare][tile counts]
     int groups_max;                     // 8-bin groups one RoI can contribute to one tile = ceil(PH*PW / 8)
     size_t tile_list_off;               // uint32 [tiles_total][R * groups_max]: RoI index | (8-bin group << 16)
-    size_t row_list_off;                // backward: uint32 [tiles_total * core_h][kRowCap]
-    size_t overflow_off;                // backward: uint2  [R * ny * tiles_x]
     size_t ws_bytes;
 };
 
@@ -57,8 +54,8 @@ __host__ __device__ inline size_t tiled_smem_bytes(int tile_h, int ny, int nx) {
            (size_t)kWarps * kCG * kStageWords * 4 + 64;
 }
 
-// Tile geometry + workspace layout.  `backward` adds the per-row unit lists.
-static inline bool roi_align_tiled_plan(int N, int R, int H, int W, int C, int PH, int PW, int sr, bool backward, TiledPlan* p) {
+// Tile geometry + workspace layout.
+static inline bool roi_align_tiled_plan(int N, int R, int H, int W, int C, int PH, int PW, int sr, TiledPlan* p) {
     if (sr < 1 || sr > 4 || PH * sr > kAxisMax || PW * sr > kAxisMax) return false;
     if (R <= 0 || R > 65535 || C <= 0 || N <= 0 || H <= 0 || W <= 0) return false;
     if ((long long)R * C * PH * PW >= (1LL << 31) || (long long)N * C * H * W >= (1LL << 31)) return false;
@@ -80,17 +77,10 @@ static inline bool roi_align_tiled_plan(int N, int R, int H, int W, int C, int P
     p->ytab_off = off; off = align_up(off + (size_t)R * p->ny * sizeof(AxisEntry), 256);
     p->xtab_off = off; off = align_up(off + (size_t)R * p->nx * sizeof(AxisEntry), 256);
     p->zero_off = off;
-    p->zero_bytes = align_up(sizeof(int) * (size_t)(4 + p->tiles_total + (backward ? p->tiles_total * core_h : 0)), 256);
+    p->zero_bytes = align_up(sizeof(int) * (size_t)(4 + p->tiles_total), 256);
     off += p->zero_bytes;
     p->groups_max = (PH * PW + kStageBins - 1) / kStageBins;
     p->tile_list_off = off; off = align_up(off + (size_t)p->tiles_total * R * p->groups_max * sizeof(unsigned), 256);
-    p->row_list_off = off;
-    p->overflow_off = off;
-    if (backward) {
-        off = align_up(off + (size_t)p->tiles_total * core_h * kRowCap * sizeof(unsigned), 256);
-        p->overflow_off = off;
-        off = align_up(off + (size_t)R * p->ny * p->tiles_x * sizeof(uint2), 256);
-    }
     p->ws_bytes = off;
     return true;
 }
