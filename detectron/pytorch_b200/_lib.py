@@ -46,6 +46,9 @@ _SIGNATURES = {
     "b200_roi_crop_forward": (ctypes.c_int, [_c_float_p, _c_float_p] + [ctypes.c_int] * 7 + [_c_float_p, _stream_t]),
     # (grad_output, grids, N, C, H, W, R, oh, ow, grad_image, grad_grids, stream)
     "b200_roi_crop_backward": (ctypes.c_int, [_c_float_p, _c_float_p] + [ctypes.c_int] * 7 + [_c_float_p, _c_float_p, _stream_t]),
+    # (deltas, anchors, order, scores, k, A, H, W, stride, im_h, im_w, min_size, dets, valid, stream)
+    "b200_proposal_decode": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p, _c_float_p] + [ctypes.c_int] * 4 +
+                             [ctypes.c_float] * 4 + [_c_float_p, ctypes.c_void_p, _stream_t]),
     "b200_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     # (boxes, n, dim, thresh, keep_out, num_out, workspace, workspace_bytes, stream)
     "b200_nms": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,

@@ -15,6 +15,7 @@ int roi_pool_backward(const float*, float, int, int, int, int, int, int, int, co
 int roi_crop_forward(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int roi_crop_backward(const float*, const float*, int, int, int, int, int, int, int, float*, float*, cudaStream_t);
 size_t nms_workspace_bytes(int);
+int proposal_decode(const float*, const float*, const long long*, const float*, int, int, int, int, float, float, float, float, float*, int*, cudaStream_t);
 size_t roi_align_tiled_workspace_bytes(int, int, int, int, int, int, int);
 void roi_align_tiled_set_timing_buffer(unsigned long long*);
 void nms_set_timing_buffer(unsigned long long*);
@@ -218,6 +219,15 @@ int b200_roi_align_backward(const float* top_diff, float spatial_scale, int batc
     return roi_align_backward_generic(top_diff, spatial_scale, batch_size, num_rois, height, width, channels,
                                       aligned_height, aligned_width, sampling_ratio, bottom_rois, bottom_diff, nullptr,
                                       (cudaStream_t)stream);
+}
+
+int b200_proposal_decode(const float* bbox_deltas, const float* anchors, const long long* order, const float* scores,
+                         int num_candidates, int num_anchors, int height, int width, float feat_stride, float im_height,
+                         float im_width, float min_size, float* dets_out, int* valid_out, b200_stream_t stream) {
+    if (num_candidates < 0 || num_anchors <= 0 || height <= 0 || width <= 0) return B200_ROI_EINVAL;
+    if (num_candidates > 0 && (!bbox_deltas || !anchors || !order || !scores || !dets_out || !valid_out)) return B200_ROI_EINVAL;
+    return proposal_decode(bbox_deltas, anchors, order, scores, num_candidates, num_anchors, height, width, feat_stride,
+                           im_height, im_width, min_size, dets_out, valid_out, (cudaStream_t)stream);
 }
 
 int b200_roi_align_legacy_forward(const float* bottom_data, float spatial_scale, int batch_size, int num_rois,

@@ -1,0 +1,105 @@
+"""GPU-resident RPN proposal layer.
+
+Mirrors `GenerateProposalsOp` of lib/modeling/generate_proposals.py:12-168 (reference): same constructor
+`(anchors, spatial_scale)`, same `forward(rpn_cls_prob, rpn_bbox_pred, im_info) -> (rois ndarray (R, 5), roi_probs
+ndarray (R, 1))`.  The reference copies the score map, the deltas and im_info to the host (three blocking D2H copies,
+generate_proposals.py:58-63), runs a 200 k-anchor numpy top-k, decode, clip, filter and the Cython NMS on one CPU
+thread, and the caller copies the RoIs back.  Here everything up to the final result stays on the device:
+
+    torch.topk / torch.sort (stable)  ->  b200_proposal_decode (anchor rebuild + bbox_transform + clip + filter, one
+    kernel)  ->  b200_nms (bitmask + on-device scan)  ->  ONE D2H of the kept rows per image
+
+Configuration: the reference reads `cfg[TRAIN|TEST].RPN_{PRE,POST}_NMS_TOP_N, RPN_NMS_THRESH, RPN_MIN_SIZE` from its
+global config at call time; pass that object as `cfg=` to do the same, or give the four values per mode as keyword
+arguments (`train=dict(...)`, `test=dict(...)`); defaults are the reference's (lib/core/config.py:127-141, 200-214).
+
+Documented differences (see oracle/proposals.py): equal scores are ordered by ascending (h, w, a) index (the
+reference's argpartition/argsort order of ties is unspecified), and NMS suppresses at IoU > thresh with the CUDA
+kernel's rounding (the reference's host NMS uses >=); results on the golden vectors are identical.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from detectron.pytorch_b200 import _lib, ops
+
+_DEFAULTS = {
+    "TRAIN": dict(RPN_PRE_NMS_TOP_N=12000, RPN_POST_NMS_TOP_N=2000, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=0),
+    "TEST": dict(RPN_PRE_NMS_TOP_N=6000, RPN_POST_NMS_TOP_N=1000, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=0),
+}
+
+
+class GenerateProposalsOp(nn.Module):
+    def __init__(self, anchors, spatial_scale, cfg=None, train=None, test=None):
+        super().__init__()
+        self._anchors = np.asarray(anchors)
+        self._num_anchors = self._anchors.shape[0]
+        self._feat_stride = 1. / spatial_scale
+        self._cfg = cfg
+        self._params = {"TRAIN": dict(_DEFAULTS["TRAIN"], **(train or {})), "TEST": dict(_DEFAULTS["TEST"], **(test or {}))}
+        self._anchors_dev = {}
+
+    def _mode_params(self):
+        key = 'TRAIN' if self.training else 'TEST'
+        if self._cfg is not None:
+            c = self._cfg[key]
+            return c.RPN_PRE_NMS_TOP_N, c.RPN_POST_NMS_TOP_N, c.RPN_NMS_THRESH, c.RPN_MIN_SIZE
+        p = self._params[key]
+        return p["RPN_PRE_NMS_TOP_N"], p["RPN_POST_NMS_TOP_N"], p["RPN_NMS_THRESH"], p["RPN_MIN_SIZE"]
+
+    def _anchors_on(self, device):
+        key = str(device)
+        if key not in self._anchors_dev:
+            self._anchors_dev[key] = torch.from_numpy(np.ascontiguousarray(self._anchors, dtype=np.float32)).to(device)
+        return self._anchors_dev[key]
+
+    def forward(self, rpn_cls_prob, rpn_bbox_pred, im_info):
+        """rpn_cls_prob (N, A, H, W), rpn_bbox_pred (N, 4A, H, W) CUDA fp32; im_info (N, 3) [height, width, scale] (any
+        device).  Returns numpy arrays like the reference: rois (R, 5) [batch, x1, y1, x2, y2], roi_probs (R, 1)."""
+        if not rpn_cls_prob.is_cuda:
+            raise NotImplementedError("GenerateProposalsOp (B200) needs CUDA tensors; the host path is the reference's own")
+        scores = rpn_cls_prob.detach().float()
+        deltas = rpn_bbox_pred.detach().float().contiguous()
+        info = im_info.detach().cpu().numpy().astype(np.float32) if torch.is_tensor(im_info) else np.asarray(im_info, np.float32)
+        pre, post, thresh, min_size = self._mode_params()
+        per_image = [self.proposals_for_one_image(info[i], deltas[i], scores[i], pre, post, thresh, min_size)
+                     for i in range(scores.size(0))]
+        # one D2H per image, after all images have been enqueued
+        rois = np.empty((0, 5), dtype=np.float32)
+        probs = np.empty((0, 1), dtype=np.float32)
+        for i, (dets, valid, keep, num) in enumerate(per_image):
+            n = int(num.item()) if num is not None else dets.size(0)
+            k = keep[:n].long() if keep is not None else torch.arange(dets.size(0), device=dets.device)
+            k = k[valid[k] != 0]
+            if thresh > 0 and post > 0:
+                k = k[:post]
+            d = dets[k].cpu().numpy()
+            rois = np.append(rois, np.hstack((np.full((d.shape[0], 1), i, dtype=np.float32), d[:, :4])), axis=0)
+            probs = np.append(probs, d[:, 4:5], axis=0)
+        return rois, probs
+
+    def proposals_for_one_image(self, im_info, bbox_deltas, scores, pre_nms_topN, post_nms_topN, nms_thresh, min_size):
+        """Device part for one image: returns (dets (k, 5), valid (k), keep indices, number kept) as CUDA tensors."""
+        A, H, W = scores.shape
+        dev = scores.device
+        flat = scores.permute(1, 2, 0).reshape(-1)                                  # (H, W, A) order, as the reference enumerates anchors
+        total = flat.numel()
+        if pre_nms_topN <= 0 or pre_nms_topN >= total:
+            top_scores, order = torch.sort(flat, descending=True, stable=True)
+        else:
+            top_scores, order = torch.topk(flat, int(pre_nms_topN), largest=True, sorted=True)
+        k = int(order.numel())
+        dets = torch.empty((k, 5), dtype=torch.float32, device=dev)
+        valid = torch.empty((k,), dtype=torch.int32, device=dev)
+        lib = _lib.load()
+        min_size_scaled = float(np.float32(min_size) * np.float32(im_info[2]))
+        with torch.cuda.device(dev):
+            _lib.check(lib.b200_proposal_decode(bbox_deltas.data_ptr(), self._anchors_on(dev).data_ptr(), order.data_ptr(),
+                                                top_scores.contiguous().data_ptr(), k, A, H, W, float(self._feat_stride),
+                                                float(im_info[0]), float(im_info[1]), min_size_scaled, dets.data_ptr(),
+                                                valid.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                       "b200_proposal_decode")
+        if nms_thresh > 0 and k > 0:
+            keep, num = ops.nms_raw(dets, float(nms_thresh))
+            return dets, valid, keep, num
+        return dets, valid, None, None

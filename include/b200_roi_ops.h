@@ -167,6 +167,17 @@ B200_API unsigned long long b200_roi_ops_launch_count(void);
  * adds per-warp clock64 deltas [staging, compute, end-of-item wait, warp-items, RoI items, 8-bin groups, max compute]. */
 B200_API void b200_roi_ops_debug_timing_buffer(void* device_u64x16);
 
+/* ---- RPN proposal decode (the GPU-resident proposal layer) --------------------------------
+ * replaces the numpy block of GenerateProposalsOp.proposals_for_one_image, lib/modeling/generate_proposals.py:108-150
+ * (gather by score order, utils.boxes.bbox_transform :157-196, clip_tiled_boxes :138-154, _filter_boxes :171-182),
+ * for candidates that were selected and sorted on the device.  `order` holds indices into the (H, W, A)-flattened
+ * score map, best first; row t of dets_out is (x1, y1, x2, y2, score) ready for b200_nms, or the degenerate box
+ * (0, 0, -1, -1, score) with valid_out[t] = 0 when the size / centre filter rejects the candidate (such rows cannot
+ * interact with any box in NMS; the caller drops them afterwards).  min_size is already multiplied by im_info[2]. */
+B200_API int b200_proposal_decode(const float* bbox_deltas, const float* anchors, const long long* order, const float* scores,
+                         int num_candidates, int num_anchors, int height, int width, float feat_stride, float im_height,
+                         float im_width, float min_size, float* dets_out, int* valid_out, b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

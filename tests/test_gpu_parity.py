@@ -422,3 +422,46 @@ def test_ops_honour_current_stream_and_noncontiguous_input():
         out = RoIAlignFunction(7, 7, c["scale"], 2)(F, dev(r))
     s.synchronize()
     assert np.array_equal(out.cpu().numpy(), O.roi_align_forward(f, r, 7, 7, c["scale"], 2))
+
+
+# ------------------------------------------------------------------------------ proposal layer
+def _golden_proposals():
+    g = np.load(os.path.join(GOLDEN, "proposals.npz"))
+    return g, sorted({k.split("/")[0] for k in g.files if not k.startswith("cython_nms")})
+
+
+@pytest.mark.parametrize("name", ["all_candidates", "c4_test", "fpn_p5_train", "min_size"])
+def test_generate_proposals_matches_the_reference_op(name):
+    """Device proposal layer vs the output of the reference's own GenerateProposalsOp (golden vectors generated on CPU
+    by tests/golden/make_golden_proposals.py from the unmodified reference code)."""
+    from detectron.pytorch_b200.modeling.generate_proposals import GenerateProposalsOp
+    G, _ = _golden_proposals()
+    g = {k.split("/", 1)[1]: G[k] for k in G.files if k.startswith(name + "/")}
+    stride, pre, post, thresh, min_size = g["params"]
+    mode = dict(RPN_PRE_NMS_TOP_N=int(pre), RPN_POST_NMS_TOP_N=int(post), RPN_NMS_THRESH=float(thresh), RPN_MIN_SIZE=float(min_size))
+    op = GenerateProposalsOp(g["anchors"], 1.0 / float(stride), train=mode, test=mode)
+    rois, probs = op(dev(g["scores"]), dev(g["deltas"]), torch.from_numpy(g["im_info"]))
+    assert rois.shape == g["rois"].shape and probs.shape == g["probs"].shape
+    assert np.array_equal(probs, g["probs"])                       # same candidates survive, in the same order
+    assert np.array_equal(rois[:, 0], g["rois"][:, 0])
+    np.testing.assert_allclose(rois, g["rois"], rtol=0, atol=1e-4)
+    assert np.mean(rois == g["rois"]) > 0.999                      # double-precision exp: CUDA vs numpy agree to the last float32 bit almost everywhere
+
+
+def test_generate_proposals_realistic_level_vs_oracle():
+    """FPN P2-sized level (3 x 200 x 336 = 201 600 anchors, top 2000 -> NMS 0.7 -> 1000) against oracle/proposals.py."""
+    from detectron.pytorch_b200.modeling.generate_proposals import GenerateProposalsOp
+    from oracle import proposals as OP
+    rng = np.random.RandomState(3)
+    N, A, H, W, stride = 2, 3, 200, 336, 4
+    anchors = np.array([[-22., -10., 25., 13.], [-14., -14., 17., 17.], [-10., -22., 13., 25.]])     # 32 px, ratios 0.5 / 1 / 2
+    scores = ((rng.permutation(N * A * H * W).astype(np.float32) + 0.5) / (N * A * H * W)).reshape(N, A, H, W)
+    deltas = (rng.standard_normal((N, 4 * A, H, W)) * 0.5).astype(np.float32)
+    im_info = np.array([[800, 1333, 1.5], [800, 1216, 1.3]], dtype=np.float32)
+    mode = dict(RPN_PRE_NMS_TOP_N=2000, RPN_POST_NMS_TOP_N=1000, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=0)
+    op = GenerateProposalsOp(anchors, 1.0 / stride, train=mode, test=mode)
+    rois, probs = op(dev(scores), dev(deltas), torch.from_numpy(im_info))
+    ref_rois, ref_probs = OP.generate_proposals(scores, deltas, im_info, anchors, float(stride), 2000, 1000, 0.7, 0)
+    assert rois.shape == ref_rois.shape
+    assert np.array_equal(probs, ref_probs)
+    np.testing.assert_allclose(rois, ref_rois, rtol=0, atol=1e-4)
