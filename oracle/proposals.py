@@ -15,8 +15,12 @@ Two places where the reference is not a function of its inputs are made determin
   * NMS: the reference calls utils.boxes.nms -> cython_nms.nms on the host (suppress when IoU >= thresh).  The device
     path uses the CUDA kernel's semantics (IoU > thresh, the SASS rounding recipe); `nms="cuda"` (default) selects
     oracle_nms_cuda, `nms="cython"` the restatement of the Cython routine, so both can be compared.
-Parity of this layer is therefore "unpinned" in the SURVEY's sense: there is no golden output in the reference, and
-np.exp (float32) vs CUDA expf may differ in the last bit.  The GPU tests compare boxes within 1e-3 px.
+Pinning: the reference ships no golden outputs for this layer, so tests/golden/make_golden_proposals.py runs the
+UNMODIFIED reference op (GenerateProposalsOp + utils.boxes + the reference's own Cython NMS, built from a patched copy
+in a temp dir) on seeded inputs in the build container and stores inputs and outputs in tests/golden/proposals.npz;
+tests/test_oracle_proposals.py requires this restatement to reproduce them bit for bit (nms="cython"), and requires
+the same result with the CUDA NMS semantics on those inputs.  See bbox_transform for the precision the reference's
+lines actually evaluate in.
 """
 import numpy as np
 
