@@ -235,7 +235,15 @@ def main():
             sys.stderr.write("bench: CUDA graph path failed (%s); timing direct launches\n" % exc)
             use_graph = False
             ms_total = timed(step, K, graph=False)
+        # The timed region is only ~35 ms long (nvidia-smi samples every 100 ms): keep replaying the identical steps,
+        # untimed, for another half second so that the clock / throttle samples are taken under this very load.
+        t_soak = time.perf_counter()
+        while time.perf_counter() - t_soak < 0.5:
+            for i in range(K):
+                step(i)
+            torch.cuda.synchronize()
         clocks = clk.summary()
+        clocks["window"] = "timed region + 0.5 s of the identical steps launched back to back (untimed)"
     launches_per_step = None
     l0 = _lib.launch_count(); step(0); launches_per_step = _lib.launch_count() - l0
     torch.cuda.synchronize()
