@@ -135,6 +135,18 @@ def test_roi_align_baseline_cfg1_and_cfg2_full_size(fwd_path):
             assert_fwd_matches(out, G.roi_align_forward(dev(f), dev(r), P, P, s, sr).cpu().numpy(), fwd_path)
 
 
+def test_roi_align_backward_rows_path_many_rows_unranked(monkeypatch):
+    """N * H > 1024: the main kernel skips the heaviest-first row order (items are handed out in natural order)."""
+    monkeypatch.setenv("B200_ROI_ALIGN_BWD_PATH", "rows")
+    shape, s, P, sr = (6, 64, 180, 40), 1.0 / 8, 7, 2
+    r = S.make_rois(300, shape, s, seed=9).astype(np.float32)
+    dy = np.random.RandomState(4).standard_normal((r.shape[0], shape[1], P, P)).astype(np.float32)
+    f = S.make_features(shape, seed=2)
+    assert _lib.load().b200_roi_align_backward_workspace_bytes(shape[0], r.shape[0], shape[1], shape[2], shape[3], P, P, sr) > 0
+    _, dx = run_fwd_bwd(RoIAlignFunction(P, P, s, sr), f, r, dy)
+    np.testing.assert_allclose(dx, O.roi_align_backward(dy, r, shape, P, P, s, sr, acc64=True), **GRAD_TOL)
+
+
 ROWS_CASES = {
     # name: (shape, scale, P, sr, n_rois)  -- shapes the row-stationary backward covers (C % 64 == 0, P in {7, 14}, sr in {1, 2})
     "c64_odd_w": ((2, 64, 25, 45), 1.0 / 16, 7, 2, 40),
