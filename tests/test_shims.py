@@ -68,3 +68,31 @@ def test_no_silent_fallback_when_library_missing(monkeypatch, tmp_path):
     monkeypatch.setattr(build, "find_nvcc", lambda: None)
     with pytest.raises(ImportError):
         _lib.load()
+
+
+def test_generate_proposals_op_mirrors_the_reference_configuration_surface():
+    """Host-side behaviour of the device proposal layer: cfg[TRAIN|TEST].RPN_* lookup at call time like the reference
+    (generate_proposals.py:108-113), keyword overrides, and no silent CPU path."""
+    import numpy as np
+    import pytest
+    import torch
+    from detectron.pytorch_b200.modeling.generate_proposals import GenerateProposalsOp
+
+    class _Mode(object):
+        def __init__(self, pre, post, thr, ms):
+            self.RPN_PRE_NMS_TOP_N, self.RPN_POST_NMS_TOP_N, self.RPN_NMS_THRESH, self.RPN_MIN_SIZE = pre, post, thr, ms
+
+    cfg = {"TRAIN": _Mode(12000, 2000, 0.7, 0), "TEST": _Mode(1000, 300, 0.5, 4)}
+    anchors = np.array([[-8., -8., 8., 8.]])
+    op = GenerateProposalsOp(anchors, 1.0 / 16, cfg=cfg)
+    assert op._mode_params() == (12000, 2000, 0.7, 0)
+    op.eval()
+    assert op._mode_params() == (1000, 300, 0.5, 4)
+    cfg["TEST"].RPN_POST_NMS_TOP_N = 50                      # read at call time, not at construction
+    assert op._mode_params()[1] == 50
+    op2 = GenerateProposalsOp(anchors, 1.0 / 16, test=dict(RPN_PRE_NMS_TOP_N=77))
+    op2.eval()
+    assert op2._mode_params() == (77, 1000, 0.7, 0)          # the reference's TEST defaults for the rest
+    assert op2._feat_stride == 16.0 and op2._num_anchors == 1
+    with pytest.raises(NotImplementedError):
+        op2(torch.zeros(1, 1, 2, 2), torch.zeros(1, 4, 2, 2), torch.tensor([[32., 32., 1.]]))
