@@ -61,7 +61,8 @@ def import_reference(tmp):
     from core.config import cfg
     import modeling.generate_anchors as ga
     import modeling.generate_proposals as gp
-    return cfg, ga, gp, cython_nms
+    import utils.fpn as fpn_utils
+    return cfg, ga, gp, cython_nms, fpn_utils
 
 
 def make_inputs(seed, N, A, H, W):
@@ -76,7 +77,7 @@ def make_inputs(seed, N, A, H, W):
 def main():
     tmp = tempfile.mkdtemp(prefix="ref_cython_")
     build_cython(tmp)
-    cfg, ga, gp, cython_nms = import_reference(tmp)
+    cfg, ga, gp, cython_nms, fpn_utils = import_reference(tmp)
     cases = {
         # name: (training, N, H, W, stride, anchor sizes, pre, post, thresh, min_size, im_info)
         "fpn_p5_train": (True, 2, 25, 42, 32, (256,), 600, 100, 0.7, 0, [[800, 1333, 1.6], [768, 1024, 1.2]]),
@@ -106,6 +107,16 @@ def main():
     for n in (1, 65, 1000, 3000):
         b = S.make_nms_boxes(n, seed=n)
         out["cython_nms/%d/keep" % n] = np.asarray(cython_nms.nms(b, np.float32(0.7)), dtype=np.int64)
+    # FPN level assignment by the reference's own utils.fpn.map_rois_to_fpn_levels (pins oracle/fpn.py)
+    for seed, (k_min, k_max) in enumerate([(2, 5), (2, 6), (3, 4)]):
+        r = S.make_rois(400, (2, 8, 200, 336), 1.0 / 4, seed=seed)[:, 1:5].astype(np.float32)
+        r[:7] = [[0, 0, 223, 223], [0, 0, 222.99, 223], [10, 10, 9, 9], [5, 5, 4, 30], [0, 0, 111, 111], [0, 0, 447, 447], [0, 0, 2000, 2000]]
+        out["fpn_levels/%d/rois" % seed] = r
+        out["fpn_levels/%d/k" % seed] = np.asarray([k_min, k_max])
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out["fpn_levels/%d/lvls" % seed] = fpn_utils.map_rois_to_fpn_levels(r.copy(), k_min, k_max)
     np.savez_compressed(os.path.join(HERE, "proposals.npz"), **out)
     shutil.rmtree(tmp, ignore_errors=True)
 
