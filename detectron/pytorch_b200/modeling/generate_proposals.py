@@ -30,8 +30,9 @@ _DEFAULTS = {
 
 
 class GenerateProposalsOp(nn.Module):
-    def __init__(self, anchors, spatial_scale, cfg=None, train=None, test=None):
+    def __init__(self, anchors, spatial_scale, cfg=None, train=None, test=None, return_tensors=False):
         super().__init__()
+        self._return_tensors = bool(return_tensors)       # True: CUDA tensors out (for the on-device FPN chain), False: numpy like the reference
         self._anchors = np.asarray(anchors)
         self._num_anchors = self._anchors.shape[0]
         self._feat_stride = 1. / spatial_scale
@@ -67,15 +68,23 @@ class GenerateProposalsOp(nn.Module):
         # one D2H per image, after all images have been enqueued
         rois = np.empty((0, 5), dtype=np.float32)
         probs = np.empty((0, 1), dtype=np.float32)
+        t_rois, t_probs = [], []
         for i, (dets, valid, keep, num) in enumerate(per_image):
             n = int(num.item()) if num is not None else dets.size(0)
             k = keep[:n].long() if keep is not None else torch.arange(dets.size(0), device=dets.device)
             k = k[valid[k] != 0]
             if thresh > 0 and post > 0:
                 k = k[:post]
+            if self._return_tensors:
+                d = dets[k]
+                t_rois.append(torch.cat([torch.full((d.size(0), 1), float(i), device=d.device), d[:, :4]], dim=1))
+                t_probs.append(d[:, 4:5])
+                continue
             d = dets[k].cpu().numpy()
             rois = np.append(rois, np.hstack((np.full((d.shape[0], 1), i, dtype=np.float32), d[:, :4])), axis=0)
             probs = np.append(probs, d[:, 4:5], axis=0)
+        if self._return_tensors:
+            return torch.cat(t_rois, dim=0), torch.cat(t_probs, dim=0)
         return rois, probs
 
     def proposals_for_one_image(self, im_info, bbox_deltas, scores, pre_nms_topN, post_nms_topN, nms_thresh, min_size):

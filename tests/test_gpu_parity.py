@@ -477,3 +477,47 @@ def test_generate_proposals_realistic_level_vs_oracle():
     assert rois.shape == ref_rois.shape
     assert np.array_equal(probs, ref_probs)
     np.testing.assert_allclose(rois, ref_rois, rtol=0, atol=1e-4)
+
+
+def test_rpn_heads_to_box_head_chain_on_device():
+    """SURVEY 8f N1 + N2 end to end: per-level device proposals -> collect -> distribute -> RoIAlignFPNFunction, all on
+    CUDA tensors, against the oracle chain (oracle/proposals.py -> oracle/fpn.py -> per-level RoIAlign oracle + restore)."""
+    from detectron.pytorch_b200.modeling.collect_and_distribute_fpn_rpn_proposals import collect, distribute
+    from detectron.pytorch_b200.modeling.generate_proposals import GenerateProposalsOp
+    from detectron.pytorch_b200.modeling.roi_xfrom.roi_align.functions.roi_align_fpn import RoIAlignFPNFunction
+    from oracle import fpn as OF
+    from oracle import proposals as OP
+    rng = np.random.RandomState(21)
+    N, A, C, P, sr = 2, 3, 64, 7, 2
+    sizes = {2: (48, 64), 3: (24, 32), 4: (12, 16), 5: (6, 8)}
+    im_info = np.array([[192, 256, 1.0], [180, 240, 1.2]], dtype=np.float32)
+    mode = dict(RPN_PRE_NMS_TOP_N=300, RPN_POST_NMS_TOP_N=100, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=0)
+    lvl_rois, lvl_probs, ref_rois, ref_probs, feats = [], [], [], [], {}
+    for lvl, (H, W) in sizes.items():
+        stride = 2 ** lvl
+        base = 8.0 * stride
+        anchors = np.array([[-base * .7 + .5, -base * .35 + .5, base * .7 - .5, base * .35 - .5], [-base / 2 + .5, -base / 2 + .5, base / 2 - .5, base / 2 - .5],
+                            [-base * .35 + .5, -base * .7 + .5, base * .35 - .5, base * .7 - .5]])
+        scores = ((rng.permutation(N * A * H * W).astype(np.float32) + 0.5) / (N * A * H * W)).reshape(N, A, H, W)
+        deltas = (rng.standard_normal((N, 4 * A, H, W)) * 0.3).astype(np.float32)
+        op = GenerateProposalsOp(anchors, 1.0 / stride, train=mode, test=mode, return_tensors=True)
+        r, p = op(dev(scores), dev(deltas), torch.from_numpy(im_info))
+        lvl_rois.append(r); lvl_probs.append(p)
+        rr, pp = OP.generate_proposals(scores, deltas, im_info, anchors, float(stride), 300, 100, 0.7, 0)
+        ref_rois.append(rr); ref_probs.append(pp)
+        feats[lvl] = S.make_features((N, C, H, W), seed=lvl)
+    top = 250
+    rois = collect(lvl_rois, lvl_probs, top)
+    blobs = distribute(rois, 2, 5)
+    r_ref = OF.collect(ref_rois, ref_probs, top)
+    b_ref = OF.distribute(r_ref, 2, 5)
+    assert np.array_equal(blobs["rois_idx_restore_int32"].cpu().numpy(), b_ref["rois_idx_restore_int32"])
+    np.testing.assert_allclose(rois.cpu().numpy(), r_ref, rtol=0, atol=1e-4)
+    levels = [2, 3, 4, 5]
+    scales = [1.0 / 2 ** l for l in levels]
+    out = RoIAlignFPNFunction(P, P, scales, sr)([dev(feats[l]) for l in levels], [blobs["rois_fpn%d" % l].contiguous() for l in levels],
+                                                blobs["rois_idx_restore_int32"])
+    ref_parts = [O.roi_align_forward(feats[l], b_ref["rois_fpn%d" % l], P, P, sc, sr) for l, sc in zip(levels, scales) if len(b_ref["rois_fpn%d" % l])]
+    ref_out = np.concatenate(ref_parts, axis=0)[b_ref["rois_idx_restore_int32"]]
+    assert out.shape == ref_out.shape
+    np.testing.assert_allclose(out.cpu().numpy(), ref_out, rtol=1e-4, atol=1e-4)       # RoI coordinates agree to 1e-4 px
