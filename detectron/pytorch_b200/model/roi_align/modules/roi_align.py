@@ -1,27 +1,16 @@
-"""Drop-in for `model.roi_align.modules.roi_align` (reference lib/model/roi_align/modules/roi_align.py:6-42)."""
-from torch.nn.modules.module import Module
-from torch.nn.functional import avg_pool2d, max_pool2d
+"""`RoIAlign`, `RoIAlignAvg`, `RoIAlignMax` of the legacy flavour (one sample per lattice corner, no sampling ratio):
+same import path, constructors `(aligned_height, aligned_width, spatial_scale)` and attributes as
+lib/model/roi_align/modules/roi_align.py:6-42 (reference).  Avg / Max align at (h+1) x (w+1) and reduce with a
+2x2 stride-1 pool.  Built by detectron.pytorch_b200._modules.roi_module."""
+from detectron.pytorch_b200._modules import roi_module
+
 from ..functions.roi_align import RoIAlignFunction
 
+_FIELDS = (("aligned_height", int), ("aligned_width", int), ("spatial_scale", float))
+_GROW = ("aligned_height", "aligned_width")
 
-class RoIAlign(Module):
-    def __init__(self, aligned_height, aligned_width, spatial_scale):
-        super(RoIAlign, self).__init__()
-        self.aligned_width = int(aligned_width)
-        self.aligned_height = int(aligned_height)
-        self.spatial_scale = float(spatial_scale)
-
-    def forward(self, features, rois):
-        return RoIAlignFunction(self.aligned_height, self.aligned_width, self.spatial_scale)(features, rois)
-
-
-class RoIAlignAvg(RoIAlign):
-    def forward(self, features, rois):
-        x = RoIAlignFunction(self.aligned_height + 1, self.aligned_width + 1, self.spatial_scale)(features, rois)
-        return avg_pool2d(x, kernel_size=2, stride=1)
-
-
-class RoIAlignMax(RoIAlign):
-    def forward(self, features, rois):
-        x = RoIAlignFunction(self.aligned_height + 1, self.aligned_width + 1, self.spatial_scale)(features, rois)
-        return max_pool2d(x, kernel_size=2, stride=1)
+RoIAlign = roi_module("RoIAlign", RoIAlignFunction, _FIELDS, doc="Legacy RoIAlign (forward(features, rois)).")
+RoIAlignAvg = roi_module("RoIAlignAvg", RoIAlignFunction, _FIELDS, grow=_GROW, epilogue="avg", base=RoIAlign,
+                         doc="Legacy RoIAlign at (h+1) x (w+1), then 2x2 stride-1 average pooling.")
+RoIAlignMax = roi_module("RoIAlignMax", RoIAlignFunction, _FIELDS, grow=_GROW, epilogue="max", base=RoIAlign,
+                         doc="Legacy RoIAlign at (h+1) x (w+1), then 2x2 stride-1 max pooling.")

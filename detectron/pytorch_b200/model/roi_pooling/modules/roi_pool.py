@@ -1,14 +1,10 @@
-"""Drop-in for `model.roi_pooling.modules.roi_pool` (reference lib/model/roi_pooling/modules/roi_pool.py:5-14)."""
-from torch.nn.modules.module import Module
+"""`_RoIPooling(pooled_height, pooled_width, spatial_scale)` -- same import path, constructor and attributes as the
+reference's lib/model/roi_pooling/modules/roi_pool.py:5-14; built by detectron.pytorch_b200._modules.roi_module."""
+from detectron.pytorch_b200._modules import roi_module
+
 from ..functions.roi_pool import RoIPoolFunction
 
-
-class _RoIPooling(Module):
-    def __init__(self, pooled_height, pooled_width, spatial_scale):
-        super(_RoIPooling, self).__init__()
-        self.pooled_width = int(pooled_width)
-        self.pooled_height = int(pooled_height)
-        self.spatial_scale = float(spatial_scale)
-
-    def forward(self, features, rois):
-        return RoIPoolFunction(self.pooled_height, self.pooled_width, self.spatial_scale)(features, rois)
+_RoIPooling = roi_module(
+    "_RoIPooling", RoIPoolFunction,
+    fields=(("pooled_height", int), ("pooled_width", int), ("spatial_scale", float)),
+    doc="Quantised max pooling of every RoI to pooled_height x pooled_width (forward(features, rois)).")

@@ -1,36 +1,16 @@
-"""Drop-in for `modeling.roi_xfrom.roi_align.modules.roi_align`
-(reference lib/modeling/roi_xfrom/roi_align/modules/roi_align.py:6-45)."""
-from torch.nn.modules.module import Module
-from torch.nn.functional import avg_pool2d, max_pool2d
+"""`RoIAlign`, `RoIAlignAvg`, `RoIAlignMax` of the Caffe2-exact flavour: same import path, constructors
+`(aligned_height, aligned_width, spatial_scale, sampling_ratio)` and attributes as
+lib/modeling/roi_xfrom/roi_align/modules/roi_align.py:6-45 (reference).  Avg / Max align at (h+1) x (w+1) and reduce
+with a 2x2 stride-1 pool (:19-31, :33-45).  Built by detectron.pytorch_b200._modules.roi_module."""
+from detectron.pytorch_b200._modules import roi_module
+
 from ..functions.roi_align import RoIAlignFunction
 
+_FIELDS = (("aligned_height", int), ("aligned_width", int), ("spatial_scale", float), ("sampling_ratio", int))
+_GROW = ("aligned_height", "aligned_width")
 
-class RoIAlign(Module):
-    def __init__(self, aligned_height, aligned_width, spatial_scale, sampling_ratio):
-        super(RoIAlign, self).__init__()
-        self.aligned_width = int(aligned_width)
-        self.aligned_height = int(aligned_height)
-        self.spatial_scale = float(spatial_scale)
-        self.sampling_ratio = int(sampling_ratio)
-
-    def forward(self, features, rois):
-        return RoIAlignFunction(self.aligned_height, self.aligned_width,
-                                self.spatial_scale, self.sampling_ratio)(features, rois)
-
-
-class RoIAlignAvg(RoIAlign):
-    """RoIAlign at (h+1) x (w+1) followed by a 2x2 stride-1 average pool (reference :19-31)."""
-
-    def forward(self, features, rois):
-        x = RoIAlignFunction(self.aligned_height + 1, self.aligned_width + 1,
-                             self.spatial_scale, self.sampling_ratio)(features, rois)
-        return avg_pool2d(x, kernel_size=2, stride=1)
-
-
-class RoIAlignMax(RoIAlign):
-    """RoIAlign at (h+1) x (w+1) followed by a 2x2 stride-1 max pool (reference :33-45)."""
-
-    def forward(self, features, rois):
-        x = RoIAlignFunction(self.aligned_height + 1, self.aligned_width + 1,
-                             self.spatial_scale, self.sampling_ratio)(features, rois)
-        return max_pool2d(x, kernel_size=2, stride=1)
+RoIAlign = roi_module("RoIAlign", RoIAlignFunction, _FIELDS, doc="Caffe2-exact RoIAlign (forward(features, rois)).")
+RoIAlignAvg = roi_module("RoIAlignAvg", RoIAlignFunction, _FIELDS, grow=_GROW, epilogue="avg", base=RoIAlign,
+                         doc="RoIAlign at (h+1) x (w+1), then 2x2 stride-1 average pooling.")
+RoIAlignMax = roi_module("RoIAlignMax", RoIAlignFunction, _FIELDS, grow=_GROW, epilogue="max", base=RoIAlign,
+                         doc="RoIAlign at (h+1) x (w+1), then 2x2 stride-1 max pooling.")

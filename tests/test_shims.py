@@ -96,3 +96,45 @@ def test_generate_proposals_op_mirrors_the_reference_configuration_surface():
     assert op2._feat_stride == 16.0 and op2._num_anchors == 1
     with pytest.raises(NotImplementedError):
         op2(torch.zeros(1, 1, 2, 2), torch.zeros(1, 4, 2, 2), torch.tensor([[32., 32., 1.]]))
+
+
+def test_module_shells_call_their_function_with_the_reference_arguments():
+    """The nn.Module shells (detectron.pytorch_b200._modules) on CPU, with a recording stand-in for the CUDA function:
+    constructor arguments and attributes as in the reference, Avg / Max enlarge the aligned size by one and pool 2x2."""
+    import pytest
+    import torch
+    from detectron.pytorch_b200._modules import roi_module
+    from detectron.pytorch_b200.model.roi_align.modules import roi_align as legacy
+    from detectron.pytorch_b200.model.roi_crop.modules.roi_crop import _RoICrop
+    from detectron.pytorch_b200.model.roi_pooling.modules.roi_pool import _RoIPooling
+    from detectron.pytorch_b200.modeling.roi_xfrom.roi_align.modules import roi_align as xfrom
+
+    calls = []
+
+    class Recorder(object):
+        def __init__(self, *ctor):
+            self.ctor = ctor
+
+        def __call__(self, features, rois):
+            calls.append(self.ctor)
+            return torch.arange(float(rois.shape[0] * 2 * self.ctor[0] * self.ctor[1])).reshape(rois.shape[0], 2, self.ctor[0], self.ctor[1])
+
+    for mod, extra in ((xfrom, (2,)), (legacy, ())):
+        for cls, grow in ((mod.RoIAlign, 0), (mod.RoIAlignAvg, 1), (mod.RoIAlignMax, 1)):
+            probe = roi_module(cls.__name__, Recorder, cls._fields, grow=cls._grow, epilogue=cls._epilogue)
+            m = probe(7, 5, 0.25, *extra)
+            assert (m.aligned_height, m.aligned_width, m.spatial_scale) == (7, 5, 0.25)
+            y = m(torch.zeros(1, 2, 8, 8), torch.zeros(3, 5))
+            assert calls[-1] == (7 + grow, 5 + grow, 0.25) + extra
+            assert y.shape == (3, 2, 7, 5)
+        assert issubclass(mod.RoIAlignAvg, mod.RoIAlign) and issubclass(mod.RoIAlignMax, mod.RoIAlign)
+    ref = torch.arange(3 * 2 * 8 * 6, dtype=torch.float32).reshape(3, 2, 8, 6)
+    m = roi_module("RoIAlignMax", Recorder, xfrom.RoIAlignMax._fields, grow=xfrom.RoIAlignMax._grow, epilogue="max")(7, 5, 1.0, 2)
+    assert torch.equal(m(torch.zeros(1, 2, 4, 4), torch.zeros(3, 5)), torch.nn.functional.max_pool2d(ref, 2, 1))
+    # the real classes reach the CUDA functions, which refuse CPU tensors like the reference does
+    for m in (xfrom.RoIAlignAvg(7, 7, 0.25, 2), legacy.RoIAlign(7, 7, 0.25), _RoIPooling(7, 7, 0.0625)):
+        with pytest.raises(NotImplementedError):
+            m(torch.zeros(1, 2, 8, 8), torch.zeros(1, 5))
+    assert _RoICrop().layout == 'BHWD' and _RoIPooling(7, 6, 0.5).pooled_width == 6
+    with pytest.raises(TypeError):
+        xfrom.RoIAlign(7, 7, 0.25)
