@@ -13,7 +13,7 @@ or, to make an unmodified checkout of the reference pick these up under ITS impo
 __version__ = "0.1.0"
 
 
-def install_reference_aliases(overwrite=True):
+def install_reference_aliases(overwrite=True, proposals=False):
     """Register this package's op modules in sys.modules under the reference's import paths.
 
     After this, `from modeling.roi_xfrom.roi_align.functions.roi_align import RoIAlignFunction`
@@ -21,7 +21,9 @@ def install_reference_aliases(overwrite=True):
     RoIPoolFunction` (:11), `from model.roi_crop.functions.roi_crop import RoICropFunction` (:12) and
     `from model.nms.nms_gpu import nms_gpu` resolve to the sm_100a implementations.
     Parent packages that already exist (e.g. the reference's own `modeling`) are left alone; only the
-    op sub-packages are injected.
+    op sub-packages are injected.  `proposals=True` additionally routes `modeling.generate_proposals` (the RPN proposal
+    layer, rpn_heads.py / FPN.py import it) and `modeling.collect_and_distribute_fpn_rpn_proposals` to the device
+    implementations; the latter only implements the inference path, hence opt-in.
     """
     import importlib
     import sys
@@ -32,11 +34,14 @@ def install_reference_aliases(overwrite=True):
         "model.roi_pooling.modules", "model.roi_pooling.modules.roi_pool",
         "model.roi_crop", "model.roi_crop.functions", "model.roi_crop.functions.roi_crop",
         "model.roi_crop.modules", "model.roi_crop.modules.roi_crop",
+        "model.roi_crop.functions.gridgen", "model.roi_crop.functions.crop_resize", "model.roi_crop.modules.gridgen",
         "model.nms", "model.nms.nms_gpu", "model.nms.nms_wrapper",
         "modeling.roi_xfrom", "modeling.roi_xfrom.roi_align", "modeling.roi_xfrom.roi_align.functions",
         "modeling.roi_xfrom.roi_align.functions.roi_align", "modeling.roi_xfrom.roi_align.modules",
-        "modeling.roi_xfrom.roi_align.modules.roi_align",
+        "modeling.roi_xfrom.roi_align.modules.roi_align", "modeling.roi_xfrom.roi_align.functions.roi_align_fpn",
     ]
+    if proposals:
+        names += ["modeling.generate_proposals", "modeling.collect_and_distribute_fpn_rpn_proposals"]
     installed = []
     for top in ("model", "modeling"):
         if top not in sys.modules:

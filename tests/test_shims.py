@@ -34,6 +34,16 @@ def test_reference_import_paths_and_signatures():
                   _RoIPooling(7, 7, 0.25), _RoICrop()):
             assert isinstance(m, torch.nn.Module)
         assert RoICropFunction().input1 is None
+        from model.roi_crop.functions.gridgen import AffineGridGenFunction                       # helpers of the RoICrop mode
+        from model.roi_crop.modules.gridgen import _AffineGridGen
+        from model.roi_crop.functions.crop_resize import RoICropFunction as CropResize
+        assert CropResize is RoICropFunction and _AffineGridGen(3, 4).f.height == 3 and AffineGridGenFunction(3, 4).width == 4
+        assert "modeling.generate_proposals" not in sys.modules                                  # opt-in only
+        pkg.install_reference_aliases(proposals=True)
+        from modeling.generate_proposals import GenerateProposalsOp
+        from modeling.collect_and_distribute_fpn_rpn_proposals import CollectAndDistributeFpnRpnProposalsOp
+        assert list(inspect.signature(GenerateProposalsOp.__init__).parameters)[1:3] == ["anchors", "spatial_scale"]
+        assert isinstance(CollectAndDistributeFpnRpnProposalsOp(), torch.nn.Module)
     finally:
         for k in [k for k in sys.modules if k.split(".")[0] in ("model", "modeling")]:
             del sys.modules[k]
