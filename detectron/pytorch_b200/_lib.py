@@ -19,6 +19,7 @@ _SIGNATURES = {
     "b200_roi_ops_abi_version": (ctypes.c_int, []),
     "b200_roi_ops_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "b200_roi_ops_launch_count": (ctypes.c_ulonglong, []),
+    "b200_roi_ops_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p]),
     "b200_roi_ops_debug_timing_buffer": (None, [ctypes.c_void_p]),
     # (bottom, scale, N, R, H, W, C, PH, PW, sr, rois, top, stream)
     "b200_roi_align_forward": (ctypes.c_int, [_c_float_p, ctypes.c_float] + [ctypes.c_int] * 8 + [_c_float_p, _c_float_p, _stream_t]),
@@ -82,7 +83,7 @@ def load():
             fn = getattr(lib, name)          # AttributeError here == header/library mismatch: fail loudly
             fn.restype = restype
             fn.argtypes = argtypes
-        if lib.b200_roi_ops_abi_version() != 2:
+        if lib.b200_roi_ops_abi_version() != 3:
             raise ImportError("libb200_roi_ops.so ABI version mismatch")
         _lib = lib
     return _lib
@@ -96,3 +97,8 @@ def check(status, what):
 
 def launch_count():
     return int(load().b200_roi_ops_launch_count())
+
+
+def set_option(name, value=None):
+    """Path-selection switch (see b200_roi_ops_set_option in include/b200_roi_ops.h); value None restores the default."""
+    check(load().b200_roi_ops_set_option(name.encode(), None if value is None else str(value).encode()), "b200_roi_ops_set_option")

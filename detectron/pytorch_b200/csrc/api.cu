@@ -1,10 +1,40 @@
 // api.cu -- the extern "C" boundary of libb200_roi_ops.so (see include/b200_roi_ops.h).
 // Argument validation + dispatch only; kernels live in the per-op translation units.
 #include "common.cuh"
+#include <mutex>
 #include <stdlib.h>
+#include <string.h>
 
 namespace b200 {
 unsigned long long g_launch_count = 0;
+
+static const char* const kOptionNames[kNumOptions] = {"B200_ROI_ALIGN_PATH", "B200_ROI_ALIGN_BWD_PATH", "B200_ROI_ALIGN_BWD_CPL",
+                                                      "B200_FWD_ZERO", "B200_NMS_SCAN"};
+static int g_options[kNumOptions];
+static std::once_flag g_options_once;
+
+static void options_init() {
+    for (int i = 0; i < kNumOptions; ++i) {
+        const char* e = getenv(kOptionNames[i]);
+        __atomic_store_n(&g_options[i], e ? (int)(unsigned char)e[0] : 0, __ATOMIC_RELAXED);
+    }
+}
+
+int option_get(Option which) {
+    std::call_once(g_options_once, options_init);
+    return __atomic_load_n(&g_options[which], __ATOMIC_RELAXED);
+}
+
+static int option_set(const char* name, const char* value) {
+    std::call_once(g_options_once, options_init);
+    if (!name) return B200_ROI_EINVAL;
+    for (int i = 0; i < kNumOptions; ++i)
+        if (strcmp(name, kOptionNames[i]) == 0) {
+            __atomic_store_n(&g_options[i], value ? (int)(unsigned char)value[0] : 0, __ATOMIC_RELAXED);
+            return B200_ROI_OK;
+        }
+    return B200_ROI_EINVAL;
+}
 
 int roi_align_forward_generic(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, cudaStream_t);
 int roi_align_backward_generic(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, cudaStream_t);
@@ -20,13 +50,25 @@ size_t roi_align_tiled_workspace_bytes(int, int, int, int, int, int, int);
 void roi_align_tiled_set_timing_buffer(unsigned long long*);
 void nms_set_timing_buffer(unsigned long long*);
 int roi_align_forward_tiled(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
+size_t roi_align_stream_workspace_bytes(int, int, int, int, int, int, int);
+int roi_align_forward_stream(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
 
-// B200_ROI_ALIGN_PATH=generic|tiled|auto (default auto) -- test/benchmark override of the forward dispatch
+// B200_ROI_ALIGN_PATH=generic|tiled|stream|auto (default auto) -- test/benchmark override of the forward dispatch
+//   0 auto: streaming-strip path (TMA) -> tiled path -> generic, each when it applies
+//   1 generic only; 2 tiled (-> generic); 3 stream (-> generic)
 static int forward_path_mode() {
-    const char* e = getenv("B200_ROI_ALIGN_PATH");      // read per call: tests flip it at run time
-    if (e && e[0] == 'g') return 1;
-    if (e && e[0] == 't') return 2;
+    const int e = option_get(kOptFwdPath);
+    if (e == 'g') return 1;
+    if (e == 't') return 2;
+    if (e == 's') return 3;
     return 0;
+}
+
+static size_t forward_workspace_bytes(int mode, int N, int R, int H, int W, int PH, int PW, int sr) {
+    if (mode == 1) return 0;
+    const size_t a = (mode == 3 || mode == 0) ? roi_align_stream_workspace_bytes(N, R, H, W, PH, PW, sr) : 0;
+    const size_t b = (mode == 2 || mode == 0) ? roi_align_tiled_workspace_bytes(N, R, H, W, PH, PW, sr) : 0;
+    return a > b ? a : b;
 }
 
 static bool tiled_pays_off(int R, int C, int H, int W, int PH, int PW) {
@@ -43,10 +85,10 @@ int roi_align_backward_rows(const float*, float, int, int, int, int, int, int, i
 
 // B200_ROI_ALIGN_BWD_PATH=generic|nhwc|rows|auto
 static int backward_path_mode() {
-    const char* e = getenv("B200_ROI_ALIGN_BWD_PATH");
-    if (e && e[0] == 'g') return 1;
-    if (e && e[0] == 'n') return 2;
-    if (e && e[0] == 'r') return 3;
+    const int e = option_get(kOptBwdPath);
+    if (e == 'g') return 1;
+    if (e == 'n') return 2;
+    if (e == 'r') return 3;
     return 0;
 }
 
@@ -78,7 +120,7 @@ using namespace b200;
 
 extern "C" {
 
-int b200_roi_ops_abi_version(void) { return 2; }
+int b200_roi_ops_abi_version(void) { return 3; }
 
 const char* b200_roi_ops_strerror(int status) {
     if (status == B200_ROI_OK) return "success";
@@ -90,6 +132,8 @@ const char* b200_roi_ops_strerror(int status) {
 
 unsigned long long b200_roi_ops_launch_count(void) { return g_launch_count; }
 
+int b200_roi_ops_set_option(const char* name, const char* value) { return option_set(name, value); }
+
 void b200_roi_ops_debug_timing_buffer(void* device_u64x16) {
     roi_align_tiled_set_timing_buffer((unsigned long long*)device_u64x16);
     nms_set_timing_buffer((unsigned long long*)device_u64x16);
@@ -97,8 +141,8 @@ void b200_roi_ops_debug_timing_buffer(void* device_u64x16) {
 
 size_t b200_roi_align_workspace_bytes(int batch_size, int num_rois, int height, int width, int aligned_height,
                                       int aligned_width, int sampling_ratio) {
-    if (forward_path_mode() == 1) return 0;
-    return roi_align_tiled_workspace_bytes(batch_size, num_rois, height, width, aligned_height, aligned_width, sampling_ratio);
+    if (batch_size <= 0 || num_rois <= 0 || height <= 0 || width <= 0 || aligned_height <= 0 || aligned_width <= 0) return 0;
+    return forward_workspace_bytes(forward_path_mode(), batch_size, num_rois, height, width, aligned_height, aligned_width, sampling_ratio);
 }
 
 int b200_roi_align_forward_ws(const float* bottom_data, float spatial_scale, int batch_size, int num_rois, int height,
@@ -117,8 +161,14 @@ int b200_roi_align_forward_indexed(const float* bottom_data, float spatial_scale
     if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
     if (num_rois > 0 && channels > 0 && (!bottom_data || !bottom_rois || !top_data)) return B200_ROI_EINVAL;
     const int mode = forward_path_mode();
-    if (mode != 1 && workspace != nullptr &&
-        (mode == 2 || tiled_pays_off(num_rois, channels, height, width, aligned_height, aligned_width))) {
+    const bool pays = tiled_pays_off(num_rois, channels, height, width, aligned_height, aligned_width);
+    if (workspace != nullptr && (mode == 3 || (mode == 0 && pays))) {
+        const int rc = roi_align_forward_stream(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
+                                                aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data, top_rows,
+                                                workspace, workspace_bytes, (cudaStream_t)stream);
+        if (rc != 1000) return rc;
+    }
+    if (workspace != nullptr && (mode == 2 || (mode == 0 && pays))) {
         const int rc = roi_align_forward_tiled(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
                                                aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data, top_rows,
                                                workspace, workspace_bytes, (cudaStream_t)stream);
@@ -135,9 +185,9 @@ int b200_roi_align_forward(const float* bottom_data, float spatial_scale, int ba
     if (bad_dims(batch_size, num_rois, height, width, channels, aligned_height, aligned_width)) return B200_ROI_EINVAL;
     if (num_rois > 0 && channels > 0 && (!bottom_data || !bottom_rois || !top_data)) return B200_ROI_EINVAL;
     const int mode = forward_path_mode();
-    const size_t wsb = (mode == 1) ? 0 : roi_align_tiled_workspace_bytes(batch_size, num_rois, height, width, aligned_height,
-                                                                         aligned_width, sampling_ratio);
-    if (wsb > 0 && (mode == 2 || tiled_pays_off(num_rois, channels, height, width, aligned_height, aligned_width))) {
+    const size_t wsb = (num_rois > 0) ? forward_workspace_bytes(mode, batch_size, num_rois, height, width, aligned_height, aligned_width,
+                                                                sampling_ratio) : 0;
+    if (wsb > 0 && (mode >= 2 || tiled_pays_off(num_rois, channels, height, width, aligned_height, aligned_width))) {
         void* ws = nullptr;
         if (cudaMallocAsync(&ws, wsb, (cudaStream_t)stream) == cudaSuccess) {
             const int rc = b200_roi_align_forward_ws(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,

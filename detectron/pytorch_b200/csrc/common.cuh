@@ -17,6 +17,20 @@ inline int finish_launch(int n_launches = 1) {
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
+// ---- dispatch switches -------------------------------------------------------------------------
+// A/B and test overrides of the path selection.  Each switch is read from the environment ONCE (first use) and can
+// be changed afterwards through b200_roi_ops_set_option() -- the hot path never calls getenv().
+// The value is the first character of the string ('\0' = auto / default).
+enum Option {
+    kOptFwdPath = 0,      // B200_ROI_ALIGN_PATH      = auto | generic | tiled | stream
+    kOptBwdPath,          // B200_ROI_ALIGN_BWD_PATH  = auto | generic | nhwc | rows
+    kOptBwdCpl,           // B200_ROI_ALIGN_BWD_CPL   = 4 | 2
+    kOptFwdZero,          // B200_FWD_ZERO            = dense | bins
+    kOptNmsScan,          // B200_NMS_SCAN            = resolver | simple
+    kNumOptions
+};
+int option_get(Option which);
+
 // ---- arithmetic that must round exactly like the reference kernels' SASS --------------------
 // All helpers use the _rn intrinsics, which nvcc never contracts or re-associates, so the
 // fusion pattern is exactly what is written here (see oracle/roi_ops_oracle.c for the recipes

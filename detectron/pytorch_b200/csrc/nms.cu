@@ -384,8 +384,7 @@ int nms(const float* boxes, int n, int dim, float thresh, int* keep_out, int* nu
     const long long tiles = (long long)cb * (cb + 1) / 2;
     if (tiles > 0x7fffffffLL) return B200_ROI_EINVAL;
     nms_mask_kernel<<<(unsigned)tiles, kNmsTile, 0, stream>>>(boxes, n, dim, thresh, lo, hi, mask, diag_t);
-    const char* e_mode = getenv("B200_NMS_SCAN");             // "simple" selects the unpipelined scan (A/B tests)
-    const bool simple = e_mode && e_mode[0] == 's';
+    const bool simple = option_get(kOptNmsScan) == 's';       // "simple" selects the unpipelined scan (A/B tests)
     for (int reach = 4; reach >= 2 && !simple; --reach) {
         const size_t smem_res = sizeof(u64) * ((size_t)reach * cb * kNmsTile + 4 * (size_t)cb) + 16;
         if (smem_res > 224 * 1024) continue;

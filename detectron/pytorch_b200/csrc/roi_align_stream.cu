@@ -1,0 +1,755 @@
+// roi_align_stream.cu -- Caffe2-exact RoIAlign FORWARD, "streaming strip" fast path (TMA + mbarrier ring).
+//
+// The feature map is cut into vertical strips of WX columns (+ a halo); one persistent CTA per SM owns a
+// contiguous piece of the linear space (image, strip, 32-channel group, row) and streams the rows of its
+// strips top to bottom through a ring of K row slots in shared memory.  Rows are fetched by TMA
+// (cp.async.bulk.tensor, one 3-D box = 8 channels x 1 row x XB columns per instruction, 4 per row), signalled
+// on per-slot mbarriers; a producer warp runs ahead of 16 consumer warps, so loading overlaps the arithmetic
+// completely and no thread ever stages a feature value through registers.
+//
+// Shared-memory layout of one row slot: [32 channels][XB columns] as TMA writes it (x innermost), with the
+// box of channel octet i (channels 8i..8i+7) started i columns to the LEFT of the strip.  With XB = 4 (mod 8)
+// the word address of (channel c, column x) is c*XB + (c >> 3) + (x - x0): as c runs over a warp's 32 lanes
+// the bank is 4*((c & 7) * odd) + (c >> 3) + const -- a bijection.  So the compute mapping is
+// lane = channel, one warp = one bilinear tap of one sample for 32 channels per conflict-free LDS.32, and all
+// addressing / weights are warp-uniform.  (A transposed [cell][channel] layout would need a register-staged
+// transpose; TMA cannot interleave channels that are H*W apart in global memory.)
+//
+// Work = "fragments": up to 8 consecutive bins of one bin row of one RoI, keyed by the first feature row
+// they read.  A fragment is processed by ONE warp when the rows [key, end) it needs are resident, so every
+// output element is computed by one lane in the reference's own operation order and written exactly once
+// with a plain store: bit-identical to the reference kernel, deterministic, no zero-fill of the output.
+// Only bins whose samples cannot be resident together (x-span beyond the strip halo, y-span beyond the
+// ring) are cut into per-sample fragments that accumulate with red.global.add onto elements the fill
+// kernel zeroed (at most two partial sums per element -> still deterministic).
+//
+// Prepass (channel independent, two small kernels): `count` builds the per-RoI axis tables (all IEEE
+// divisions; ring-slot byte offsets precomputed) and a histogram of fragments per (image, strip, row); its
+// last CTA scans the histogram (CSR row pointers) and cuts the linear space into one piece per SM of equal
+// estimated cost; `fill` writes the 8-byte fragment records into the CSR.
+//
+// Semantics: lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu (reference) :16-63, :65-121.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <stdlib.h>
+
+namespace b200 {
+
+namespace {
+
+constexpr int kConsumerWarps = 16;
+constexpr int kStreamThreads = 32 * (kConsumerWarps + 1);     // + the TMA producer warp
+constexpr int kFragBins = 8;                                  // bins per fragment (one flush)
+constexpr int kStageStride = 36;                              // words per staged bin: conflict-free both ways
+constexpr int kStageWordsPerWarp = kFragBins * kStageStride;
+constexpr int kMaxSlots = 32;                                 // ring depth K <= 32 (phase bits live in one register)
+constexpr int kAxisMaxS = 32;                                 // P * sampling_ratio per axis
+constexpr int kPrepThreads = 128;
+constexpr unsigned kSmemBudget = 227u * 1024u;
+
+typedef unsigned long long u64;
+
+struct StreamGeom {
+    int N, R, C, H, W, PH, PW, sr;
+    int ny, nx;
+    int XB, WX, S, K;           // box width, strip core width, strips per image, ring depth
+    int row_bytes;              // bytes of one ring slot = 32 * XB * 4
+    int Q, keys;                // strip columns = N * S, keys = Q * H
+    int G;                      // 32-channel groups
+    int pieces;                 // persistent CTAs
+    int max_entries;
+    float scale;
+};
+
+struct StreamWs {
+    uint4* ytab;                // [R][ny] {hy, ly, byte offset of the ring slot of row y_low, of row y_low + 1}
+    uint4* xtab;                // [R][nx] {hx, lx, x_low * 4, 0}
+    int* hist;                  // [keys] fragments per key                           (zero block)
+    int* cost;                  // [keys] estimated cost per key                      (zero block)
+    int* cursor;                // [keys] fill cursors                                (zero block)
+    int* maxend;                // [keys] max over the key's fragments of `end`       (zero block)
+    int* ticket;                // [4]                                                (zero block)
+    int* rowptr;                // [keys + 1] CSR offsets into entries
+    unsigned* cpre;             // [keys + 1] exclusive prefix of the cost
+    int* piece_start;           // [pieces + 1] linear start index of every piece
+    uint2* entries;             // fragment records
+};
+
+// fragment record: x = r | ph << 16 | pw0 << 21 | (npw - 1) << 26 | red << 29 ; y = key | (end - key) << 16 | smask << 24
+__device__ __forceinline__ uint2 pack_entry(int r, int ph, int pw0, int npw, int red, int key, int end, unsigned smask) {
+    uint2 e;
+    e.x = (unsigned)r | ((unsigned)ph << 16) | ((unsigned)pw0 << 21) | ((unsigned)(npw - 1) << 26) | ((unsigned)red << 29);
+    e.y = (unsigned)key | ((unsigned)(end - key) << 16) | (smask << 24);
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// axis samples, adjusted so that both taps are always inside the map
+// ------------------------------------------------------------------------------------------------
+struct AdjTap {
+    int   low;                  // low cell in [0, size - 2]
+    float l, h;                 // weights of cell low + 1 / cell low (0, 0 for a sample the reference skips)
+};
+
+// The reference clamps a sample on the last cell to low = high = size - 1 with weights (h, l) = (1, 0).  Reading
+// cells (size - 2, size - 1) with weights (0, 1) instead is the same sum term for term (x*1 and y*0 swap places in
+// the FMA chain; the zero products do not change any finite partial sum), and keeps every tap in the map.
+__device__ __forceinline__ AdjTap adj_axis(float v, int size) {
+    const AxisTap t = xfrom_axis(v, size);
+    AdjTap a;
+    a.low = t.low; a.l = t.l; a.h = t.h;
+    if (t.low >= size - 1) { a.low = size - 2; a.l = 1.f; a.h = 0.f; }
+    if (!t.valid) { a.l = 0.f; a.h = 0.f; }
+    return a;
+}
+
+// Enumerate the fragments of bin row `ph` of one RoI.  yl / xl: adjusted low cells per axis sample.
+// emit(strip, key, end, pw0, npw, smask, red, zero_owner)
+template <int SR, class Emit>
+__device__ __forceinline__ void enum_row(const int* yl, const int* xl, int ph, const StreamGeom& g, Emit&& emit) {
+    const int i0 = ph * SR, i1 = i0 + SR - 1;
+    int ngroups = 1;
+    int key[2], end[2];
+    unsigned ym[2];
+    key[0] = yl[i0]; end[0] = yl[i1] + 2; ym[0] = (1u << SR) - 1u;
+    key[1] = 0; end[1] = 0; ym[1] = 0;
+    if (SR == 2 && end[0] - key[0] > g.K) {          // rows cannot be resident together: one fragment per y sample
+        ngroups = 2;
+        end[0] = key[0] + 2; ym[0] = 1u;
+        key[1] = yl[i1]; end[1] = key[1] + 2; ym[1] = 2u;
+    }
+    constexpr unsigned kXFull = (1u << SR) - 1u;
+    for (int gi = 0; gi < ngroups; ++gi) {
+        int run_s = -1, run_pw0 = 0, run_n = 0;
+        unsigned run_xm = 0;
+        auto flush = [&]() {
+            if (run_n == 0) return;
+            unsigned smask;
+            if (SR == 1) smask = 1u;
+            else smask = ((ym[gi] & 1u) ? run_xm : 0u) | ((ym[gi] & 2u) ? (run_xm << 2) : 0u);
+            const bool red = (ym[gi] != kXFull) || (run_xm != kXFull);
+            const bool owner = red && (ym[gi] & 1u) && (run_xm & 1u);
+            emit(run_s, key[gi], end[gi], run_pw0, run_n, smask, red ? 1 : 0, owner);
+            run_n = 0;
+        };
+        auto push = [&](int s, unsigned xm, int pw) {
+            if (run_n > 0 && s == run_s && xm == run_xm && run_n < kFragBins && pw == run_pw0 + run_n) { ++run_n; return; }
+            flush();
+            run_s = s; run_xm = xm; run_pw0 = pw; run_n = 1;
+        };
+        for (int pw = 0; pw < g.PW; ++pw) {
+            const int j0 = pw * SR, j1 = j0 + SR - 1;
+            const int s0 = min(xl[j0] / g.WX, g.S - 1);
+            if (SR == 1 || xl[j1] + 1 <= s0 * g.WX + g.XB - 4) {
+                push(s0, kXFull, pw);
+            } else {                                   // x samples in different strips: one fragment per x sample
+                push(s0, 1u, pw);
+                push(min(xl[j1] / g.WX, g.S - 1), 2u, pw);
+            }
+        }
+        flush();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prepass 1: tables + histogram; last CTA: scan + partition
+// ------------------------------------------------------------------------------------------------
+template <int SR>
+__global__ void __launch_bounds__(kPrepThreads)
+stream_count(const float* __restrict__ rois, StreamGeom g, StreamWs ws) {
+    __shared__ int s_yl[kAxisMaxS], s_xl[kAxisMaxS];
+    __shared__ int s_last;
+    __shared__ unsigned s_h[kPrepThreads], s_c[kPrepThreads];
+    const int r = blockIdx.x, t = threadIdx.x;
+    const XfromRoi geo = xfrom_roi(rois + 5 * (size_t)r, g.scale, g.PH, g.PW, g.sr);
+    if (t < g.ny + g.nx) {
+        const bool isy = t < g.ny;
+        const int s = isy ? t : t - g.ny;
+        if (isy) {
+            const AdjTap a = adj_axis(xfrom_coord(geo.start_h, geo.bin_h, s / SR, s % SR, SR), g.H);
+            s_yl[s] = a.low;
+            uint4 e;
+            e.x = __float_as_uint(a.h); e.y = __float_as_uint(a.l);
+            e.z = (unsigned)((a.low % g.K) * g.row_bytes);
+            e.w = (unsigned)(((a.low + 1) % g.K) * g.row_bytes);
+            ws.ytab[(size_t)r * g.ny + s] = e;
+        } else {
+            const AdjTap a = adj_axis(xfrom_coord(geo.start_w, geo.bin_w, s / SR, s % SR, SR), g.W);
+            s_xl[s] = a.low;
+            uint4 e;
+            e.x = __float_as_uint(a.h); e.y = __float_as_uint(a.l);
+            e.z = (unsigned)(a.low * 4); e.w = 0u;
+            ws.xtab[(size_t)r * g.nx + s] = e;
+        }
+    }
+    __syncthreads();
+    const bool batch_ok = geo.batch >= 0 && geo.batch < g.N;
+    if (batch_ok && t < g.PH) {
+        const int kbase = geo.batch * g.S;
+        enum_row<SR>(s_yl, s_xl, t, g, [&](int s, int key, int end, int pw0, int npw, unsigned smask, int red, bool owner) {
+            const int k = (kbase + s) * g.H + key;
+            atomicAdd(&ws.hist[k], 1);
+            atomicAdd(&ws.cost[k], 2 + npw);
+            (void)end; (void)pw0; (void)smask; (void)red; (void)owner;
+        });
+    }
+    // ---- last CTA: CSR row pointers, cost prefix, piece boundaries
+    __threadfence();
+    __syncthreads();
+    if (t == 0) s_last = (atomicAdd(&ws.ticket[0], 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int keys = g.keys;
+    const int chunk = (keys + kPrepThreads - 1) / kPrepThreads;
+    const int b = min(keys, t * chunk), e = min(keys, b + chunk);
+    unsigned sh = 0, sc = 0;
+    for (int k = b; k < e; ++k) { sh += (unsigned)__ldcg(&ws.hist[k]); sc += (unsigned)__ldcg(&ws.cost[k]) + 2u; }
+    s_h[t] = sh; s_c[t] = sc;
+    __syncthreads();
+    if (t == 0) {
+        unsigned ah = 0, ac = 0;
+        for (int i = 0; i < kPrepThreads; ++i) { const unsigned h = s_h[i], c = s_c[i]; s_h[i] = ah; s_c[i] = ac; ah += h; ac += c; }
+        ws.rowptr[keys] = (int)ah;
+        ws.cpre[keys] = ac;
+    }
+    __syncthreads();
+    sh = s_h[t]; sc = s_c[t];
+    for (int k = b; k < e; ++k) {
+        ws.rowptr[k] = (int)sh; ws.cpre[k] = sc;
+        sh += (unsigned)__ldcg(&ws.hist[k]); sc += (unsigned)__ldcg(&ws.cost[k]) + 2u;
+    }
+    __threadfence();
+    __syncthreads();
+    // piece p starts where the cumulative cost over the linear order (column q, channel group, row) reaches p/pieces
+    const unsigned total = __ldcg(&ws.cpre[keys]);
+    const u64 grand = (u64)total * (u64)g.G;
+    for (int p = t; p <= g.pieces; p += kPrepThreads) {
+        int L;
+        if (p == 0) L = 0;
+        else if (p == g.pieces) L = g.Q * g.G * g.H;
+        else {
+            const u64 target = grand / (u64)g.pieces * (u64)p + (grand % (u64)g.pieces) * (u64)p / (u64)g.pieces;
+            int lo = 0, hi = g.Q - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if ((u64)g.G * (u64)__ldcg(&ws.cpre[(size_t)mid * g.H]) <= target) lo = mid; else hi = mid - 1;
+            }
+            const int q = lo;
+            const unsigned c0 = __ldcg(&ws.cpre[(size_t)q * g.H]);
+            const unsigned colsum = __ldcg(&ws.cpre[(size_t)(q + 1) * g.H]) - c0;      // >= H > 0
+            u64 rem = target - (u64)g.G * (u64)c0;
+            int gg = (int)(rem / colsum);
+            if (gg > g.G - 1) gg = g.G - 1;
+            rem -= (u64)gg * colsum;
+            int ylo = 0, yhi = g.H - 1;
+            while (ylo < yhi) {
+                const int mid = (ylo + yhi + 1) >> 1;
+                if ((u64)(__ldcg(&ws.cpre[(size_t)q * g.H + mid]) - c0) <= rem) ylo = mid; else yhi = mid - 1;
+            }
+            L = (q * g.G + gg) * g.H + ylo;
+        }
+        ws.piece_start[p] = L;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prepass 2: fragment records into the CSR; zero-fill of the elements that are accumulated with red.add
+// ------------------------------------------------------------------------------------------------
+template <int SR>
+__global__ void __launch_bounds__(kPrepThreads)
+stream_fill(const float* __restrict__ rois, StreamGeom g, StreamWs ws, float* __restrict__ out, const int* __restrict__ row_map) {
+    __shared__ int s_yl[kAxisMaxS], s_xl[kAxisMaxS];
+    __shared__ unsigned short s_zero[kAxisMaxS * kAxisMaxS];
+    __shared__ int s_nzero;
+    const int r = blockIdx.x, t = threadIdx.x;
+    const XfromRoi geo = xfrom_roi(rois + 5 * (size_t)r, g.scale, g.PH, g.PW, g.sr);
+    if (t == 0) s_nzero = 0;
+    if (t < g.ny + g.nx) {
+        const bool isy = t < g.ny;
+        const int s = isy ? t : t - g.ny;
+        if (isy) s_yl[s] = adj_axis(xfrom_coord(geo.start_h, geo.bin_h, s / SR, s % SR, SR), g.H).low;
+        else     s_xl[s] = adj_axis(xfrom_coord(geo.start_w, geo.bin_w, s / SR, s % SR, SR), g.W).low;
+    }
+    __syncthreads();
+    const bool batch_ok = geo.batch >= 0 && geo.batch < g.N;
+    const int bins = g.PH * g.PW;
+    if (batch_ok) {
+        if (t < g.PH) {
+            const int kbase = geo.batch * g.S;
+            enum_row<SR>(s_yl, s_xl, t, g, [&](int s, int key, int end, int pw0, int npw, unsigned smask, int red, bool owner) {
+                const int k = (kbase + s) * g.H + key;
+                const int pos = ws.rowptr[k] + atomicAdd(&ws.cursor[k], 1);
+                if (pos < g.max_entries) ws.entries[pos] = pack_entry(r, t, pw0, npw, red, key, end, smask);
+                atomicMax(&ws.maxend[k], end);
+                if (owner) {
+                    const int z = atomicAdd(&s_nzero, npw);
+                    for (int i = 0; i < npw; ++i) s_zero[z + i] = (unsigned short)(t * g.PW + pw0 + i);
+                }
+            });
+        }
+    } else {
+        for (int i = t; i < bins; i += kPrepThreads) s_zero[i] = (unsigned short)i;       // the reference would read out of bounds
+        if (t == 0) s_nzero = bins;
+    }
+    __syncthreads();
+    const int nz = s_nzero;
+    if (nz == 0) return;
+    float* out_r = out + (size_t)(row_map ? row_map[r] : r) * g.C * bins;
+    for (int idx = t; idx < g.C * nz; idx += kPrepThreads) {
+        const int c = idx / nz, k = idx - c * nz;
+        out_r[(size_t)c * bins + s_zero[k]] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// try_wait suspends the thread in hardware for a bounded time per attempt.  A wait that does not finish within ~2 s
+// of SM clocks is a protocol bug: trap (surfaces as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, unsigned bar, int x, int y, int c) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"((u64)map), "r"(bar), "r"(x), "r"(y), "r"(c) : "memory");
+}
+__device__ __forceinline__ float lds32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32_off4(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+struct StreamArgs {
+    const uint4* ytab;
+    const uint4* xtab;
+    const uint2* entries;
+    const int* rowptr;
+    const int* maxend;
+    const int* piece_start;
+    float* out;
+    const int* row_map;
+    int C, H, S, G, K, XB, WX, PH, PW, ny, nx, row_bytes;
+};
+
+// one item = the part of one (strip column q, channel group) that lies in this CTA's piece
+struct Item {
+    int n, s, g, ya, yb, e0, e1, yhi, kbase;
+};
+
+// Decode the item that starts at linear index L (all lanes of the calling warp; yhi by warp reduction).
+__device__ __forceinline__ Item decode_item(int L, int L1, const StreamArgs& a, int lane) {
+    Item it;
+    const int col = L / a.H;
+    it.ya = L - col * a.H;
+    const int q = col / a.G;
+    it.g = col - q * a.G;
+    it.n = q / a.S;
+    it.s = q - it.n * a.S;
+    it.yb = min(a.H, it.ya + (L1 - L));
+    it.kbase = q * a.H;
+    it.e0 = __ldg(&a.rowptr[it.kbase + it.ya]);
+    it.e1 = __ldg(&a.rowptr[it.kbase + it.yb]);
+    int m = 0;
+    if (it.e1 > it.e0) {
+        for (int y = it.ya + lane; y < it.yb; y += 32) m = max(m, __ldg(&a.maxend[it.kbase + y]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    it.yhi = m;
+    return it;
+}
+
+// Packed fp32x2 arithmetic (sm_100 FMUL2): both halves are independent IEEE-754 RN multiplications, i.e. bit-identical
+// to two __fmul_rn; used for the warp-uniform weight products only (it halves their issue slots).
+__device__ __forceinline__ u64 pack2f(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2f(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 mul2f(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+struct Taps { float v1, v2, v3, v4; };
+
+// the four taps of one sample for this lane's channel: rows (top, bottom) x columns (x_low, x_low + 1)
+__device__ __forceinline__ Taps load_taps(unsigned row_top, unsigned row_bot, unsigned xoff) {
+    Taps t;
+    const unsigned at = row_top + xoff, ab = row_bot + xoff;
+    t.v1 = lds32(at); t.v2 = lds32_off4(at); t.v3 = lds32(ab); t.v4 = lds32_off4(ab);
+    return t;
+}
+
+// One bilinear sample, the reference's rounding recipe:
+// val = FFMA(v4, w4, FFMA(v3, w3, FFMA(v1, w1, FMUL(v2, w2)))) with w1 = hy*hx, w2 = hy*lx, w3 = ly*hx, w4 = ly*lx.
+// hyhy = (hy, hy), lyly = (ly, ly), hxlx = (hx, lx) packed.
+__device__ __forceinline__ float sample_val(const Taps& t, u64 hyhy, u64 lyly, u64 hxlx) {
+    float w1, w2, w3, w4;
+    unpack2f(mul2f(hyhy, hxlx), w1, w2);
+    unpack2f(mul2f(lyly, hxlx), w3, w4);
+    return __fmaf_rn(t.v4, w4, __fmaf_rn(t.v3, w3, __fmaf_rn(t.v1, w1, __fmul_rn(t.v2, w2))));
+}
+
+template <int SR>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+roi_align_stream_fwd(const __grid_constant__ CUtensorMap tmap, const StreamArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    const unsigned ring = (smem_addr(smem_raw) + 127u) & ~127u;                 // TMA destinations: 128-byte aligned
+    unsigned char* ring_ptr = smem_raw + (ring - smem_addr(smem_raw));
+    float* stage_all = reinterpret_cast<float*>(ring_ptr + (size_t)a.K * a.row_bytes);
+    const unsigned bars = ring + (unsigned)a.K * (unsigned)a.row_bytes + kConsumerWarps * kStageWordsPerWarp * 4;
+    // full[k] at bars + 8k, empty[k] at bars + 8 * (kMaxSlots + k)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int k = 0; k < a.K; ++k) { mbar_init(bars + 8u * k, 1u); mbar_init(bars + 8u * (kMaxSlots + k), kConsumerWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const int L0 = __ldg(&a.piece_start[blockIdx.x]), L1 = __ldg(&a.piece_start[blockIdx.x + 1]);
+
+    if (warp == kConsumerWarps) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"((u64)&tmap) : "memory");
+        unsigned ephase = 0xffffffffu;                // waiting for parity 1 on a fresh barrier passes immediately
+        for (int L = L0; L < L1;) {
+            const Item it = decode_item(L, L1, a, lane);
+            L += it.yb - it.ya;
+            if (it.e1 <= it.e0) continue;
+            if (lane == 0) {
+                int slot = it.ya % a.K;
+                const int x0 = it.s * a.WX;
+                const int cbase = it.n * a.C + it.g * 32;
+                const unsigned oct_bytes = (unsigned)a.row_bytes >> 2;
+                for (int y = it.ya; y < it.yhi; ++y) {
+                    const unsigned full = bars + 8u * slot, empty = bars + 8u * (kMaxSlots + slot);
+                    mbar_wait(empty, (ephase >> slot) & 1u);
+                    ephase ^= 1u << slot;
+                    mbar_arrive_expect_tx(full, (unsigned)a.row_bytes);
+                    const unsigned dst = ring + (unsigned)slot * (unsigned)a.row_bytes;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) tma_load_3d(dst + i * oct_bytes, &tmap, full, x0 - i, y, cbase + 8 * i);
+                    if (++slot == a.K) slot = 0;
+                }
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // =============================== consumers ===============================
+    float* stage = stage_all + warp * kStageWordsPerWarp;
+    const unsigned lane_base = ring + (unsigned)(lane * a.XB + (lane >> 3)) * 4u;
+    const int bins = a.PH * a.PW;
+    unsigned fphase = 0u;
+    const int chsub = lane >> 3, fb = lane & 7;
+    constexpr float kInvCount = 1.f / (float)(SR * SR);
+
+    for (int L = L0; L < L1;) {
+        const Item it = decode_item(L, L1, a, lane);
+        L += it.yb - it.ya;
+        if (it.e1 <= it.e0) continue;
+        const unsigned lc = lane_base - (unsigned)(it.s * a.WX) * 4u;
+        int acq = it.ya, rel = it.ya;
+        int acq_slot = it.ya % a.K, rel_slot = acq_slot;
+        const int c0 = it.g * 32;
+
+        int e = it.e0 + warp;
+        uint2 ent = make_uint2(0u, 0u);
+        if (e < it.e1) ent = __ldg(&a.entries[e]);
+        while (e < it.e1) {
+            const uint2 cur = ent;
+            const int e_next = e + kConsumerWarps;
+            if (e_next < it.e1) ent = __ldg(&a.entries[e_next]);
+            const int r = cur.x & 0xffffu, ph = (cur.x >> 16) & 31u, pw0 = (cur.x >> 21) & 31u;
+            const int npw = (int)((cur.x >> 26) & 7u) + 1;
+            const bool red = (cur.x >> 29) & 1u;
+            const int key = cur.y & 0xffffu, end = key + (int)((cur.y >> 16) & 0xffu);
+            const unsigned smask = (cur.y >> 24) & 0xfu;
+            // axis tables of this fragment (uniform addresses: one sector each)
+            const uint4* yt = a.ytab + (size_t)r * a.ny + ph * SR;
+            const uint4* xt = a.xtab + (size_t)r * a.nx + pw0 * SR;
+            const uint4 yA = __ldg(yt);
+            uint4 yB = yA;
+            if (SR == 2) yB = __ldg(yt + 1);
+            uint4 xA = __ldg(xt), xB = xA;
+            if (SR == 2) xB = __ldg(xt + 1);
+            // rows below the key are no longer needed by this warp (entries are sorted by key)
+            if (rel < key) {
+                if (lane == 0) {
+                    int rs = rel_slot;
+                    for (int y = rel; y < key; ++y) { mbar_arrive(bars + 8u * (kMaxSlots + rs)); if (++rs == a.K) rs = 0; }
+                }
+                rel_slot = (rel_slot + (key - rel)) % a.K;
+                rel = key;
+            }
+            // rows [key, end) must be resident
+            while (acq < end) {
+                mbar_wait(bars + 8u * acq_slot, (fphase >> acq_slot) & 1u);
+                fphase ^= 1u << acq_slot;
+                ++acq;
+                if (++acq_slot == a.K) acq_slot = 0;
+            }
+            // row bases for this lane and the packed axis weights (uniform; hoisted out of the bin loop)
+            const unsigned rt0 = lc + yA.z, rb0 = lc + yA.w, rt1 = lc + yB.z, rb1 = lc + yB.w;
+            const u64 hh0 = pack2f(__uint_as_float(yA.x), __uint_as_float(yA.x)), ll0 = pack2f(__uint_as_float(yA.y), __uint_as_float(yA.y));
+            const u64 hh1 = pack2f(__uint_as_float(yB.x), __uint_as_float(yB.x)), ll1 = pack2f(__uint_as_float(yB.y), __uint_as_float(yB.y));
+            for (int b = 0; b < npw; ++b) {
+                const uint4 cxA = xA, cxB = xB;
+                if (b + 1 < npw) {
+                    xA = __ldg(xt + (b + 1) * SR);
+                    if (SR == 2) xB = __ldg(xt + (b + 1) * SR + 1);
+                }
+                const u64 wxA = pack2f(__uint_as_float(cxA.x), __uint_as_float(cxA.y));
+                const u64 wxB = pack2f(__uint_as_float(cxB.x), __uint_as_float(cxB.y));
+                float acc = 0.f;
+                if (SR == 1) {
+                    const Taps t0 = load_taps(rt0, rb0, cxA.z);
+                    acc = __fadd_rn(acc, sample_val(t0, hh0, ll0, wxA));
+                } else if (smask == 0xfu) {
+                    // all 16 taps are requested before the first one is used
+                    const Taps t0 = load_taps(rt0, rb0, cxA.z);
+                    const Taps t1 = load_taps(rt0, rb0, cxB.z);
+                    const Taps t2 = load_taps(rt1, rb1, cxA.z);
+                    const Taps t3 = load_taps(rt1, rb1, cxB.z);
+                    acc = __fadd_rn(acc, sample_val(t0, hh0, ll0, wxA));        // the reference's order: iy outer, ix inner
+                    acc = __fadd_rn(acc, sample_val(t1, hh0, ll0, wxB));
+                    acc = __fadd_rn(acc, sample_val(t2, hh1, ll1, wxA));
+                    acc = __fadd_rn(acc, sample_val(t3, hh1, ll1, wxB));
+                } else {
+                    if (smask & 1u) acc = __fadd_rn(acc, sample_val(load_taps(rt0, rb0, cxA.z), hh0, ll0, wxA));
+                    if (smask & 2u) acc = __fadd_rn(acc, sample_val(load_taps(rt0, rb0, cxB.z), hh0, ll0, wxB));
+                    if (smask & 4u) acc = __fadd_rn(acc, sample_val(load_taps(rt1, rb1, cxA.z), hh1, ll1, wxA));
+                    if (smask & 8u) acc = __fadd_rn(acc, sample_val(load_taps(rt1, rb1, cxB.z), hh1, ll1, wxB));
+                }
+                stage[b * kStageStride + lane] = __fmul_rn(acc, kInvCount);       // count 1 / 4: exact, == the reference's division
+            }
+            __syncwarp();
+            // flush: lanes = (channel within a group of 4, bin) -> a store's lanes are consecutive bins of one channel
+            if (fb < npw) {
+                const int orow = a.row_map ? __ldg(&a.row_map[r]) : r;
+                float* dst = a.out + ((size_t)orow * a.C + c0) * bins + ph * a.PW + pw0 + fb;
+                const float* src = stage + fb * kStageStride + chsub;
+                const int cmax = a.C - c0 - chsub;               // channel 4*cb + chsub is real iff 4*cb < cmax
+                if (!red) {
+#pragma unroll
+                    for (int cb = 0; cb < 8; ++cb)
+                        if (4 * cb < cmax) dst[(size_t)(4 * cb + chsub) * bins] = src[4 * cb];
+                } else {
+#pragma unroll
+                    for (int cb = 0; cb < 8; ++cb)
+                        if (4 * cb < cmax) atomicAdd(dst + (size_t)(4 * cb + chsub) * bins, src[4 * cb]);
+                }
+            }
+            __syncwarp();
+            e = e_next;
+        }
+        // item tail: stay in step with the producer (every warp waits for and releases every row of the item)
+        while (acq < it.yhi) {
+            mbar_wait(bars + 8u * acq_slot, (fphase >> acq_slot) & 1u);
+            fphase ^= 1u << acq_slot;
+            ++acq;
+            if (++acq_slot == a.K) acq_slot = 0;
+        }
+        if (lane == 0) {
+            int rs = rel_slot;
+            for (int y = rel; y < it.yhi; ++y) { mbar_arrive(bars + 8u * (kMaxSlots + rs)); if (++rs == a.K) rs = 0; }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: geometry, workspace, tensor map, launches
+// ------------------------------------------------------------------------------------------------
+size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct StreamLayout {
+    size_t ytab_off, xtab_off, zero_off, zero_bytes, rowptr_off, cpre_off, piece_off, entries_off, ws_bytes;
+};
+
+bool stream_geometry(int N, int R, int C, int H, int W, int PH, int PW, int sr, float scale, int sm_count, StreamGeom* g, StreamLayout* lay,
+                     unsigned* smem_bytes) {
+    if (sr < 1 || sr > 2 || PH * sr > kAxisMaxS || PW * sr > kAxisMaxS || PH > 31 || PW > 31) return false;
+    if (N <= 0 || R <= 0 || R > 65535 || H < 2 || W < 4 || (W & 3) || H > 65535) return false;
+    if ((long long)R * PH * PW * sr * sr >= (1LL << 28)) return false;
+    // ring budget: everything but the per-warp staging, the barriers and the alignment slack
+    const unsigned fixed = kConsumerWarps * kStageWordsPerWarp * 4 + 2 * kMaxSlots * 8 + 128;
+    const unsigned ring_budget = kSmemBudget - fixed;
+    int best_xb = 0, best_s = 0, best_wx = 0, best_k = 0;
+    long best_score = -1;
+    for (int xb = 36; xb <= 104; xb += 8) {                   // XB = 4 (mod 8): conflict-free channel stride
+        int k = (int)(ring_budget / (128u * (unsigned)xb));
+        if (k > kMaxSlots) k = kMaxSlots;
+        if (k < 16) continue;
+        const int hx = xb >= 60 ? 9 : (xb >= 44 ? 5 : 3);    // halo: bins whose x samples are <= hx + 1 cells apart stay whole
+        const int wx = xb - 3 - hx;
+        int s = 1;
+        while ((s - 1) * wx + xb - 3 < W) ++s;                // the last strip needs no halo
+        const long score = (long)s * xb;
+        if (best_score < 0 || score < best_score) { best_score = score; best_xb = xb; best_s = s; best_wx = wx; best_k = k; }
+    }
+    if (best_score < 0) return false;
+    g->N = N; g->R = R; g->C = C; g->H = H; g->W = W; g->PH = PH; g->PW = PW; g->sr = sr;
+    g->ny = PH * sr; g->nx = PW * sr;
+    g->XB = best_xb; g->WX = best_wx; g->S = best_s; g->K = best_k;
+    g->row_bytes = 128 * best_xb;
+    g->Q = N * best_s;
+    if ((long long)g->Q * H >= (1LL << 24)) return false;
+    g->keys = g->Q * H;
+    g->G = (C + 31) / 32;
+    if (g->G < 1) g->G = 1;
+    if ((long long)g->Q * g->G * H >= (1LL << 30)) return false;
+    g->pieces = sm_count > 0 ? sm_count : kNumSMs;
+    g->max_entries = R * PH * PW * sr * sr;                    // worst case: every sample its own fragment
+    g->scale = scale;
+    size_t off = 0;
+    lay->ytab_off = off; off = align_up_sz(off + (size_t)R * g->ny * 16, 256);
+    lay->xtab_off = off; off = align_up_sz(off + (size_t)R * g->nx * 16, 256);
+    lay->zero_off = off; lay->zero_bytes = align_up_sz(((size_t)4 * g->keys + 4) * 4, 256); off += lay->zero_bytes;
+    lay->rowptr_off = off; off = align_up_sz(off + ((size_t)g->keys + 1) * 4, 256);
+    lay->cpre_off = off; off = align_up_sz(off + ((size_t)g->keys + 1) * 4, 256);
+    lay->piece_off = off; off = align_up_sz(off + ((size_t)g->pieces + 1) * 4, 256);
+    lay->entries_off = off; off = align_up_sz(off + (size_t)g->max_entries * 8, 256);
+    lay->ws_bytes = off;
+    *smem_bytes = (unsigned)g->K * (unsigned)g->row_bytes + fixed;
+    return true;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+struct DeviceInfo {
+    bool ok = false;
+    int sm_count = 0;
+};
+
+// per device, set up once under a lock (the reference calls these ops from one host thread per GPU)
+bool stream_device_info(int* sm_count) {
+    static std::mutex mu;
+    static DeviceInfo info[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!info[dev].ok) {
+        const int max_dyn = (int)kSmemBudget;
+        if (cudaFuncSetAttribute(roi_align_stream_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != cudaSuccess ||
+            cudaFuncSetAttribute(roi_align_stream_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != cudaSuccess ||
+            cudaDeviceGetAttribute(&info[dev].sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return false;
+        }
+        info[dev].ok = true;
+    }
+    *sm_count = info[dev].sm_count;
+    return true;
+}
+
+}  // namespace
+
+size_t roi_align_stream_workspace_bytes(int N, int R, int H, int W, int PH, int PW, int sr) {
+    StreamGeom g;
+    StreamLayout lay;
+    unsigned smem = 0;
+    if (!stream_geometry(N, R, 32, H, W, PH, PW, sr, 1.f, kNumSMs, &g, &lay, &smem)) return 0;
+    return lay.ws_bytes;
+}
+
+// returns B200_ROI_OK when the streaming path ran; 1000 when it does not apply (caller falls back)
+int roi_align_forward_stream(const float* bottom, float scale, int N, int R, int H, int W, int C, int PH, int PW, int sr,
+                             const float* rois, float* top, const int* row_map, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (workspace == nullptr || C <= 0 || ((uintptr_t)bottom & 15u)) return 1000;
+    if ((long long)N * C >= (1LL << 31) || (long long)R * C * PH * PW >= (1LL << 31)) return 1000;
+    int sm_count = 0;
+    if (!stream_device_info(&sm_count)) return 1000;
+    StreamGeom g;
+    StreamLayout lay;
+    unsigned smem = 0;
+    if (!stream_geometry(N, R, C, H, W, PH, PW, sr, scale, sm_count, &g, &lay, &smem)) return 1000;
+    if (workspace_bytes < lay.ws_bytes) return 1000;
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return 1000;
+
+    CUtensorMap tmap;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * (cuuint64_t)C};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * (cuuint64_t)H * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)g.XB, 1u, 8u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)bottom, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 1000;
+
+    unsigned char* wsb = (unsigned char*)workspace;
+    StreamWs ws;
+    ws.ytab = (uint4*)(wsb + lay.ytab_off);
+    ws.xtab = (uint4*)(wsb + lay.xtab_off);
+    int* zero = (int*)(wsb + lay.zero_off);
+    ws.hist = zero; ws.cost = zero + g.keys; ws.cursor = zero + 2 * (size_t)g.keys; ws.maxend = zero + 3 * (size_t)g.keys;
+    ws.ticket = zero + 4 * (size_t)g.keys;
+    ws.rowptr = (int*)(wsb + lay.rowptr_off);
+    ws.cpre = (unsigned*)(wsb + lay.cpre_off);
+    ws.piece_start = (int*)(wsb + lay.piece_off);
+    ws.entries = (uint2*)(wsb + lay.entries_off);
+
+    cudaError_t err = cudaMemsetAsync(zero, 0, lay.zero_bytes, stream);
+    if (err != cudaSuccess) return (int)err;
+    StreamArgs a;
+    a.ytab = ws.ytab; a.xtab = ws.xtab; a.entries = ws.entries; a.rowptr = ws.rowptr; a.maxend = ws.maxend;
+    a.piece_start = ws.piece_start; a.out = top; a.row_map = row_map;
+    a.C = C; a.H = H; a.S = g.S; a.G = g.G; a.K = g.K; a.XB = g.XB; a.WX = g.WX; a.PH = PH; a.PW = PW; a.ny = g.ny; a.nx = g.nx;
+    a.row_bytes = g.row_bytes;
+    if (sr == 1) {
+        stream_count<1><<<R, kPrepThreads, 0, stream>>>(rois, g, ws);
+        stream_fill<1><<<R, kPrepThreads, 0, stream>>>(rois, g, ws, top, row_map);
+        roi_align_stream_fwd<1><<<g.pieces, kStreamThreads, smem, stream>>>(tmap, a);
+    } else {
+        stream_count<2><<<R, kPrepThreads, 0, stream>>>(rois, g, ws);
+        stream_fill<2><<<R, kPrepThreads, 0, stream>>>(rois, g, ws, top, row_map);
+        roi_align_stream_fwd<2><<<g.pieces, kStreamThreads, smem, stream>>>(tmap, a);
+    }
+    return finish_launch(3);
+}
+
+}  // namespace b200

@@ -388,8 +388,7 @@ int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int 
     // The bins the main kernel accumulates into must start at zero.  With a dense output one memset of the whole tensor
     // (25.7 MB at cfg2, ~4 us) is cheaper than the prepass storing ~1.3 M scattered zeros; the indexed variant shares
     // its output tensor with other calls and zero-fills exactly its own split bins.  B200_FWD_ZERO=bins forces the latter.
-    const char* e_zero = getenv("B200_FWD_ZERO");
-    const bool whole = row_map == nullptr && !(e_zero && e_zero[0] == 'b');
+    const bool whole = row_map == nullptr && option_get(kOptFwdZero) != 'b';
     if (whole) {
         err = cudaMemsetAsync(top, 0, sizeof(float) * (size_t)R * C * PH * PW, stream);
         if (err != cudaSuccess) return (int)err;

@@ -163,6 +163,12 @@ B200_API int b200_nms(const float* boxes_dev, int boxes_num, int boxes_dim, floa
 /* ---- introspection used by the benchmark / tests (no compute) ----------------------------------
  * Number of kernel launches the library has enqueued since load (all entry points). */
 B200_API unsigned long long b200_roi_ops_launch_count(void);
+/* Path-selection switches (A/B runs and tests): name is one of "B200_ROI_ALIGN_PATH" (auto|generic|tiled|stream),
+ * "B200_ROI_ALIGN_BWD_PATH" (auto|generic|nhwc|rows), "B200_ROI_ALIGN_BWD_CPL" (4|2), "B200_FWD_ZERO" (dense|bins),
+ * "B200_NMS_SCAN" (resolver|simple); value NULL or "" restores the default.  Each switch takes its initial value from the
+ * environment variable of the same name, read once at first use -- no entry point calls getenv() on the hot path.
+ * Returns 0, or B200_ROI_EINVAL for an unknown name. */
+B200_API int b200_roi_ops_set_option(const char* name, const char* value);
 /* Debug: register (or clear with NULL) a device buffer of 8 x uint64 into which the tiled RoIAlign forward
  * adds per-warp clock64 deltas [staging, compute, end-of-item wait, warp-items, RoI items, 8-bin groups, max compute]. */
 B200_API void b200_roi_ops_debug_timing_buffer(void* device_u64x16);

@@ -24,3 +24,19 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def lib_option():
+    """Set path-selection switches of libb200_roi_ops.so for one test (b200_roi_ops_set_option); restored to the default
+    afterwards.  The library reads the environment only once, at first use, so tests cannot steer it with setenv."""
+    from detectron.pytorch_b200 import _lib
+    touched = []
+
+    def set_option(name, value):
+        _lib.set_option(name, value)
+        touched.append(name)
+
+    yield set_option
+    for name in touched:
+        _lib.set_option(name, None)

@@ -36,7 +36,7 @@ def test_sm100a_cubin_embedded():
 
 def test_argument_validation_without_gpu():
     lib = _lib.load()
-    assert lib.b200_roi_ops_abi_version() == 2
+    assert lib.b200_roi_ops_abi_version() == 3
     EINVAL = -1
     # negative / zero dimensions and null pointers are rejected before any CUDA call
     assert lib.b200_roi_align_forward(None, 0.25, 1, 4, 0, 10, 3, 7, 7, 2, None, None, None) == EINVAL
@@ -53,7 +53,7 @@ def test_argument_validation_without_gpu():
     assert lib.b200_nms_workspace_bytes(64) == (64 + 64) * 8
 
 
-def test_workspace_sizing_is_host_arithmetic(monkeypatch):
+def test_workspace_sizing_is_host_arithmetic(lib_option):
     lib = _lib.load()
     # forward fast path: per-RoI tables + per-tile work lists; 0 when the parameters are outside the fast path
     w = lib.b200_roi_align_workspace_bytes(1, 512, 200, 272, 7, 7, 2)
@@ -64,11 +64,12 @@ def test_workspace_sizing_is_host_arithmetic(monkeypatch):
     # backward, row-stationary gather path: tables + per-row unit lists + a channel-innermost copy of dY
     wb = lib.b200_roi_align_backward_workspace_bytes(1, 512, 256, 200, 272, 7, 7, 2)
     assert 512 * 256 * 49 * 4 < wb < 512 * 256 * 49 * 4 + (4 << 20) and wb % 256 == 0
-    monkeypatch.setenv("B200_ROI_ALIGN_BWD_PATH", "nhwc")     # vector-reduction path: one channel-innermost scratch image of dX
+    lib_option("B200_ROI_ALIGN_BWD_PATH", "nhwc")     # vector-reduction path: one channel-innermost scratch image of dX
     assert lib.b200_roi_align_backward_workspace_bytes(1, 512, 256, 200, 272, 7, 7, 2) == 256 * 200 * 272 * 4
-    monkeypatch.setenv("B200_ROI_ALIGN_BWD_PATH", "generic")
+    lib_option("B200_ROI_ALIGN_BWD_PATH", "generic")
     assert lib.b200_roi_align_backward_workspace_bytes(1, 512, 256, 200, 272, 7, 7, 2) == 0
-    monkeypatch.delenv("B200_ROI_ALIGN_BWD_PATH")
+    lib_option("B200_ROI_ALIGN_BWD_PATH", None)
+    assert lib.b200_roi_ops_set_option(b"NO_SUCH_SWITCH", b"x") == -1
     assert lib.b200_roi_align_backward_workspace_bytes(0, 512, 256, 200, 272, 7, 7, 2) == 0
     assert lib.b200_roi_align_backward_workspace_bytes(1, 512, 252, 200, 272, 7, 7, 2) == 252 * 200 * 272 * 4     # C % 64 != 0 -> NHWC path
     assert lib.b200_roi_align_backward_workspace_bytes(1, 8, 256, 200, 272, 7, 7, 2) == 0      # tiny gather volume -> scalar atomics
