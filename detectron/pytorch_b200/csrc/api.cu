@@ -9,7 +9,7 @@ namespace b200 {
 unsigned long long g_launch_count = 0;
 
 static const char* const kOptionNames[kNumOptions] = {"B200_ROI_ALIGN_PATH", "B200_ROI_ALIGN_BWD_PATH", "B200_ROI_ALIGN_BWD_CPL",
-                                                      "B200_FWD_ZERO", "B200_NMS_SCAN"};
+                                                      "B200_FWD_ZERO", "B200_NMS_SCAN", "B200_STREAM_STAGE"};
 static int g_options[kNumOptions];
 static std::once_flag g_options_once;
 
@@ -49,6 +49,7 @@ int proposal_decode(const float*, const float*, const long long*, const float*, 
 size_t roi_align_tiled_workspace_bytes(int, int, int, int, int, int, int);
 void roi_align_tiled_set_timing_buffer(unsigned long long*);
 void nms_set_timing_buffer(unsigned long long*);
+void roi_align_stream_set_debug_buffer(unsigned long long*);
 int roi_align_forward_tiled(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
 size_t roi_align_stream_workspace_bytes(int, int, int, int, int, int, int);
 int roi_align_forward_stream(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
@@ -137,6 +138,7 @@ int b200_roi_ops_set_option(const char* name, const char* value) { return option
 void b200_roi_ops_debug_timing_buffer(void* device_u64x16) {
     roi_align_tiled_set_timing_buffer((unsigned long long*)device_u64x16);
     nms_set_timing_buffer((unsigned long long*)device_u64x16);
+    roi_align_stream_set_debug_buffer((unsigned long long*)device_u64x16);      // -DB200_STREAM_DEBUG builds only
 }
 
 size_t b200_roi_align_workspace_bytes(int batch_size, int num_rois, int height, int width, int aligned_height,

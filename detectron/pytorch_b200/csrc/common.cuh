@@ -27,6 +27,7 @@ enum Option {
     kOptBwdCpl,           // B200_ROI_ALIGN_BWD_CPL   = 4 | 2
     kOptFwdZero,          // B200_FWD_ZERO            = dense | bins
     kOptNmsScan,          // B200_NMS_SCAN            = resolver | simple
+    kOptStreamStage,      // B200_STREAM_STAGE        = async (cp.async) | regs (LDG -> registers -> STS)
     kNumOptions
 };
 int option_get(Option which);

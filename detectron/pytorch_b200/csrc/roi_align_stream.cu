@@ -1,19 +1,19 @@
-// roi_align_stream.cu -- Caffe2-exact RoIAlign FORWARD, "streaming strip" fast path (TMA + mbarrier ring).
+// roi_align_stream.cu -- Caffe2-exact RoIAlign FORWARD, "streaming strip" fast path (cp.async + mbarrier ring).
 //
 // The feature map is cut into vertical strips of WX columns (+ a halo); one persistent CTA per SM owns a
 // contiguous piece of the linear space (image, strip, 32-channel group, row) and streams the rows of its
-// strips top to bottom through a ring of K row slots in shared memory.  Rows are fetched by TMA
-// (cp.async.bulk.tensor, one 3-D box = 8 channels x 1 row x XB columns per instruction, 4 per row), signalled
-// on per-slot mbarriers; a producer warp runs ahead of 16 consumer warps, so loading overlaps the arithmetic
-// completely and no thread ever stages a feature value through registers.
+// strips top to bottom through a ring of K row slots in shared memory.  Four producer warps fetch rows with
+// 4-byte cp.async (LDGSTS: global -> shared without a register round trip, 128-byte coalesced per warp) and
+// signal per-slot mbarriers (cp.async.mbarrier.arrive); they run ahead of 16 consumer warps, which release
+// slots on a second set of mbarriers, so loading overlaps the arithmetic completely.
 //
-// Shared-memory layout of one row slot: [32 channels][XB columns] as TMA writes it (x innermost), with the
-// box of channel octet i (channels 8i..8i+7) started i columns to the LEFT of the strip.  With XB = 4 (mod 8)
-// the word address of (channel c, column x) is c*XB + (c >> 3) + (x - x0): as c runs over a warp's 32 lanes
-// the bank is 4*((c & 7) * odd) + (c >> 3) + const -- a bijection.  So the compute mapping is
-// lane = channel, one warp = one bilinear tap of one sample for 32 channels per conflict-free LDS.32, and all
-// addressing / weights are warp-uniform.  (A transposed [cell][channel] layout would need a register-staged
-// transpose; TMA cannot interleave channels that are H*W apart in global memory.)
+// Shared-memory layout of one row slot: [32 channels][SX columns], SX odd.  The compute mapping is
+// lane = channel: one warp evaluates one bilinear tap of one sample for 32 channels with ONE conflict-free
+// LDS.32 (bank = c * SX + x), and all addressing / weights are warp-uniform.
+// Why not TMA (cp.async.bulk.tensor): measured on this B200 (tools/tma_probe.cu) a tile load whose innermost
+// start coordinate is not 16-byte aligned faults, and with 16-byte placement granularity every channel row would
+// start at a bank that is a multiple of 4 -- a lane = channel access would hit at most 8 banks (4-way conflict).
+// The 4-byte cp.async can place a row at any word, which is what the odd channel stride needs.
 //
 // Work = "fragments": up to 8 consecutive bins of one bin row of one RoI, keyed by the first feature row
 // they read.  A fragment is processed by ONE warp when the rows [key, end) it needs are resident, so every
@@ -30,7 +30,6 @@
 //
 // Semantics: lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu (reference) :16-63, :65-121.
 #include "common.cuh"
-#include <cuda.h>
 #include <mutex>
 #include <stdlib.h>
 
@@ -39,7 +38,8 @@ namespace b200 {
 namespace {
 
 constexpr int kConsumerWarps = 16;
-constexpr int kStreamThreads = 32 * (kConsumerWarps + 1);     // + the TMA producer warp
+constexpr int kProducerWarps = 4;
+constexpr int kStreamThreads = 32 * (kConsumerWarps + kProducerWarps);
 constexpr int kFragBins = 8;                                  // bins per fragment (one flush)
 constexpr int kStageStride = 36;                              // words per staged bin: conflict-free both ways
 constexpr int kStageWordsPerWarp = kFragBins * kStageStride;
@@ -50,11 +50,27 @@ constexpr unsigned kSmemBudget = 227u * 1024u;
 
 typedef unsigned long long u64;
 
+// Debug build (-DB200_STREAM_DEBUG, tools/stream_debug.py): every warp leaves progress markers in a HOST-pinned buffer
+// registered with b200_roi_ops_debug_timing_buffer(), so that they survive a trap.  Compiled out by default.
+#ifdef B200_STREAM_DEBUG
+__device__ u64* g_stream_dbg = nullptr;
+#define SDBG(slot, val)                                                                                      \
+    do {                                                                                                     \
+        if (g_stream_dbg != nullptr && (threadIdx.x & 31) == 0) {                                            \
+            volatile u64* dbg_p = g_stream_dbg + ((size_t)blockIdx.x * 17 + (threadIdx.x >> 5)) * 8;        \
+            dbg_p[slot] = (u64)(val);                                                                        \
+            __threadfence_system();                                                                          \
+        }                                                                                                    \
+    } while (0)
+#else
+#define SDBG(slot, val) do { } while (0)
+#endif
+
 struct StreamGeom {
     int N, R, C, H, W, PH, PW, sr;
     int ny, nx;
-    int XB, WX, S, K;           // box width, strip core width, strips per image, ring depth
-    int row_bytes;              // bytes of one ring slot = 32 * XB * 4
+    int SX, WX, S, K;           // columns held per row (odd, 32 m + 1), strip core width, strips per image, ring depth
+    int row_bytes;              // bytes of one ring slot = 32 * SX * 4
     int Q, keys;                // strip columns = N * S, keys = Q * H
     int G;                      // 32-channel groups
     int pieces;                 // persistent CTAs
@@ -141,7 +157,7 @@ __device__ __forceinline__ void enum_row(const int* yl, const int* xl, int ph, c
         for (int pw = 0; pw < g.PW; ++pw) {
             const int j0 = pw * SR, j1 = j0 + SR - 1;
             const int s0 = min(xl[j0] / g.WX, g.S - 1);
-            if (SR == 1 || xl[j1] + 1 <= s0 * g.WX + g.XB - 4) {
+            if (SR == 1 || xl[j1] + 1 <= s0 * g.WX + g.SX - 1) {
                 push(s0, kXFull, pw);
             } else {                                   // x samples in different strips: one fragment per x sample
                 push(s0, 1u, pw);
@@ -304,7 +320,7 @@ stream_fill(const float* __restrict__ rois, StreamGeom g, StreamWs ws, float* __
 }
 
 // ------------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + TMA
+// PTX helpers: mbarrier + cp.async
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -312,9 +328,6 @@ __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
 }
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
     unsigned ok;
@@ -328,17 +341,23 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
 }
 // try_wait suspends the thread in hardware for a bounded time per attempt.  A wait that does not finish within ~2 s
 // of SM clocks is a protocol bug: trap (surfaces as a launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity, unsigned tag = 0u) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (clock64() - t0 > 4000000000LL) {
+            SDBG(6, 0xDEAD000000000000ull | ((u64)tag << 16) | ((u64)parity << 8) | (u64)((bar >> 3) & 0xff));
+            __trap();
+        }
     }
 }
-__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, unsigned bar, int x, int y, int c) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"((u64)map), "r"(bar), "r"(x), "r"(y), "r"(c) : "memory");
+// 4-byte cp.async (LDGSTS): global -> shared without registers.  ok == false copies nothing and zero-fills the word.
+__device__ __forceinline__ void cp_async4(unsigned dst, const float* src, bool ok) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive(unsigned bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ float lds32(unsigned addr) {
     float v;
@@ -358,9 +377,10 @@ struct StreamArgs {
     const int* rowptr;
     const int* maxend;
     const int* piece_start;
+    const float* bottom;
     float* out;
     const int* row_map;
-    int C, H, S, G, K, XB, WX, PH, PW, ny, nx, row_bytes;
+    int C, H, W, S, G, K, SX, WX, PH, PW, ny, nx, row_bytes;
 };
 
 // one item = the part of one (strip column q, channel group) that lies in this CTA's piece
@@ -417,57 +437,117 @@ __device__ __forceinline__ float sample_val(const Taps& t, u64 hyhy, u64 lyly, u
     return __fmaf_rn(t.v4, w4, __fmaf_rn(t.v3, w3, __fmaf_rn(t.v1, w1, __fmul_rn(t.v2, w2))));
 }
 
-template <int SR>
+// Stage row y of one (image, strip, channel group) into a ring slot: M full 32-column chunks per channel
+// (lane = column: 128-byte coalesced) plus the last column x = 32 M for all channels at once (lane = channel).
+// ASYNC: 4-byte cp.async; otherwise LDG -> registers -> STS in batches of 8 channels.
+template <int M, bool ASYNC>
+__device__ __forceinline__ void stage_row(const float* __restrict__ src_row, size_t plane, unsigned dst, int SX, int xw, int cvalid,
+                                          int lane, unsigned full_bar) {
+    // src_row: (channel 0, row y, column x0); xw = number of valid columns from x0; cvalid = number of real channels
+    if (ASYNC) {
+#pragma unroll 4
+        for (int c = 0; c < 32; ++c) {
+            const bool cok = c < cvalid;
+            const float* sc = src_row + (size_t)(cok ? c : 0) * plane;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int x = lane + 32 * m;
+                const bool ok = cok && x < xw;
+                cp_async4(dst + (unsigned)(c * SX + x) * 4u, sc + (ok ? x : 0), ok);
+            }
+        }
+        {
+            const bool ok = lane < cvalid && 32 * M < xw;
+            cp_async4(dst + (unsigned)(lane * SX + 32 * M) * 4u, src_row + (ok ? (size_t)lane * plane + 32 * M : 0), ok);
+        }
+        cp_async_arrive(full_bar);
+    } else {
+        for (int c8 = 0; c8 < 32; c8 += 8) {
+            float v[8][M];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool cok = c8 + j < cvalid;
+                const float* sc = src_row + (size_t)(cok ? c8 + j : 0) * plane;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const int x = lane + 32 * m;
+                    v[j][m] = (cok && x < xw) ? __ldcs(sc + x) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int m = 0; m < M; ++m)
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + (unsigned)((c8 + j) * SX + lane + 32 * m) * 4u), "f"(v[j][m]) : "memory");
+        }
+        {
+            const bool ok = lane < cvalid && 32 * M < xw;
+            const float t = ok ? __ldcs(src_row + (size_t)lane * plane + 32 * M) : 0.f;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + (unsigned)(lane * SX + 32 * M) * 4u), "f"(t) : "memory");
+        }
+        mbar_arrive(full_bar);
+    }
+}
+
+template <int SR, int M, bool ASYNC>
 __global__ void __launch_bounds__(kStreamThreads, 1)
-roi_align_stream_fwd(const __grid_constant__ CUtensorMap tmap, const StreamArgs a) {
+roi_align_stream_fwd(const StreamArgs a) {
     extern __shared__ unsigned char smem_raw[];
-    const unsigned ring = (smem_addr(smem_raw) + 127u) & ~127u;                 // TMA destinations: 128-byte aligned
+    const unsigned ring = (smem_addr(smem_raw) + 127u) & ~127u;
     unsigned char* ring_ptr = smem_raw + (ring - smem_addr(smem_raw));
     float* stage_all = reinterpret_cast<float*>(ring_ptr + (size_t)a.K * a.row_bytes);
     const unsigned bars = ring + (unsigned)a.K * (unsigned)a.row_bytes + kConsumerWarps * kStageWordsPerWarp * 4;
-    // full[k] at bars + 8k, empty[k] at bars + 8 * (kMaxSlots + k)
+    // full[k] at bars + 8k (32 arrivals: the lanes of the producer warp that staged the row),
+    // empty[k] at bars + 8 * (kMaxSlots + k) (one arrival per consumer warp)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
-        for (int k = 0; k < a.K; ++k) { mbar_init(bars + 8u * k, 1u); mbar_init(bars + 8u * (kMaxSlots + k), kConsumerWarps); }
+        for (int k = 0; k < a.K; ++k) { mbar_init(bars + 8u * k, 32u); mbar_init(bars + 8u * (kMaxSlots + k), kConsumerWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
     const int L0 = __ldg(&a.piece_start[blockIdx.x]), L1 = __ldg(&a.piece_start[blockIdx.x + 1]);
+    SDBG(0, 1); SDBG(1, ((u64)(unsigned)L0 << 32) | (unsigned)L1);
 
-    if (warp == kConsumerWarps) {
-        // =============================== TMA producer ===============================
-        if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"((u64)&tmap) : "memory");
+    if (warp >= kConsumerWarps) {
+        // =============================== producers ===============================
+        // Row i of the CTA's row stream (all items, in order) is staged by producer warp i % kProducerWarps.  Every
+        // producer tracks the phase of every slot (one flip per row of the stream) but waits only for its own rows.
+        const int pw = warp - kConsumerWarps;
         unsigned ephase = 0xffffffffu;                // waiting for parity 1 on a fresh barrier passes immediately
+        int turn = 0;                                 // stream row index modulo kProducerWarps
+        const size_t plane = (size_t)a.H * a.W;
         for (int L = L0; L < L1;) {
             const Item it = decode_item(L, L1, a, lane);
             L += it.yb - it.ya;
+            SDBG(2, ((u64)it.ya << 48) | ((u64)it.yb << 32) | ((u64)it.yhi << 16) | (u64)(it.e1 - it.e0));
             if (it.e1 <= it.e0) continue;
-            if (lane == 0) {
-                int slot = it.ya % a.K;
-                const int x0 = it.s * a.WX;
-                const int cbase = it.n * a.C + it.g * 32;
-                const unsigned oct_bytes = (unsigned)a.row_bytes >> 2;
-                for (int y = it.ya; y < it.yhi; ++y) {
+            int slot = it.ya % a.K;
+            const int x0 = it.s * a.WX;
+            const int c0 = it.g * 32;
+            const int cvalid = min(32, a.C - c0);
+            const int xw = a.W - x0;
+            const float* src = a.bottom + ((size_t)it.n * a.C + c0) * plane + (size_t)it.ya * a.W + x0;
+            for (int y = it.ya; y < it.yhi; ++y) {
+                if (turn == pw) {
                     const unsigned full = bars + 8u * slot, empty = bars + 8u * (kMaxSlots + slot);
-                    mbar_wait(empty, (ephase >> slot) & 1u);
-                    ephase ^= 1u << slot;
-                    mbar_arrive_expect_tx(full, (unsigned)a.row_bytes);
-                    const unsigned dst = ring + (unsigned)slot * (unsigned)a.row_bytes;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) tma_load_3d(dst + i * oct_bytes, &tmap, full, x0 - i, y, cbase + 8 * i);
-                    if (++slot == a.K) slot = 0;
+                    mbar_wait(empty, (ephase >> slot) & 1u, 0x1000u + (unsigned)y);
+                    SDBG(4, ((u64)y << 32) | (u64)slot);
+                    stage_row<M, ASYNC>(src, plane, ring + (unsigned)slot * (unsigned)a.row_bytes, a.SX, xw, cvalid, lane, full);
                 }
+                ephase ^= 1u << slot;
+                if (++slot == a.K) slot = 0;
+                if (++turn == kProducerWarps) turn = 0;
+                src += a.W;
             }
-            __syncwarp();
         }
+        SDBG(0, 9);
         return;
     }
 
     // =============================== consumers ===============================
     float* stage = stage_all + warp * kStageWordsPerWarp;
-    const unsigned lane_base = ring + (unsigned)(lane * a.XB + (lane >> 3)) * 4u;
+    const unsigned lane_base = ring + (unsigned)(lane * a.SX) * 4u;
     const int bins = a.PH * a.PW;
     unsigned fphase = 0u;
     const int chsub = lane >> 3, fb = lane & 7;
@@ -476,7 +556,9 @@ roi_align_stream_fwd(const __grid_constant__ CUtensorMap tmap, const StreamArgs 
     for (int L = L0; L < L1;) {
         const Item it = decode_item(L, L1, a, lane);
         L += it.yb - it.ya;
+        SDBG(2, ((u64)it.ya << 48) | ((u64)it.yb << 32) | ((u64)it.yhi << 16) | (u64)(it.e1 - it.e0));
         if (it.e1 <= it.e0) continue;
+        SDBG(0, 2);
         const unsigned lc = lane_base - (unsigned)(it.s * a.WX) * 4u;
         int acq = it.ya, rel = it.ya;
         int acq_slot = it.ya % a.K, rel_slot = acq_slot;
@@ -512,12 +594,14 @@ roi_align_stream_fwd(const __grid_constant__ CUtensorMap tmap, const StreamArgs 
                 rel = key;
             }
             // rows [key, end) must be resident
+            SDBG(3, ((u64)cur.x << 32) | (u64)cur.y);
             while (acq < end) {
-                mbar_wait(bars + 8u * acq_slot, (fphase >> acq_slot) & 1u);
+                mbar_wait(bars + 8u * acq_slot, (fphase >> acq_slot) & 1u, 0x2000u + (unsigned)acq);
                 fphase ^= 1u << acq_slot;
                 ++acq;
                 if (++acq_slot == a.K) acq_slot = 0;
             }
+            SDBG(0, 4);
             // row bases for this lane and the packed axis weights (uniform; hoisted out of the bin loop)
             const unsigned rt0 = lc + yA.z, rb0 = lc + yA.w, rt1 = lc + yB.z, rb1 = lc + yB.w;
             const u64 hh0 = pack2f(__uint_as_float(yA.x), __uint_as_float(yA.x)), ll0 = pack2f(__uint_as_float(yA.y), __uint_as_float(yA.y));
@@ -573,8 +657,9 @@ roi_align_stream_fwd(const __grid_constant__ CUtensorMap tmap, const StreamArgs 
             e = e_next;
         }
         // item tail: stay in step with the producer (every warp waits for and releases every row of the item)
+        SDBG(0, 5);
         while (acq < it.yhi) {
-            mbar_wait(bars + 8u * acq_slot, (fphase >> acq_slot) & 1u);
+            mbar_wait(bars + 8u * acq_slot, (fphase >> acq_slot) & 1u, 0x3000u + (unsigned)acq);
             fphase ^= 1u << acq_slot;
             ++acq;
             if (++acq_slot == a.K) acq_slot = 0;
@@ -584,7 +669,9 @@ roi_align_stream_fwd(const __grid_constant__ CUtensorMap tmap, const StreamArgs 
             for (int y = rel; y < it.yhi; ++y) { mbar_arrive(bars + 8u * (kMaxSlots + rs)); if (++rs == a.K) rs = 0; }
         }
         __syncwarp();
+        SDBG(0, 6);
     }
+    SDBG(0, 9);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -599,29 +686,30 @@ struct StreamLayout {
 bool stream_geometry(int N, int R, int C, int H, int W, int PH, int PW, int sr, float scale, int sm_count, StreamGeom* g, StreamLayout* lay,
                      unsigned* smem_bytes) {
     if (sr < 1 || sr > 2 || PH * sr > kAxisMaxS || PW * sr > kAxisMaxS || PH > 31 || PW > 31) return false;
-    if (N <= 0 || R <= 0 || R > 65535 || H < 2 || W < 4 || (W & 3) || H > 65535) return false;
+    if (N <= 0 || R <= 0 || R > 65535 || H < 2 || W < 2 || H > 65535) return false;
     if ((long long)R * PH * PW * sr * sr >= (1LL << 28)) return false;
     // ring budget: everything but the per-warp staging, the barriers and the alignment slack
     const unsigned fixed = kConsumerWarps * kStageWordsPerWarp * 4 + 2 * kMaxSlots * 8 + 128;
     const unsigned ring_budget = kSmemBudget - fixed;
-    int best_xb = 0, best_s = 0, best_wx = 0, best_k = 0;
+    int best_sx = 0, best_s = 0, best_wx = 0, best_k = 0;
     long best_score = -1;
-    for (int xb = 36; xb <= 104; xb += 8) {                   // XB = 4 (mod 8): conflict-free channel stride
-        int k = (int)(ring_budget / (128u * (unsigned)xb));
+    for (int m = 1; m <= 3; ++m) {                            // SX = 32 m + 1: odd channel stride, m coalesced chunks + 1 column
+        const int sx = 32 * m + 1;
+        int k = (int)(ring_budget / (128u * (unsigned)sx));
         if (k > kMaxSlots) k = kMaxSlots;
-        if (k < 16) continue;
-        const int hx = xb >= 60 ? 9 : (xb >= 44 ? 5 : 3);    // halo: bins whose x samples are <= hx + 1 cells apart stay whole
-        const int wx = xb - 3 - hx;
+        if (k < 12) continue;
+        const int hx = m >= 2 ? 9 : 5;                        // halo: bins whose x samples are <= hx + 1 cells apart stay whole
+        const int wx = sx - 1 - hx;
         int s = 1;
-        while ((s - 1) * wx + xb - 3 < W) ++s;                // the last strip needs no halo
-        const long score = (long)s * xb;
-        if (best_score < 0 || score < best_score) { best_score = score; best_xb = xb; best_s = s; best_wx = wx; best_k = k; }
+        while ((s - 1) * wx + sx < W) ++s;                    // the last strip needs no halo
+        const long score = (long)s * sx;
+        if (best_score < 0 || score < best_score) { best_score = score; best_sx = sx; best_s = s; best_wx = wx; best_k = k; }
     }
     if (best_score < 0) return false;
     g->N = N; g->R = R; g->C = C; g->H = H; g->W = W; g->PH = PH; g->PW = PW; g->sr = sr;
     g->ny = PH * sr; g->nx = PW * sr;
-    g->XB = best_xb; g->WX = best_wx; g->S = best_s; g->K = best_k;
-    g->row_bytes = 128 * best_xb;
+    g->SX = best_sx; g->WX = best_wx; g->S = best_s; g->K = best_k;
+    g->row_bytes = 128 * best_sx;
     g->Q = N * best_s;
     if ((long long)g->Q * H >= (1LL << 24)) return false;
     g->keys = g->Q * H;
@@ -644,23 +732,6 @@ bool stream_geometry(int N, int R, int C, int H, int W, int PH, int PW, int sr, 
     return true;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = []() -> EncodeTiledFn {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
-            (void)cudaGetLastError();
-            return nullptr;
-        }
-        return (EncodeTiledFn)p;
-    }();
-    return fn;
-}
-
 struct DeviceInfo {
     bool ok = false;
     int sm_count = 0;
@@ -675,9 +746,15 @@ bool stream_device_info(int* sm_count) {
     std::lock_guard<std::mutex> lock(mu);
     if (!info[dev].ok) {
         const int max_dyn = (int)kSmemBudget;
-        if (cudaFuncSetAttribute(roi_align_stream_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != cudaSuccess ||
-            cudaFuncSetAttribute(roi_align_stream_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != cudaSuccess ||
-            cudaDeviceGetAttribute(&info[dev].sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        bool ok = cudaDeviceGetAttribute(&info[dev].sm_count, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess;
+#define B200_STREAM_ATTR(SRV, MV, AV) \
+        ok = ok && cudaFuncSetAttribute(roi_align_stream_fwd<SRV, MV, AV>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) == cudaSuccess
+        B200_STREAM_ATTR(1, 1, true); B200_STREAM_ATTR(1, 2, true); B200_STREAM_ATTR(1, 3, true);
+        B200_STREAM_ATTR(2, 1, true); B200_STREAM_ATTR(2, 2, true); B200_STREAM_ATTR(2, 3, true);
+        B200_STREAM_ATTR(1, 1, false); B200_STREAM_ATTR(1, 2, false); B200_STREAM_ATTR(1, 3, false);
+        B200_STREAM_ATTR(2, 1, false); B200_STREAM_ATTR(2, 2, false); B200_STREAM_ATTR(2, 3, false);
+#undef B200_STREAM_ATTR
+        if (!ok) {
             (void)cudaGetLastError();
             return false;
         }
@@ -688,6 +765,14 @@ bool stream_device_info(int* sm_count) {
 }
 
 }  // namespace
+
+void roi_align_stream_set_debug_buffer(unsigned long long* host_pinned) {
+#ifdef B200_STREAM_DEBUG
+    cudaMemcpyToSymbol(g_stream_dbg, &host_pinned, sizeof(host_pinned));
+#else
+    (void)host_pinned;
+#endif
+}
 
 size_t roi_align_stream_workspace_bytes(int N, int R, int H, int W, int PH, int PW, int sr) {
     StreamGeom g;
@@ -700,7 +785,7 @@ size_t roi_align_stream_workspace_bytes(int N, int R, int H, int W, int PH, int 
 // returns B200_ROI_OK when the streaming path ran; 1000 when it does not apply (caller falls back)
 int roi_align_forward_stream(const float* bottom, float scale, int N, int R, int H, int W, int C, int PH, int PW, int sr,
                              const float* rois, float* top, const int* row_map, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    if (workspace == nullptr || C <= 0 || ((uintptr_t)bottom & 15u)) return 1000;
+    if (workspace == nullptr || C <= 0) return 1000;
     if ((long long)N * C >= (1LL << 31) || (long long)R * C * PH * PW >= (1LL << 31)) return 1000;
     int sm_count = 0;
     if (!stream_device_info(&sm_count)) return 1000;
@@ -709,18 +794,6 @@ int roi_align_forward_stream(const float* bottom, float scale, int N, int R, int
     unsigned smem = 0;
     if (!stream_geometry(N, R, C, H, W, PH, PW, sr, scale, sm_count, &g, &lay, &smem)) return 1000;
     if (workspace_bytes < lay.ws_bytes) return 1000;
-    EncodeTiledFn encode = encode_tiled_fn();
-    if (!encode) return 1000;
-
-    CUtensorMap tmap;
-    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * (cuuint64_t)C};
-    const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * (cuuint64_t)H * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)g.XB, 1u, 8u};
-    const cuuint32_t estr[3] = {1u, 1u, 1u};
-    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)bottom, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return 1000;
-
     unsigned char* wsb = (unsigned char*)workspace;
     StreamWs ws;
     ws.ytab = (uint4*)(wsb + lay.ytab_off);
@@ -737,18 +810,24 @@ int roi_align_forward_stream(const float* bottom, float scale, int N, int R, int
     if (err != cudaSuccess) return (int)err;
     StreamArgs a;
     a.ytab = ws.ytab; a.xtab = ws.xtab; a.entries = ws.entries; a.rowptr = ws.rowptr; a.maxend = ws.maxend;
-    a.piece_start = ws.piece_start; a.out = top; a.row_map = row_map;
-    a.C = C; a.H = H; a.S = g.S; a.G = g.G; a.K = g.K; a.XB = g.XB; a.WX = g.WX; a.PH = PH; a.PW = PW; a.ny = g.ny; a.nx = g.nx;
+    a.piece_start = ws.piece_start; a.bottom = bottom; a.out = top; a.row_map = row_map;
+    a.C = C; a.H = H; a.W = W; a.S = g.S; a.G = g.G; a.K = g.K; a.SX = g.SX; a.WX = g.WX; a.PH = PH; a.PW = PW; a.ny = g.ny; a.nx = g.nx;
     a.row_bytes = g.row_bytes;
+    const bool async = option_get(kOptStreamStage) != 'r';          // B200_STREAM_STAGE=regs selects LDG -> registers -> STS (A/B)
+    const int m = (g.SX - 1) / 32;
     if (sr == 1) {
         stream_count<1><<<R, kPrepThreads, 0, stream>>>(rois, g, ws);
         stream_fill<1><<<R, kPrepThreads, 0, stream>>>(rois, g, ws, top, row_map);
-        roi_align_stream_fwd<1><<<g.pieces, kStreamThreads, smem, stream>>>(tmap, a);
     } else {
         stream_count<2><<<R, kPrepThreads, 0, stream>>>(rois, g, ws);
         stream_fill<2><<<R, kPrepThreads, 0, stream>>>(rois, g, ws, top, row_map);
-        roi_align_stream_fwd<2><<<g.pieces, kStreamThreads, smem, stream>>>(tmap, a);
     }
+#define B200_STREAM_LAUNCH(SRV, MV, AV) roi_align_stream_fwd<SRV, MV, AV><<<g.pieces, kStreamThreads, smem, stream>>>(a)
+#define B200_STREAM_LAUNCH_M(SRV, AV) (m == 1 ? B200_STREAM_LAUNCH(SRV, 1, AV) : m == 2 ? B200_STREAM_LAUNCH(SRV, 2, AV) : B200_STREAM_LAUNCH(SRV, 3, AV))
+    if (sr == 1) { if (async) B200_STREAM_LAUNCH_M(1, true); else B200_STREAM_LAUNCH_M(1, false); }
+    else         { if (async) B200_STREAM_LAUNCH_M(2, true); else B200_STREAM_LAUNCH_M(2, false); }
+#undef B200_STREAM_LAUNCH_M
+#undef B200_STREAM_LAUNCH
     return finish_launch(3);
 }
 

@@ -27,6 +27,32 @@ def test_library_builds_and_exports_header_symbols():
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared       # python binding covers exactly the header
 
 
+def test_reference_named_launchers_are_exported():
+    """the reference's own launcher names with the reference's argument lists (include/b200_ref_launchers.h),
+    so that lib/.../src/*_cuda.c links unchanged.  Two libraries because the two RoIAlign flavours share their names."""
+    build.build()
+    text = open(os.path.join(ROOT, "include", "b200_ref_launchers.h")).read()
+    body = text[text.index("#ifndef B200_REF_LEGACY_ROI_ALIGN"):]
+    main_part, legacy_part = body[:body.rindex("#else")], body[body.rindex("#else"):]
+    names = lambda t: sorted(set(re.findall(r"B200_REF_API\s+\w+\s+(\w+)\s*\(", t)))
+    lib = ctypes.CDLL(build.compat_lib_path("libb200_ref_launchers.so"))
+    assert names(main_part) == ["BilinearSamplerBHWD_updateGradInput_cuda_kernel", "BilinearSamplerBHWD_updateOutput_cuda_kernel",
+                                "ROIAlignBackwardLaucher", "ROIAlignForwardLaucher", "ROIPoolBackwardLaucher", "ROIPoolForwardLaucher",
+                                "nms_cuda_compute"]
+    for n in names(main_part):
+        assert hasattr(lib, n), n
+    leg = ctypes.CDLL(build.compat_lib_path("libb200_ref_launchers_legacy.so"))
+    assert names(legacy_part) == ["ROIAlignBackwardLaucher", "ROIAlignForwardLaucher"]
+    for n in names(legacy_part):
+        assert hasattr(leg, n), n
+    # argument errors come back as 0 (the reference's glue treats 0 as failure), before any CUDA call
+    lib.ROIAlignForwardLaucher.restype = ctypes.c_int
+    assert lib.ROIAlignForwardLaucher(None, ctypes.c_float(0.25), 4, 0, 10, 3, 7, 7, 2, None, None, None) == 0
+    # non-dense strides are refused by the RoICrop launchers
+    assert lib.BilinearSamplerBHWD_updateOutput_cuda_kernel(3, 7, 7, 2, 3, 10, 10, 1, None, 300, 100, 10, 2, None, 98, 1, 14, 2,
+                                                            None, 147, 49, 7, 1, None) == 0
+
+
 def test_sm100a_cubin_embedded():
     import subprocess
     path = build.build()

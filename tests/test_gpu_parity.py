@@ -42,7 +42,7 @@ def fwd_path(request, lib_option):
     """Force the RoIAlign forward AND backward dispatch (b200_roi_ops_set_option):
     generic = RoI-centric kernels (scalar atomics in the backward), tiled = feature-map-stationary
     forward + vector-reduction (NHWC scratch) backward, tiled-rows = same forward + row-stationary gather
-    backward (falls back to the scalar-atomic kernel for shapes it does not cover), stream = TMA streaming-strip
+    backward (falls back to the scalar-atomic kernel for shapes it does not cover), stream = cp.async streaming-strip
     forward (falls back to the generic kernel for shapes it does not cover) + the default backward."""
     lib_option("B200_ROI_ALIGN_PATH", {"generic": "generic", "tiled": "tiled", "tiled-rows": "tiled", "stream": "stream"}[request.param])
     lib_option("B200_ROI_ALIGN_BWD_PATH", {"generic": "generic", "tiled": "nhwc", "tiled-rows": "rows", "stream": "auto"}[request.param])
@@ -280,19 +280,21 @@ def test_roi_align_many_rois_multi_image_partial_channels(fwd_path):
 
 
 STREAM_CASES = {
-    # name: (shape, scale, P, sr, n_rois, min_size, max_size) -- shapes the TMA streaming-strip forward covers (W % 4 == 0, sr in {1, 2})
+    # name: (shape, scale, P, sr, n_rois, min_size, max_size) -- shapes the streaming-strip forward covers (sr in {1, 2})
     "c40_n2": ((2, 40, 60, 100), 1.0 / 8, 7, 2, 200, 32, 512),       # C not a multiple of 32, two strips, two images
     "p14": ((1, 64, 50, 84), 1.0 / 16, 14, 2, 60, 64, 600),           # mask-head geometry, one strip
     "sr1": ((3, 32, 40, 68), 1.0 / 16, 7, 1, 80, 32, 512),
     "wide": ((1, 32, 50, 336), 1.0 / 4, 7, 2, 150, 16, 1300),         # six strips; whole-width boxes -> x-split bins
     "tall": ((1, 32, 400, 64), 1.0 / 4, 7, 2, 100, 16, 1590),         # whole-height boxes -> y-split bins (span > ring depth)
     "c256": ((1, 256, 64, 96), 1.0 / 8, 7, 2, 128, 32, 512),          # 8 channel groups
+    "odd_w": ((2, 48, 25, 42), 1.0 / 32, 7, 2, 60, 64, 900),          # FPN P5: W = 42 (168-byte pitch), partial channel group
+    "narrow": ((1, 32, 30, 9), 1.0 / 32, 7, 2, 12, 32, 300),          # W < 32: one partial chunk
 }
 
 
 @pytest.mark.parametrize("name", sorted(STREAM_CASES))
 def test_roi_align_stream_path(name, lib_option):
-    """TMA streaming-strip forward vs the oracle: every bin whose samples fit the strip halo / the ring is computed by one
+    """Streaming-strip forward (cp.async + mbarrier ring) vs the oracle: every bin whose samples fit the strip halo / the ring is computed by one
     lane in the reference's order -> bit-exact; bins cut into two partial sums (huge boxes) agree to 1e-6.  The launch
     counter proves the streaming kernels ran (count + fill + main) and not a fallback."""
     lib_option("B200_ROI_ALIGN_PATH", "stream")
