@@ -13,7 +13,7 @@ or, to make an unmodified checkout of the reference pick these up under ITS impo
 __version__ = "0.1.0"
 
 
-def install_reference_aliases(overwrite=True, proposals=False):
+def install_reference_aliases(overwrite=True, proposals=False, nms=False):
     """Register this package's op modules in sys.modules under the reference's import paths.
 
     After this, `from modeling.roi_xfrom.roi_align.functions.roi_align import RoIAlignFunction`
@@ -24,6 +24,9 @@ def install_reference_aliases(overwrite=True, proposals=False):
     op sub-packages are injected.  `proposals=True` additionally routes `modeling.generate_proposals` (the RPN proposal
     layer, rpn_heads.py / FPN.py import it) and `modeling.collect_and_distribute_fpn_rpn_proposals` to the device
     implementations; the latter only implements the inference path, hence opt-in.
+    `nms=True` re-points the reference's `utils.boxes.nms` (lib/utils/boxes.py:320-324; called from
+    generate_proposals.py:161 and core/test.py:764 with numpy arrays) at the device NMS (`utils/boxes.py` here); the
+    reference's `utils.boxes` must be importable for that.
     """
     import importlib
     import sys
@@ -59,4 +62,8 @@ def install_reference_aliases(overwrite=True, proposals=False):
         if parent in sys.modules:
             setattr(sys.modules[parent], child, mod)
         installed.append(name)
+    if nms:
+        ref_boxes = importlib.import_module("utils.boxes")          # the reference's module
+        ref_boxes.nms = importlib.import_module(__name__ + ".utils.boxes").nms
+        installed.append("utils.boxes.nms")
     return installed

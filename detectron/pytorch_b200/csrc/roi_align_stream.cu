@@ -46,6 +46,7 @@ constexpr int kStageWordsPerWarp = kFragBins * kStageStride;
 constexpr int kMaxSlots = 32;                                 // ring depth K <= 32 (phase bits live in one register)
 constexpr int kAxisMaxS = 32;                                 // P * sampling_ratio per axis
 constexpr int kPrepThreads = 128;
+constexpr int kScanCap = 6144;                                // keys whose cost prefix is kept in shared memory by the scan
 constexpr unsigned kSmemBudget = 227u * 1024u;
 
 typedef unsigned long long u64;
@@ -217,29 +218,66 @@ stream_count(const float* __restrict__ rois, StreamGeom g, StreamWs ws) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // Everything below is latency bound (one CTA): the histogram is pulled into shared memory with all loads of a
+    // chunk in flight, scanned there, and the piece boundaries are binary-searched in the shared copy of the prefix.
+    __shared__ unsigned s_pre[kScanCap + 1];                  // exclusive cost prefix (keys <= kScanCap)
+    __shared__ unsigned s_carry[2];
     const int keys = g.keys;
-    const int chunk = (keys + kPrepThreads - 1) / kPrepThreads;
-    const int b = min(keys, t * chunk), e = min(keys, b + chunk);
-    unsigned sh = 0, sc = 0;
-    for (int k = b; k < e; ++k) { sh += (unsigned)__ldcg(&ws.hist[k]); sc += (unsigned)__ldcg(&ws.cost[k]) + 2u; }
-    s_h[t] = sh; s_c[t] = sc;
+    const bool in_smem = keys <= kScanCap;
+    if (t == 0) { s_carry[0] = 0u; s_carry[1] = 0u; }
     __syncthreads();
-    if (t == 0) {
-        unsigned ah = 0, ac = 0;
-        for (int i = 0; i < kPrepThreads; ++i) { const unsigned h = s_h[i], c = s_c[i]; s_h[i] = ah; s_c[i] = ac; ah += h; ac += c; }
-        ws.rowptr[keys] = (int)ah;
-        ws.cpre[keys] = ac;
+    constexpr int kPer = 8, kChunk = kPrepThreads * kPer;
+    for (int base = 0; base < keys; base += kChunk) {
+        unsigned h[kPer], c[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {                      // thread t owns keys base + t * kPer + j; loads are independent
+            const int k = base + t * kPer + j;
+            h[j] = k < keys ? (unsigned)__ldcg(&ws.hist[k]) : 0u;
+            c[j] = k < keys ? (unsigned)__ldcg(&ws.cost[k]) + 2u : 0u;
+        }
+        unsigned sh = 0, sc = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) { sh += h[j]; sc += c[j]; }
+        s_h[t] = sh; s_c[t] = sc;
+        __syncthreads();
+        if (t < 32) {                                         // exclusive scan of the 128 thread sums by one warp (4 per lane)
+            unsigned vh[4], vc[4], th = 0, tc = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { vh[j] = s_h[t * 4 + j]; vc[j] = s_c[t * 4 + j]; th += vh[j]; tc += vc[j]; }
+            unsigned ih = th, ic = tc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned uh = __shfl_up_sync(0xffffffffu, ih, d), uc = __shfl_up_sync(0xffffffffu, ic, d);
+                if (t >= d) { ih += uh; ic += uc; }
+            }
+            unsigned rh = ih - th + s_carry[0], rc = ic - tc + s_carry[1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s_h[t * 4 + j] = rh; s_c[t * 4 + j] = rc; rh += vh[j]; rc += vc[j]; }
+            __syncwarp();
+            if (t == 31) { s_carry[0] = rh; s_carry[1] = rc; }
+        }
+        __syncthreads();
+        unsigned rh = s_h[t], rc = s_c[t];
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int k = base + t * kPer + j;
+            if (k < keys) {
+                ws.rowptr[k] = (int)rh; ws.cpre[k] = rc;
+                if (in_smem) s_pre[k] = rc;
+            }
+            rh += h[j]; rc += c[j];
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    sh = s_h[t]; sc = s_c[t];
-    for (int k = b; k < e; ++k) {
-        ws.rowptr[k] = (int)sh; ws.cpre[k] = sc;
-        sh += (unsigned)__ldcg(&ws.hist[k]); sc += (unsigned)__ldcg(&ws.cost[k]) + 2u;
+    if (t == 0) {
+        ws.rowptr[keys] = (int)s_carry[0]; ws.cpre[keys] = s_carry[1];
+        if (in_smem) s_pre[keys] = s_carry[1];
     }
     __threadfence();
     __syncthreads();
     // piece p starts where the cumulative cost over the linear order (column q, channel group, row) reaches p/pieces
-    const unsigned total = __ldcg(&ws.cpre[keys]);
+    auto pre = [&](size_t k) -> unsigned { return in_smem ? s_pre[k] : __ldcg(&ws.cpre[k]); };
+    const unsigned total = s_carry[1];
     const u64 grand = (u64)total * (u64)g.G;
     for (int p = t; p <= g.pieces; p += kPrepThreads) {
         int L;
@@ -250,11 +288,11 @@ stream_count(const float* __restrict__ rois, StreamGeom g, StreamWs ws) {
             int lo = 0, hi = g.Q - 1;
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
-                if ((u64)g.G * (u64)__ldcg(&ws.cpre[(size_t)mid * g.H]) <= target) lo = mid; else hi = mid - 1;
+                if ((u64)g.G * (u64)pre((size_t)mid * g.H) <= target) lo = mid; else hi = mid - 1;
             }
             const int q = lo;
-            const unsigned c0 = __ldcg(&ws.cpre[(size_t)q * g.H]);
-            const unsigned colsum = __ldcg(&ws.cpre[(size_t)(q + 1) * g.H]) - c0;      // >= H > 0
+            const unsigned c0 = pre((size_t)q * g.H);
+            const unsigned colsum = pre((size_t)(q + 1) * g.H) - c0;      // >= 2 H > 0
             u64 rem = target - (u64)g.G * (u64)c0;
             int gg = (int)(rem / colsum);
             if (gg > g.G - 1) gg = g.G - 1;
@@ -262,7 +300,7 @@ stream_count(const float* __restrict__ rois, StreamGeom g, StreamWs ws) {
             int ylo = 0, yhi = g.H - 1;
             while (ylo < yhi) {
                 const int mid = (ylo + yhi + 1) >> 1;
-                if ((u64)(__ldcg(&ws.cpre[(size_t)q * g.H + mid]) - c0) <= rem) ylo = mid; else yhi = mid - 1;
+                if ((u64)(pre((size_t)q * g.H + mid) - c0) <= rem) ylo = mid; else yhi = mid - 1;
             }
             L = (q * g.G + gg) * g.H + ylo;
         }
