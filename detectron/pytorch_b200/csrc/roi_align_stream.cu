@@ -37,7 +37,10 @@ namespace b200 {
 
 namespace {
 
-constexpr int kConsumerWarps = 16;
+#ifndef B200_STREAM_CWARPS
+#define B200_STREAM_CWARPS 16
+#endif
+constexpr int kConsumerWarps = B200_STREAM_CWARPS;
 constexpr int kProducerWarps = 4;
 constexpr int kStreamThreads = 32 * (kConsumerWarps + kProducerWarps);
 constexpr int kFragBins = 8;                                  // bins per fragment (one flush)
@@ -80,7 +83,7 @@ struct StreamGeom {
 };
 
 struct StreamWs {
-    uint4* ytab;                // [R][ny] {hy, ly, byte offset of the ring slot of row y_low, of row y_low + 1}
+    uint4* ytab;                // [R][ny] {hy, ly, byte offset of the ring slot of row y_low, 0}; the lower tap row is the NEXT slot
     uint4* xtab;                // [R][nx] {hx, lx, x_low * 4, 0}
     int* hist;                  // [keys] fragments per key                           (zero block)
     int* cost;                  // [keys] estimated cost per key                      (zero block)
@@ -121,20 +124,21 @@ __device__ __forceinline__ AdjTap adj_axis(float v, int size) {
     return a;
 }
 
-// Enumerate the fragments of bin row `ph` of one RoI.  yl / xl: adjusted low cells per axis sample.
+// Enumerate the fragments of bin row `ph` of one RoI.  yl / yh: the reference's low / high tap row per y sample
+// (equal on the clamped last row); xl: adjusted low cell per x sample.
 // emit(strip, key, end, pw0, npw, smask, red, zero_owner)
 template <int SR, class Emit>
-__device__ __forceinline__ void enum_row(const int* yl, const int* xl, int ph, const StreamGeom& g, Emit&& emit) {
+__device__ __forceinline__ void enum_row(const int* yl, const int* yh, const int* xl, int ph, const StreamGeom& g, Emit&& emit) {
     const int i0 = ph * SR, i1 = i0 + SR - 1;
     int ngroups = 1;
     int key[2], end[2];
     unsigned ym[2];
-    key[0] = yl[i0]; end[0] = yl[i1] + 2; ym[0] = (1u << SR) - 1u;
+    key[0] = yl[i0]; end[0] = yh[i1] + 1; ym[0] = (1u << SR) - 1u;
     key[1] = 0; end[1] = 0; ym[1] = 0;
     if (SR == 2 && end[0] - key[0] > g.K) {          // rows cannot be resident together: one fragment per y sample
         ngroups = 2;
-        end[0] = key[0] + 2; ym[0] = 1u;
-        key[1] = yl[i1]; end[1] = key[1] + 2; ym[1] = 2u;
+        end[0] = yh[i0] + 1; ym[0] = 1u;
+        key[1] = yl[i1]; end[1] = yh[i1] + 1; ym[1] = 2u;
     }
     constexpr unsigned kXFull = (1u << SR) - 1u;
     for (int gi = 0; gi < ngroups; ++gi) {
@@ -175,7 +179,7 @@ __device__ __forceinline__ void enum_row(const int* yl, const int* xl, int ph, c
 template <int SR>
 __global__ void __launch_bounds__(kPrepThreads)
 stream_count(const float* __restrict__ rois, StreamGeom g, StreamWs ws) {
-    __shared__ int s_yl[kAxisMaxS], s_xl[kAxisMaxS];
+    __shared__ int s_yl[kAxisMaxS], s_yh[kAxisMaxS], s_xl[kAxisMaxS];
     __shared__ int s_last;
     __shared__ unsigned s_h[kPrepThreads], s_c[kPrepThreads];
     const int r = blockIdx.x, t = threadIdx.x;
@@ -184,12 +188,14 @@ stream_count(const float* __restrict__ rois, StreamGeom g, StreamWs ws) {
         const bool isy = t < g.ny;
         const int s = isy ? t : t - g.ny;
         if (isy) {
-            const AdjTap a = adj_axis(xfrom_coord(geo.start_h, geo.bin_h, s / SR, s % SR, SR), g.H);
-            s_yl[s] = a.low;
+            // rows exactly as the reference takes them (low == high == H - 1 on the clamped last row, weights (1, 0)): the
+            // lower tap then reads whatever the next ring slot holds with weight 0 -- always finite, the ring starts zeroed
+            const AxisTap a = xfrom_axis(xfrom_coord(geo.start_h, geo.bin_h, s / SR, s % SR, SR), g.H);
+            s_yl[s] = a.low; s_yh[s] = a.high;
             uint4 e;
-            e.x = __float_as_uint(a.h); e.y = __float_as_uint(a.l);
+            e.x = __float_as_uint(a.valid ? a.h : 0.f); e.y = __float_as_uint(a.valid ? a.l : 0.f);
             e.z = (unsigned)((a.low % g.K) * g.row_bytes);
-            e.w = (unsigned)(((a.low + 1) % g.K) * g.row_bytes);
+            e.w = 0u;
             ws.ytab[(size_t)r * g.ny + s] = e;
         } else {
             const AdjTap a = adj_axis(xfrom_coord(geo.start_w, geo.bin_w, s / SR, s % SR, SR), g.W);
@@ -204,7 +210,7 @@ stream_count(const float* __restrict__ rois, StreamGeom g, StreamWs ws) {
     const bool batch_ok = geo.batch >= 0 && geo.batch < g.N;
     if (batch_ok && t < g.PH) {
         const int kbase = geo.batch * g.S;
-        enum_row<SR>(s_yl, s_xl, t, g, [&](int s, int key, int end, int pw0, int npw, unsigned smask, int red, bool owner) {
+        enum_row<SR>(s_yl, s_yh, s_xl, t, g, [&](int s, int key, int end, int pw0, int npw, unsigned smask, int red, bool owner) {
             const int k = (kbase + s) * g.H + key;
             atomicAdd(&ws.hist[k], 1);
             atomicAdd(&ws.cost[k], 2 + npw);
@@ -314,7 +320,7 @@ stream_count(const float* __restrict__ rois, StreamGeom g, StreamWs ws) {
 template <int SR>
 __global__ void __launch_bounds__(kPrepThreads)
 stream_fill(const float* __restrict__ rois, StreamGeom g, StreamWs ws, float* __restrict__ out, const int* __restrict__ row_map) {
-    __shared__ int s_yl[kAxisMaxS], s_xl[kAxisMaxS];
+    __shared__ int s_yl[kAxisMaxS], s_yh[kAxisMaxS], s_xl[kAxisMaxS];
     __shared__ unsigned short s_zero[kAxisMaxS * kAxisMaxS];
     __shared__ int s_nzero;
     const int r = blockIdx.x, t = threadIdx.x;
@@ -323,8 +329,12 @@ stream_fill(const float* __restrict__ rois, StreamGeom g, StreamWs ws, float* __
     if (t < g.ny + g.nx) {
         const bool isy = t < g.ny;
         const int s = isy ? t : t - g.ny;
-        if (isy) s_yl[s] = adj_axis(xfrom_coord(geo.start_h, geo.bin_h, s / SR, s % SR, SR), g.H).low;
-        else     s_xl[s] = adj_axis(xfrom_coord(geo.start_w, geo.bin_w, s / SR, s % SR, SR), g.W).low;
+        if (isy) {
+            const AxisTap a = xfrom_axis(xfrom_coord(geo.start_h, geo.bin_h, s / SR, s % SR, SR), g.H);
+            s_yl[s] = a.low; s_yh[s] = a.high;
+        } else {
+            s_xl[s] = adj_axis(xfrom_coord(geo.start_w, geo.bin_w, s / SR, s % SR, SR), g.W).low;
+        }
     }
     __syncthreads();
     const bool batch_ok = geo.batch >= 0 && geo.batch < g.N;
@@ -332,7 +342,7 @@ stream_fill(const float* __restrict__ rois, StreamGeom g, StreamWs ws, float* __
     if (batch_ok) {
         if (t < g.PH) {
             const int kbase = geo.batch * g.S;
-            enum_row<SR>(s_yl, s_xl, t, g, [&](int s, int key, int end, int pw0, int npw, unsigned smask, int red, bool owner) {
+            enum_row<SR>(s_yl, s_yh, s_xl, t, g, [&](int s, int key, int end, int pw0, int npw, unsigned smask, int red, bool owner) {
                 const int k = (kbase + s) * g.H + key;
                 const int pos = ws.rowptr[k] + atomicAdd(&ws.cursor[k], 1);
                 if (pos < g.max_entries) ws.entries[pos] = pack_entry(r, t, pw0, npw, red, key, end, smask);
@@ -377,36 +387,31 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
         "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// try_wait suspends the thread in hardware for a bounded time per attempt.  A wait that does not finish within ~2 s
-// of SM clocks is a protocol bug: trap (surfaces as a launch failure) instead of hanging the GPU.
+// try_wait suspends the thread in hardware for a bounded time per attempt.  A wait that is still pending after 2^22
+// attempts (seconds) is a protocol bug: trap (surfaces as a launch failure) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity, unsigned tag = 0u) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
+        if (++spins > (1 << 22)) {
             SDBG(6, 0xDEAD000000000000ull | ((u64)tag << 16) | ((u64)parity << 8) | (u64)((bar >> 3) & 0xff));
             __trap();
         }
     }
 }
-// 4-byte cp.async (LDGSTS): global -> shared without registers.  ok == false copies nothing and zero-fills the word.
-__device__ __forceinline__ void cp_async4(unsigned dst, const float* src, bool ok) {
+// 4-byte cp.async (LDGSTS): global -> shared without registers.
+__device__ __forceinline__ void cp_async4(unsigned dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+// ok == false copies nothing and zero-fills the word
+__device__ __forceinline__ void cp_async4_if(unsigned dst, const float* src, bool ok) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
 }
 // the mbarrier receives one arrival from this thread once all its earlier cp.async have landed
 __device__ __forceinline__ void cp_async_arrive(unsigned bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ float lds32(unsigned addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float lds32_off4(unsigned addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(v) : "r"(addr));
-    return v;
-}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 struct StreamArgs {
     const uint4* ytab;
@@ -418,7 +423,7 @@ struct StreamArgs {
     const float* bottom;
     float* out;
     const int* row_map;
-    int C, H, W, S, G, K, SX, WX, PH, PW, ny, nx, row_bytes;
+    int C, H, W, S, G, K, WX, PH, PW, ny, nx;
 };
 
 // one item = the part of one (strip column q, channel group) that lies in this CTA's piece
@@ -457,11 +462,15 @@ __device__ __forceinline__ u64 mul2f(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0
 
 struct Taps { float v1, v2, v3, v4; };
 
-// the four taps of one sample for this lane's channel: rows (top, bottom) x columns (x_low, x_low + 1)
-__device__ __forceinline__ Taps load_taps(unsigned row_top, unsigned row_bot, unsigned xoff) {
+// The four taps of one sample for this lane's channel: rows (slot, slot + 1) x columns (x_low, x_low + 1).  The lower row
+// always sits in the NEXT physical slot (the ring has a mirror of slot 0 behind slot K - 1), so one address serves all four.
+template <int RB>
+__device__ __forceinline__ Taps load_taps(unsigned at) {
     Taps t;
-    const unsigned at = row_top + xoff, ab = row_bot + xoff;
-    t.v1 = lds32(at); t.v2 = lds32_off4(at); t.v3 = lds32(ab); t.v4 = lds32_off4(ab);
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t.v1) : "r"(at));
+    asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(t.v2) : "r"(at));
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(t.v3) : "r"(at), "n"(RB));
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(t.v4) : "r"(at), "n"(RB + 4));
     return t;
 }
 
@@ -479,26 +488,35 @@ __device__ __forceinline__ float sample_val(const Taps& t, u64 hyhy, u64 lyly, u
 // (lane = column: 128-byte coalesced) plus the last column x = 32 M for all channels at once (lane = channel).
 // ASYNC: 4-byte cp.async; otherwise LDG -> registers -> STS in batches of 8 channels.
 template <int M, bool ASYNC>
-__device__ __forceinline__ void stage_row(const float* __restrict__ src_row, size_t plane, unsigned dst, int SX, int xw, int cvalid,
-                                          int lane, unsigned full_bar) {
+__device__ __forceinline__ void stage_row(const float* __restrict__ src_row, size_t plane, unsigned dst, int xw, int cvalid, int lane) {
     // src_row: (channel 0, row y, column x0); xw = number of valid columns from x0; cvalid = number of real channels
+    constexpr int SX = 32 * M + 1;
     if (ASYNC) {
-#pragma unroll 4
-        for (int c = 0; c < 32; ++c) {
-            const bool cok = c < cvalid;
-            const float* sc = src_row + (size_t)(cok ? c : 0) * plane;
+        if (cvalid == 32 && xw >= SX) {                       // interior: no predicates, constant offsets
+            const float* sc = src_row + lane;
+            const unsigned d = dst + (unsigned)lane * 4u;
+#pragma unroll 8
+            for (int c = 0; c < 32; ++c) {
 #pragma unroll
-            for (int m = 0; m < M; ++m) {
-                const int x = lane + 32 * m;
-                const bool ok = cok && x < xw;
-                cp_async4(dst + (unsigned)(c * SX + x) * 4u, sc + (ok ? x : 0), ok);
+                for (int m = 0; m < M; ++m) cp_async4(d + (unsigned)(c * SX + 32 * m) * 4u, sc + 32 * m);
+                sc += plane;
             }
-        }
-        {
+            cp_async4(dst + (unsigned)(lane * SX + 32 * M) * 4u, src_row + (size_t)lane * plane + 32 * M);
+        } else {
+#pragma unroll 4
+            for (int c = 0; c < 32; ++c) {
+                const bool cok = c < cvalid;
+                const float* sc = src_row + (size_t)(cok ? c : 0) * plane;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const int x = lane + 32 * m;
+                    const bool ok = cok && x < xw;
+                    cp_async4_if(dst + (unsigned)(c * SX + x) * 4u, sc + (ok ? x : 0), ok);
+                }
+            }
             const bool ok = lane < cvalid && 32 * M < xw;
-            cp_async4(dst + (unsigned)(lane * SX + 32 * M) * 4u, src_row + (ok ? (size_t)lane * plane + 32 * M : 0), ok);
+            cp_async4_if(dst + (unsigned)(lane * SX + 32 * M) * 4u, src_row + (ok ? (size_t)lane * plane + 32 * M : 0), ok);
         }
-        cp_async_arrive(full_bar);
     } else {
         for (int c8 = 0; c8 < 32; c8 += 8) {
             float v[8][M];
@@ -518,27 +536,32 @@ __device__ __forceinline__ void stage_row(const float* __restrict__ src_row, siz
                 for (int m = 0; m < M; ++m)
                     asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + (unsigned)((c8 + j) * SX + lane + 32 * m) * 4u), "f"(v[j][m]) : "memory");
         }
-        {
-            const bool ok = lane < cvalid && 32 * M < xw;
-            const float t = ok ? __ldcs(src_row + (size_t)lane * plane + 32 * M) : 0.f;
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + (unsigned)(lane * SX + 32 * M) * 4u), "f"(t) : "memory");
-        }
-        mbar_arrive(full_bar);
+        const bool ok = lane < cvalid && 32 * M < xw;
+        const float t = ok ? __ldcs(src_row + (size_t)lane * plane + 32 * M) : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + (unsigned)(lane * SX + 32 * M) * 4u), "f"(t) : "memory");
     }
 }
 
 template <int SR, int M, bool ASYNC>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 roi_align_stream_fwd(const StreamArgs a) {
+    constexpr int SX = 32 * M + 1;
+    constexpr int RB = 128 * SX;                                  // bytes of one ring slot
     extern __shared__ unsigned char smem_raw[];
     const unsigned ring = (smem_addr(smem_raw) + 127u) & ~127u;
     unsigned char* ring_ptr = smem_raw + (ring - smem_addr(smem_raw));
-    float* stage_all = reinterpret_cast<float*>(ring_ptr + (size_t)a.K * a.row_bytes);
-    const unsigned bars = ring + (unsigned)a.K * (unsigned)a.row_bytes + kConsumerWarps * kStageWordsPerWarp * 4;
+    // ring: K logical slots + one mirror of slot 0 behind slot K - 1, so that row y + 1 is always the next physical slot
+    float* stage_all = reinterpret_cast<float*>(ring_ptr + (size_t)(a.K + 1) * RB);
+    const unsigned bars = ring + (unsigned)(a.K + 1) * (unsigned)RB + kConsumerWarps * kStageWordsPerWarp * 4;
     // full[k] at bars + 8k (32 arrivals: the lanes of the producer warp that staged the row),
     // empty[k] at bars + 8 * (kMaxSlots + k) (one arrival per consumer warp)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    {   // the ring starts zeroed: a tap with weight 0 may read a slot that was never written (clamped last row)
+        const int n16 = (a.K + 1) * (RB / 16);
+        float4* r4 = reinterpret_cast<float4*>(ring_ptr);
+        for (int k = tid; k < n16; k += kStreamThreads) r4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (tid == 0) {
         for (int k = 0; k < a.K; ++k) { mbar_init(bars + 8u * k, 32u); mbar_init(bars + 8u * (kMaxSlots + k), kConsumerWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -571,7 +594,9 @@ roi_align_stream_fwd(const StreamArgs a) {
                     const unsigned full = bars + 8u * slot, empty = bars + 8u * (kMaxSlots + slot);
                     mbar_wait(empty, (ephase >> slot) & 1u, 0x1000u + (unsigned)y);
                     SDBG(4, ((u64)y << 32) | (u64)slot);
-                    stage_row<M, ASYNC>(src, plane, ring + (unsigned)slot * (unsigned)a.row_bytes, a.SX, xw, cvalid, lane, full);
+                    stage_row<M, ASYNC>(src, plane, ring + (unsigned)slot * (unsigned)RB, xw, cvalid, lane);
+                    if (slot == 0) stage_row<M, ASYNC>(src, plane, ring + (unsigned)a.K * (unsigned)RB, xw, cvalid, lane);   // mirror
+                    if (ASYNC) cp_async_arrive(full); else mbar_arrive(full);
                 }
                 ephase ^= 1u << slot;
                 if (++slot == a.K) slot = 0;
@@ -585,7 +610,7 @@ roi_align_stream_fwd(const StreamArgs a) {
 
     // =============================== consumers ===============================
     float* stage = stage_all + warp * kStageWordsPerWarp;
-    const unsigned lane_base = ring + (unsigned)(lane * a.SX) * 4u;
+    const unsigned lane_base = ring + (unsigned)(lane * SX) * 4u;
     const int bins = a.PH * a.PW;
     unsigned fphase = 0u;
     const int chsub = lane >> 3, fb = lane & 7;
@@ -601,6 +626,26 @@ roi_align_stream_fwd(const StreamArgs a) {
         int acq = it.ya, rel = it.ya;
         int acq_slot = it.ya % a.K, rel_slot = acq_slot;
         const int c0 = it.g * 32;
+        // every warp waits for every row of the item before it releases it, in stream order (keeps the per-slot
+        // phase bits in step with the producers)
+        auto acquire_to = [&](int row_end, unsigned tag) {
+            while (acq < row_end) {
+                mbar_wait(bars + 8u * acq_slot, (fphase >> acq_slot) & 1u, tag + (unsigned)acq);
+                fphase ^= 1u << acq_slot;
+                ++acq;
+                if (++acq_slot == a.K) acq_slot = 0;
+            }
+        };
+        auto release_to = [&](int row_end) {                  // rows [rel, row_end) have been acquired
+            if (rel < row_end) {
+                if (lane == 0) {
+                    int rs = rel_slot;
+                    for (int y = rel; y < row_end; ++y) { mbar_arrive(bars + 8u * (kMaxSlots + rs)); if (++rs == a.K) rs = 0; }
+                }
+                rel_slot = (rel_slot + (row_end - rel)) % a.K;
+                rel = row_end;
+            }
+        };
 
         int e = it.e0 + warp;
         uint2 ent = make_uint2(0u, 0u);
@@ -608,13 +653,16 @@ roi_align_stream_fwd(const StreamArgs a) {
         while (e < it.e1) {
             const uint2 cur = ent;
             const int e_next = e + kConsumerWarps;
-            if (e_next < it.e1) ent = __ldg(&a.entries[e_next]);
+            if (e_next < it.e1) {
+                ent = __ldg(&a.entries[e_next]);
+                if (e_next + kConsumerWarps < it.e1) prefetch_l1(&a.entries[e_next + kConsumerWarps]);
+            }
             const int r = cur.x & 0xffffu, ph = (cur.x >> 16) & 31u, pw0 = (cur.x >> 21) & 31u;
             const int npw = (int)((cur.x >> 26) & 7u) + 1;
             const bool red = (cur.x >> 29) & 1u;
             const int key = cur.y & 0xffffu, end = key + (int)((cur.y >> 16) & 0xffu);
             const unsigned smask = (cur.y >> 24) & 0xfu;
-            // axis tables of this fragment (uniform addresses: one sector each)
+            // axis tables of this fragment (uniform addresses: one sector each); the next fragment's are pulled into L1
             const uint4* yt = a.ytab + (size_t)r * a.ny + ph * SR;
             const uint4* xt = a.xtab + (size_t)r * a.nx + pw0 * SR;
             const uint4 yA = __ldg(yt);
@@ -622,26 +670,18 @@ roi_align_stream_fwd(const StreamArgs a) {
             if (SR == 2) yB = __ldg(yt + 1);
             uint4 xA = __ldg(xt), xB = xA;
             if (SR == 2) xB = __ldg(xt + 1);
-            // rows below the key are no longer needed by this warp (entries are sorted by key)
-            if (rel < key) {
-                if (lane == 0) {
-                    int rs = rel_slot;
-                    for (int y = rel; y < key; ++y) { mbar_arrive(bars + 8u * (kMaxSlots + rs)); if (++rs == a.K) rs = 0; }
-                }
-                rel_slot = (rel_slot + (key - rel)) % a.K;
-                rel = key;
+            if (e_next < it.e1) {
+                const int rn = ent.x & 0xffffu;
+                const uint4* ytn = a.ytab + (size_t)rn * a.ny + ((ent.x >> 16) & 31u) * SR;
+                const uint4* xtn = a.xtab + (size_t)rn * a.nx + ((ent.x >> 21) & 31u) * SR;
+                prefetch_l1(ytn); prefetch_l1(xtn); prefetch_l1(xtn + 8);
             }
-            // rows [key, end) must be resident
+            acquire_to(key, 0x2000u);                           // entries are sorted by key: rows below it are done with
+            release_to(key);
+            acquire_to(end, 0x2800u);                           // rows [key, end) must be resident
             SDBG(3, ((u64)cur.x << 32) | (u64)cur.y);
-            while (acq < end) {
-                mbar_wait(bars + 8u * acq_slot, (fphase >> acq_slot) & 1u, 0x2000u + (unsigned)acq);
-                fphase ^= 1u << acq_slot;
-                ++acq;
-                if (++acq_slot == a.K) acq_slot = 0;
-            }
-            SDBG(0, 4);
             // row bases for this lane and the packed axis weights (uniform; hoisted out of the bin loop)
-            const unsigned rt0 = lc + yA.z, rb0 = lc + yA.w, rt1 = lc + yB.z, rb1 = lc + yB.w;
+            const unsigned rt0 = lc + yA.z, rt1 = lc + yB.z;
             const u64 hh0 = pack2f(__uint_as_float(yA.x), __uint_as_float(yA.x)), ll0 = pack2f(__uint_as_float(yA.y), __uint_as_float(yA.y));
             const u64 hh1 = pack2f(__uint_as_float(yB.x), __uint_as_float(yB.x)), ll1 = pack2f(__uint_as_float(yB.y), __uint_as_float(yB.y));
             for (int b = 0; b < npw; ++b) {
@@ -654,23 +694,23 @@ roi_align_stream_fwd(const StreamArgs a) {
                 const u64 wxB = pack2f(__uint_as_float(cxB.x), __uint_as_float(cxB.y));
                 float acc = 0.f;
                 if (SR == 1) {
-                    const Taps t0 = load_taps(rt0, rb0, cxA.z);
+                    const Taps t0 = load_taps<RB>(rt0 + cxA.z);
                     acc = __fadd_rn(acc, sample_val(t0, hh0, ll0, wxA));
                 } else if (smask == 0xfu) {
                     // all 16 taps are requested before the first one is used
-                    const Taps t0 = load_taps(rt0, rb0, cxA.z);
-                    const Taps t1 = load_taps(rt0, rb0, cxB.z);
-                    const Taps t2 = load_taps(rt1, rb1, cxA.z);
-                    const Taps t3 = load_taps(rt1, rb1, cxB.z);
+                    const Taps t0 = load_taps<RB>(rt0 + cxA.z);
+                    const Taps t1 = load_taps<RB>(rt0 + cxB.z);
+                    const Taps t2 = load_taps<RB>(rt1 + cxA.z);
+                    const Taps t3 = load_taps<RB>(rt1 + cxB.z);
                     acc = __fadd_rn(acc, sample_val(t0, hh0, ll0, wxA));        // the reference's order: iy outer, ix inner
                     acc = __fadd_rn(acc, sample_val(t1, hh0, ll0, wxB));
                     acc = __fadd_rn(acc, sample_val(t2, hh1, ll1, wxA));
                     acc = __fadd_rn(acc, sample_val(t3, hh1, ll1, wxB));
                 } else {
-                    if (smask & 1u) acc = __fadd_rn(acc, sample_val(load_taps(rt0, rb0, cxA.z), hh0, ll0, wxA));
-                    if (smask & 2u) acc = __fadd_rn(acc, sample_val(load_taps(rt0, rb0, cxB.z), hh0, ll0, wxB));
-                    if (smask & 4u) acc = __fadd_rn(acc, sample_val(load_taps(rt1, rb1, cxA.z), hh1, ll1, wxA));
-                    if (smask & 8u) acc = __fadd_rn(acc, sample_val(load_taps(rt1, rb1, cxB.z), hh1, ll1, wxB));
+                    if (smask & 1u) acc = __fadd_rn(acc, sample_val(load_taps<RB>(rt0 + cxA.z), hh0, ll0, wxA));
+                    if (smask & 2u) acc = __fadd_rn(acc, sample_val(load_taps<RB>(rt0 + cxB.z), hh0, ll0, wxB));
+                    if (smask & 4u) acc = __fadd_rn(acc, sample_val(load_taps<RB>(rt1 + cxA.z), hh1, ll1, wxA));
+                    if (smask & 8u) acc = __fadd_rn(acc, sample_val(load_taps<RB>(rt1 + cxB.z), hh1, ll1, wxB));
                 }
                 stage[b * kStageStride + lane] = __fmul_rn(acc, kInvCount);       // count 1 / 4: exact, == the reference's division
             }
@@ -694,17 +734,13 @@ roi_align_stream_fwd(const StreamArgs a) {
             __syncwarp();
             e = e_next;
         }
-        // item tail: stay in step with the producer (every warp waits for and releases every row of the item)
+        // item tail: nothing more to read -- give back what is held, then pass the remaining rows through one by one
+        // (a warp that held rows while waiting for later ones could starve the producers of slots)
         SDBG(0, 5);
+        release_to(acq);
         while (acq < it.yhi) {
-            mbar_wait(bars + 8u * acq_slot, (fphase >> acq_slot) & 1u, 0x3000u + (unsigned)acq);
-            fphase ^= 1u << acq_slot;
-            ++acq;
-            if (++acq_slot == a.K) acq_slot = 0;
-        }
-        if (lane == 0) {
-            int rs = rel_slot;
-            for (int y = rel; y < it.yhi; ++y) { mbar_arrive(bars + 8u * (kMaxSlots + rs)); if (++rs == a.K) rs = 0; }
+            acquire_to(acq + 1, 0x3000u);
+            release_to(acq);
         }
         __syncwarp();
         SDBG(0, 6);
@@ -733,7 +769,7 @@ bool stream_geometry(int N, int R, int C, int H, int W, int PH, int PW, int sr, 
     long best_score = -1;
     for (int m = 1; m <= 3; ++m) {                            // SX = 32 m + 1: odd channel stride, m coalesced chunks + 1 column
         const int sx = 32 * m + 1;
-        int k = (int)(ring_budget / (128u * (unsigned)sx));
+        int k = (int)(ring_budget / (128u * (unsigned)sx)) - 1;       // one physical slot is the mirror of slot 0
         if (k > kMaxSlots) k = kMaxSlots;
         if (k < 12) continue;
         const int hx = m >= 2 ? 9 : 5;                        // halo: bins whose x samples are <= hx + 1 cells apart stay whole
@@ -766,7 +802,7 @@ bool stream_geometry(int N, int R, int C, int H, int W, int PH, int PW, int sr, 
     lay->piece_off = off; off = align_up_sz(off + ((size_t)g->pieces + 1) * 4, 256);
     lay->entries_off = off; off = align_up_sz(off + (size_t)g->max_entries * 8, 256);
     lay->ws_bytes = off;
-    *smem_bytes = (unsigned)g->K * (unsigned)g->row_bytes + fixed;
+    *smem_bytes = (unsigned)(g->K + 1) * (unsigned)g->row_bytes + fixed;
     return true;
 }
 
@@ -849,8 +885,7 @@ int roi_align_forward_stream(const float* bottom, float scale, int N, int R, int
     StreamArgs a;
     a.ytab = ws.ytab; a.xtab = ws.xtab; a.entries = ws.entries; a.rowptr = ws.rowptr; a.maxend = ws.maxend;
     a.piece_start = ws.piece_start; a.bottom = bottom; a.out = top; a.row_map = row_map;
-    a.C = C; a.H = H; a.W = W; a.S = g.S; a.G = g.G; a.K = g.K; a.SX = g.SX; a.WX = g.WX; a.PH = PH; a.PW = PW; a.ny = g.ny; a.nx = g.nx;
-    a.row_bytes = g.row_bytes;
+    a.C = C; a.H = H; a.W = W; a.S = g.S; a.G = g.G; a.K = g.K; a.WX = g.WX; a.PH = PH; a.PW = PW; a.ny = g.ny; a.nx = g.nx;
     const bool async = option_get(kOptStreamStage) != 'r';          // B200_STREAM_STAGE=regs selects LDG -> registers -> STS (A/B)
     const int m = (g.SX - 1) / 32;
     if (sr == 1) {
