@@ -36,7 +36,7 @@ namespace b200 {
 
 constexpr int kRowCells = 32;             // cells per x-tile = lanes of the write-out
 constexpr int kTableThreads = 256;
-constexpr int kTransposeChannels = 64;    // channels per transpose CTA
+constexpr int kTransposeChannelsMax = 256; // channels per transpose CTA (whole 1 KB rows of the channel-innermost copy at C = 256)
 constexpr int kRankRows = 1024;           // N * H up to which the main kernel orders the rows by weight
 
 struct __align__(16) BwdRoi {
@@ -84,7 +84,7 @@ static bool rows_plan(int N, int R, int C, int H, int W, int PH, int PW, int sr,
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTableThreads)
 roi_align_bwd_rows_tables(const float* __restrict__ rois, const float* __restrict__ dy, float scale, int N, int R, int C, int H,
-                          int W, int PH, int PW, int sr, int table_ctas, BwdRoi* __restrict__ roi_out,
+                          int W, int PH, int PW, int sr, int table_ctas, int tr_ch, BwdRoi* __restrict__ roi_out,
                           AxisEntry* __restrict__ xtab, int* __restrict__ zeroed, uint2* __restrict__ row_list, int row_cap,
                           uint4* __restrict__ ovf, float* __restrict__ dyt, const int* __restrict__ row_map) {
     extern __shared__ __align__(16) float s_tr[];
@@ -122,10 +122,10 @@ roi_align_bwd_rows_tables(const float* __restrict__ rois, const float* __restric
     }
     // ---- dY (r, c, bin) -> dYt (r, bin, c) / count for one RoI and one block of channels
     const int bins = PH * PW;
-    const int cblocks = (C + kTransposeChannels - 1) / kTransposeChannels;
+    const int cblocks = (C + tr_ch - 1) / tr_ch;
     const int t = blockIdx.x - table_ctas;
-    const int r = t / cblocks, c0 = (t - r * cblocks) * kTransposeChannels;
-    const int cc = min(kTransposeChannels, C - c0);
+    const int r = t / cblocks, c0 = (t - r * cblocks) * tr_ch;
+    const int cc = min(tr_ch, C - c0);
     const int stride = bins | 1;                            // odd: the transposed read below is bank-conflict free
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kTableThreads / 32;
@@ -417,17 +417,20 @@ int roi_align_backward_rows(const float* top_diff, float scale, int N, int R, in
     if (workspace == nullptr || workspace_bytes < p.ws_bytes) return 1000;
     unsigned char* ws = (unsigned char*)workspace;
     const int bins = PH * PW;
-    const size_t smem_tr = (size_t)kTransposeChannels * (bins | 1) * sizeof(float);
+    int tr_ch = kTransposeChannelsMax;                       // as many channels per CTA as fit ~100 KB (two CTAs per SM)
+    while (tr_ch > 32 && (size_t)tr_ch * (bins | 1) * sizeof(float) > 100 * 1024) tr_ch >>= 1;
+    if (tr_ch > C) tr_ch = (C + 31) / 32 * 32;
+    const size_t smem_tr = (size_t)tr_ch * (bins | 1) * sizeof(float);
     if (smem_tr > 200 * 1024) return 1000;
     cudaError_t err = cudaSuccess;
     if (smem_tr > 48 * 1024) err = cudaFuncSetAttribute(roi_align_bwd_rows_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tr);
     if (err != cudaSuccess) return (int)err;
     err = cudaMemsetAsync(ws + p.zero_off, 0, p.zero_bytes, stream);    // item counter, overflow count, units per row
     if (err != cudaSuccess) return (int)err;
-    const int cblocks = (C + kTransposeChannels - 1) / kTransposeChannels;
+    const int cblocks = (C + tr_ch - 1) / tr_ch;
     const int table_ctas = (R * (p.ny + p.nx) + kTableThreads - 1) / kTableThreads;
     roi_align_bwd_rows_tables<<<table_ctas + R * cblocks, kTableThreads, smem_tr, stream>>>(
-        rois, top_diff, scale, N, R, C, H, W, PH, PW, sr, table_ctas, reinterpret_cast<BwdRoi*>(ws + p.roi_off),
+        rois, top_diff, scale, N, R, C, H, W, PH, PW, sr, table_ctas, tr_ch, reinterpret_cast<BwdRoi*>(ws + p.roi_off),
         reinterpret_cast<AxisEntry*>(ws + p.xtab_off), reinterpret_cast<int*>(ws + p.zero_off),
         reinterpret_cast<uint2*>(ws + p.row_list_off), p.row_cap, reinterpret_cast<uint4*>(ws + p.ovf_off),
         reinterpret_cast<float*>(ws + p.dyt_off), row_map);

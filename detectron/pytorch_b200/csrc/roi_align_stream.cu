@@ -45,7 +45,8 @@ constexpr int kProducerWarps = 4;
 constexpr int kStreamThreads = 32 * (kConsumerWarps + kProducerWarps);
 constexpr int kFragBins = 8;                                  // bins per fragment (one flush)
 constexpr int kStageStride = 36;                              // words per staged bin: conflict-free both ways
-constexpr int kStageWordsPerWarp = kFragBins * kStageStride;
+constexpr int kTabWords = 18 * 4;                              // per-warp axis-table buffer: 16 x entries + 2 y entries
+constexpr int kStageWordsPerWarp = kFragBins * kStageStride + kTabWords;
 constexpr int kMaxSlots = 32;                                 // ring depth K <= 32 (phase bits live in one register)
 constexpr int kAxisMaxS = 32;                                 // P * sampling_ratio per axis
 constexpr int kPrepThreads = 128;
@@ -411,7 +412,11 @@ __device__ __forceinline__ void cp_async4_if(unsigned dst, const float* src, boo
 __device__ __forceinline__ void cp_async_arrive(unsigned bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 
 struct StreamArgs {
     const uint4* ytab;
@@ -610,6 +615,7 @@ roi_align_stream_fwd(const StreamArgs a) {
 
     // =============================== consumers ===============================
     float* stage = stage_all + warp * kStageWordsPerWarp;
+    const unsigned tbuf = smem_addr(stage + kFragBins * kStageStride);      // 16-byte aligned: 288 words precede it
     const unsigned lane_base = ring + (unsigned)(lane * SX) * 4u;
     const int bins = a.PH * a.PW;
     unsigned fphase = 0u;
@@ -647,39 +653,46 @@ roi_align_stream_fwd(const StreamArgs a) {
             }
         };
 
+        // Fragment pipeline (global-load latency is the enemy: entries and tables are needed by every lane at once):
+        //   entry records are fetched two fragments ahead; the axis tables of the NEXT fragment are fetched one fragment
+        //   ahead, lane-distributed (lanes 0..15: its x entries, lanes 16..17: its y entries -- one 16-byte load per lane),
+        //   parked in registers, and dropped into this warp's table buffer in shared memory when their fragment starts;
+        //   the bin loop then reads them with broadcast LDS.128.
+        auto load_tab = [&](const uint2& en) -> uint4 {
+            const int rn = en.x & 0xffffu, phn = (en.x >> 16) & 31u, pwn = (en.x >> 21) & 31u, nn = (int)((en.x >> 26) & 7u) + 1;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (lane < nn * SR) v = __ldg(a.xtab + (size_t)rn * a.nx + pwn * SR + lane);
+            else if (lane >= 16 && lane < 16 + SR) v = __ldg(a.ytab + (size_t)rn * a.ny + phn * SR + (lane - 16));
+            return v;
+        };
         int e = it.e0 + warp;
-        uint2 ent = make_uint2(0u, 0u);
-        if (e < it.e1) ent = __ldg(&a.entries[e]);
+        uint2 ent0 = make_uint2(0u, 0u), ent1 = make_uint2(0u, 0u);
+        uint4 tab = make_uint4(0u, 0u, 0u, 0u);
+        if (e < it.e1) { ent0 = __ldg(&a.entries[e]); tab = load_tab(ent0); }
+        if (e + kConsumerWarps < it.e1) ent1 = __ldg(&a.entries[e + kConsumerWarps]);
         while (e < it.e1) {
-            const uint2 cur = ent;
+            const uint2 cur = ent0;
             const int e_next = e + kConsumerWarps;
-            if (e_next < it.e1) {
-                ent = __ldg(&a.entries[e_next]);
-                if (e_next + kConsumerWarps < it.e1) prefetch_l1(&a.entries[e_next + kConsumerWarps]);
-            }
+            // this fragment's tables -> shared (the previous fragment's readers are past their last LDS: trailing syncwarp)
+            if (lane < 18) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tbuf + lane * 16), "r"(tab.x), "r"(tab.y), "r"(tab.z), "r"(tab.w) : "memory");
+            __syncwarp();
+            ent0 = ent1;
+            if (e_next < it.e1) tab = load_tab(ent0);                               // in flight while this fragment computes
+            if (e_next + kConsumerWarps < it.e1) ent1 = __ldg(&a.entries[e_next + kConsumerWarps]);
             const int r = cur.x & 0xffffu, ph = (cur.x >> 16) & 31u, pw0 = (cur.x >> 21) & 31u;
             const int npw = (int)((cur.x >> 26) & 7u) + 1;
             const bool red = (cur.x >> 29) & 1u;
             const int key = cur.y & 0xffffu, end = key + (int)((cur.y >> 16) & 0xffu);
             const unsigned smask = (cur.y >> 24) & 0xfu;
-            // axis tables of this fragment (uniform addresses: one sector each); the next fragment's are pulled into L1
-            const uint4* yt = a.ytab + (size_t)r * a.ny + ph * SR;
-            const uint4* xt = a.xtab + (size_t)r * a.nx + pw0 * SR;
-            const uint4 yA = __ldg(yt);
-            uint4 yB = yA;
-            if (SR == 2) yB = __ldg(yt + 1);
-            uint4 xA = __ldg(xt), xB = xA;
-            if (SR == 2) xB = __ldg(xt + 1);
-            if (e_next < it.e1) {
-                const int rn = ent.x & 0xffffu;
-                const uint4* ytn = a.ytab + (size_t)rn * a.ny + ((ent.x >> 16) & 31u) * SR;
-                const uint4* xtn = a.xtab + (size_t)rn * a.nx + ((ent.x >> 21) & 31u) * SR;
-                prefetch_l1(ytn); prefetch_l1(xtn); prefetch_l1(xtn + 8);
-            }
             acquire_to(key, 0x2000u);                           // entries are sorted by key: rows below it are done with
             release_to(key);
             acquire_to(end, 0x2800u);                           // rows [key, end) must be resident
             SDBG(3, ((u64)cur.x << 32) | (u64)cur.y);
+            const uint4 yA = lds128(tbuf + 16 * 16);
+            uint4 yB = yA;
+            if (SR == 2) yB = lds128(tbuf + 17 * 16);
+            uint4 xA = lds128(tbuf), xB = xA;
+            if (SR == 2) xB = lds128(tbuf + 16);
             // row bases for this lane and the packed axis weights (uniform; hoisted out of the bin loop)
             const unsigned rt0 = lc + yA.z, rt1 = lc + yB.z;
             const u64 hh0 = pack2f(__uint_as_float(yA.x), __uint_as_float(yA.x)), ll0 = pack2f(__uint_as_float(yA.y), __uint_as_float(yA.y));
@@ -687,8 +700,8 @@ roi_align_stream_fwd(const StreamArgs a) {
             for (int b = 0; b < npw; ++b) {
                 const uint4 cxA = xA, cxB = xB;
                 if (b + 1 < npw) {
-                    xA = __ldg(xt + (b + 1) * SR);
-                    if (SR == 2) xB = __ldg(xt + (b + 1) * SR + 1);
+                    xA = lds128(tbuf + (unsigned)((b + 1) * SR) * 16u);
+                    if (SR == 2) xB = lds128(tbuf + (unsigned)((b + 1) * SR + 1) * 16u);
                 }
                 const u64 wxA = pack2f(__uint_as_float(cxA.x), __uint_as_float(cxA.y));
                 const u64 wxB = pack2f(__uint_as_float(cxB.x), __uint_as_float(cxB.y));
