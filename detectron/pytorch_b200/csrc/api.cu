@@ -9,7 +9,7 @@ namespace b200 {
 unsigned long long g_launch_count = 0;
 
 static const char* const kOptionNames[kNumOptions] = {"B200_ROI_ALIGN_PATH", "B200_ROI_ALIGN_BWD_PATH", "B200_ROI_ALIGN_BWD_CPL",
-                                                      "B200_FWD_ZERO", "B200_NMS_SCAN", "B200_STREAM_STAGE"};
+                                                      "B200_FWD_ZERO", "B200_NMS_SCAN", "B200_STREAM_STAGE", "B200_STREAM_PHASES"};
 static int g_options[kNumOptions];
 static std::once_flag g_options_once;
 
@@ -78,6 +78,8 @@ static bool tiled_pays_off(int R, int C, int H, int W, int PH, int PW) {
     return taps >= (1LL << 18) && (long long)H * W >= 1024;
 }
 int nms(const float*, int, int, float, int*, int*, void*, size_t, cudaStream_t);
+size_t nms_batched_workspace_bytes(const int*, int);
+int nms_batched(const float*, const int*, int, int, float, int*, int*, void*, size_t, cudaStream_t);
 size_t roi_align_bwd_nhwc_workspace_bytes(int, int, int, int);
 int roi_align_backward_nhwc(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
 
@@ -348,6 +350,22 @@ int b200_nms(const float* boxes_dev, int boxes_num, int boxes_dim, float nms_ove
     if (!num_out_dev || (boxes_num > 0 && (!boxes_dev || !keep_out_dev))) return B200_ROI_EINVAL;
     return nms(boxes_dev, boxes_num, boxes_dim, nms_overlap_thresh, keep_out_dev, num_out_dev, workspace,
                workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t b200_nms_batched_workspace_bytes(const int* counts_host, int num_problems) {
+    if (!counts_host) return 0;
+    return nms_batched_workspace_bytes(counts_host, num_problems);
+}
+
+int b200_nms_batched(const float* boxes_dev, const int* counts_host, int num_problems, int boxes_dim, float nms_overlap_thresh,
+                     int* keep_out_dev, int* num_out_dev, void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+    if (!counts_host || num_problems < 1 || !num_out_dev) return B200_ROI_EINVAL;
+    long long total = 0;
+    for (int p = 0; p < num_problems && p < 64; ++p) total += counts_host[p] > 0 ? counts_host[p] : 0;
+    if (total > 0 && (!boxes_dev || !keep_out_dev)) return B200_ROI_EINVAL;
+    const int rc = nms_batched(boxes_dev, counts_host, num_problems, boxes_dim, nms_overlap_thresh, keep_out_dev, num_out_dev, workspace,
+                               workspace_bytes, (cudaStream_t)stream);
+    return rc == 1000 ? B200_ROI_EINVAL : rc;
 }
 
 }  // extern "C"

@@ -28,6 +28,7 @@ enum Option {
     kOptFwdZero,          // B200_FWD_ZERO            = dense | bins
     kOptNmsScan,          // B200_NMS_SCAN            = resolver | simple
     kOptStreamStage,      // B200_STREAM_STAGE        = async (cp.async) | regs (LDG -> registers -> STS)
+    kOptStreamPhases,     // B200_STREAM_PHASES       = all | prepass (timing probe: the main kernel is not launched)
     kNumOptions
 };
 int option_get(Option which);

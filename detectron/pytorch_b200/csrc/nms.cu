@@ -78,13 +78,11 @@ struct __align__(16) ColBoxEx {
 // [2^-20, 2^20]: lo = -inf, hi = +inf) is marked undecided and re-evaluated with the exact recipe (nms_bit) after
 // the main loop.  Results are therefore bit-identical to the all-division version; the main loop is branch-free,
 // fully unrolled (bit positions are immediates) and ~26 instructions per pair instead of ~42.
-__global__ void __launch_bounds__(kNmsTile)
-nms_mask_kernel(const float* __restrict__ boxes, int n, int dim, float thresh, float lo, float hi,
-                u64* __restrict__ mask, u64* __restrict__ diag_t) {
+__device__ __forceinline__ void nms_mask_tile(const float* __restrict__ boxes, int n, int dim, float thresh, float lo, float hi,
+                                              u64* __restrict__ mask, u64* __restrict__ diag_t, int idx) {
     const int col_blocks = (n + kNmsTile - 1) / kNmsTile;
     int row_start, col_start;
     {
-        const int idx = blockIdx.x;
         if (idx < col_blocks) {
             row_start = col_start = idx;
         } else {                                    // k enumerates the pairs row < col: k = col (col - 1) / 2 + row
@@ -159,6 +157,39 @@ nms_mask_kernel(const float* __restrict__ boxes, int n, int dim, float thresh, f
     }
 }
 
+__global__ void __launch_bounds__(kNmsTile)
+nms_mask_kernel(const float* __restrict__ boxes, int n, int dim, float thresh, float lo, float hi,
+                u64* __restrict__ mask, u64* __restrict__ diag_t) {
+    nms_mask_tile(boxes, n, dim, thresh, lo, hi, mask, diag_t, (int)blockIdx.x);
+}
+
+// ---- several independent problems in one launch (the (image, level) proposal sets of one step) ----
+constexpr int kNmsMaxProblems = 64;
+struct NmsBatch {
+    int count;
+    int n[kNmsMaxProblems];                     // boxes of problem p
+    int box_off[kNmsMaxProblems];               // its first row in `boxes` / first slot in `keep_out`
+    int tile_off[kNmsMaxProblems + 1];          // its first CTA of the mask launch
+    unsigned long long mask_off[kNmsMaxProblems];       // word offsets into the workspace
+    unsigned long long diag_off[kNmsMaxProblems];
+};
+
+__global__ void __launch_bounds__(kNmsTile)
+nms_mask_batched_kernel(const float* __restrict__ boxes, const __grid_constant__ NmsBatch nb, int dim, float thresh, float lo, float hi,
+                        u64* __restrict__ ws) {
+    int p = 0;                                  // problem of this CTA: tile_off is ascending
+    {
+        int lo_p = 0, hi_p = nb.count - 1;
+        while (lo_p < hi_p) {
+            const int mid = (lo_p + hi_p + 1) >> 1;
+            if (nb.tile_off[mid] <= (int)blockIdx.x) lo_p = mid; else hi_p = mid - 1;
+        }
+        p = lo_p;
+    }
+    nms_mask_tile(boxes + (size_t)nb.box_off[p] * dim, nb.n[p], dim, thresh, lo, hi, ws + nb.mask_off[p], ws + nb.diag_off[p],
+                  (int)blockIdx.x - nb.tile_off[p]);
+}
+
 // Single-CTA greedy scan over the upper-triangular mask.  remv[] (one 64-bit word per column block)
 // lives in shared memory.
 __global__ void __launch_bounds__(kScanThreads)
@@ -225,9 +256,8 @@ nms_scan_kernel(const u64* __restrict__ mask, int n, int col_blocks, int* __rest
 // global memory, lanes = columns (coalesced 256-byte row segments, 8 rows in flight per warp); the resolver
 // only checks that the block REACH steps back has been folded.
 template <int REACH>
-__global__ void __launch_bounds__(kScanThreads)
-nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ diag_t, int n, int col_blocks,
-                         int* __restrict__ keep_out, int* __restrict__ num_out) {
+__device__ __forceinline__ void nms_scan_resolver_body(const u64* __restrict__ mask, const u64* __restrict__ diag_t, int n, int col_blocks,
+                                                       int* __restrict__ keep_out, int* __restrict__ num_out) {
     extern __shared__ u64 sm[];
     const int n_pad = col_blocks * kNmsTile;
     u64* D = sm;                                    // D[0][i] = T[i]; D[t][i] = mask[i][blk(i) + t], 1 <= t < REACH
@@ -355,6 +385,25 @@ nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ d
     }
 }
 
+template <int REACH>
+__global__ void __launch_bounds__(kScanThreads)
+nms_scan_resolver_kernel(const u64* __restrict__ mask, const u64* __restrict__ diag_t, int n, int col_blocks,
+                         int* __restrict__ keep_out, int* __restrict__ num_out) {
+    nms_scan_resolver_body<REACH>(mask, diag_t, n, col_blocks, keep_out, num_out);
+}
+
+// one CTA per problem
+template <int REACH>
+__global__ void __launch_bounds__(kScanThreads)
+nms_scan_resolver_batched_kernel(const u64* __restrict__ ws, const __grid_constant__ NmsBatch nb, int* __restrict__ keep_out,
+                                 int* __restrict__ num_out) {
+    const int p = blockIdx.x;
+    const int n = nb.n[p];
+    if (n == 0) { if (threadIdx.x == 0) num_out[p] = 0; return; }
+    nms_scan_resolver_body<REACH>(ws + nb.mask_off[p], ws + nb.diag_off[p], n, (n + kNmsTile - 1) / kNmsTile, keep_out + nb.box_off[p],
+                                  num_out + p);
+}
+
 __global__ void nms_empty_kernel(int* num_out) { *num_out = 0; }
 
 void nms_set_timing_buffer(unsigned long long* buf) { cudaMemcpyToSymbol(g_nms_timing, &buf, sizeof(buf)); }
@@ -402,6 +451,65 @@ int nms(const float* boxes, int n, int dim, float thresh, int* keep_out, int* nu
         if (e != cudaSuccess) return (int)e;
     }
     nms_scan_kernel<<<1, kScanThreads, smem, stream>>>(mask, n, cb, keep_out, num_out);
+    return finish_launch(2);
+}
+
+// ---- batched entry: `num_problems` independent score-sorted box sets, stored back to back in `boxes` ----
+static bool nms_batch_plan(const int* counts, int num_problems, NmsBatch* nb, size_t* ws_words, int* max_n) {
+    if (num_problems < 1 || num_problems > kNmsMaxProblems) return false;
+    nb->count = num_problems;
+    long long box = 0, tile = 0;
+    size_t words = 0;
+    int mx = 0;
+    for (int p = 0; p < num_problems; ++p) {
+        const int n = counts[p];
+        if (n < 0) return false;
+        const long long cb = (n + kNmsTile - 1) / kNmsTile;
+        nb->n[p] = n; nb->box_off[p] = (int)box; nb->tile_off[p] = (int)tile;
+        nb->mask_off[p] = words; words += (size_t)n * cb;
+        nb->diag_off[p] = words; words += (size_t)cb * kNmsTile;
+        box += n; tile += cb * (cb + 1) / 2;
+        if (box > 0x7fffffffLL || tile > 0x7fffffffLL) return false;
+        if (n > mx) mx = n;
+    }
+    nb->tile_off[num_problems] = (int)tile;
+    for (int p = num_problems; p < kNmsMaxProblems; ++p) { nb->n[p] = 0; nb->box_off[p] = (int)box; nb->tile_off[p + 1] = (int)tile; nb->mask_off[p] = nb->diag_off[p] = words; }
+    *ws_words = words; *max_n = mx;
+    return true;
+}
+
+size_t nms_batched_workspace_bytes(const int* counts, int num_problems) {
+    NmsBatch nb; size_t words = 0; int mx = 0;
+    if (!nms_batch_plan(counts, num_problems, &nb, &words, &mx)) return 0;
+    return (words * sizeof(u64) + 255) / 256 * 256 + 256;
+}
+
+int nms_batched(const float* boxes, const int* counts, int num_problems, int dim, float thresh, int* keep_out, int* num_out,
+                void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    NmsBatch nb; size_t words = 0; int mx = 0;
+    if (dim < 4 || !nms_batch_plan(counts, num_problems, &nb, &words, &mx)) return B200_ROI_EINVAL;
+    if (workspace == nullptr || workspace_bytes < (words * sizeof(u64) + 255) / 256 * 256) return B200_ROI_EWORKSPACE;
+    float lo = -INFINITY, hi = INFINITY;
+    if (thresh >= 9.5367431640625e-07f && thresh <= 1048576.f) {
+        lo = (float)((double)thresh * (1.0 - 3.814697265625e-06));
+        hi = (float)((double)thresh * (1.0 + 3.814697265625e-06));
+    }
+    const int cb = (mx + kNmsTile - 1) / kNmsTile;
+    int reach = 0;
+    size_t smem_res = 0;
+    for (int r = 4; r >= 2; --r) {
+        const size_t sm_r = sizeof(u64) * ((size_t)r * cb * kNmsTile + 4 * (size_t)cb) + 16;
+        if (sm_r <= 224 * 1024) { reach = r; smem_res = sm_r; break; }
+    }
+    if (reach == 0) return 1000;                        // a problem too large for the pipelined scan: the caller loops over b200_nms
+    u64* ws = (u64*)workspace;
+    if (nb.tile_off[num_problems] > 0)
+        nms_mask_batched_kernel<<<(unsigned)nb.tile_off[num_problems], kNmsTile, 0, stream>>>(boxes, nb, dim, thresh, lo, hi, ws);
+    void (*kern)(const u64*, const NmsBatch, int*, int*) =
+        (reach == 4) ? nms_scan_resolver_batched_kernel<4> : (reach == 3) ? nms_scan_resolver_batched_kernel<3> : nms_scan_resolver_batched_kernel<2>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<num_problems, kScanThreads, smem_res, stream>>>(ws, nb, keep_out, num_out);
     return finish_launch(2);
 }
 

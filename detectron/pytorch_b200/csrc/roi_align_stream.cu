@@ -50,6 +50,7 @@ constexpr int kStageWordsPerWarp = kFragBins * kStageStride + kTabWords;
 constexpr int kMaxSlots = 32;                                 // ring depth K <= 32 (phase bits live in one register)
 constexpr int kAxisMaxS = 32;                                 // P * sampling_ratio per axis
 constexpr int kPrepThreads = 128;
+constexpr unsigned kRowCost = 8u;                             // cost of streaming one row (16 acquires + staging), in bins
 constexpr int kScanCap = 6144;                                // keys whose cost prefix is kept in shared memory by the scan
 constexpr unsigned kSmemBudget = 227u * 1024u;
 
@@ -240,7 +241,7 @@ stream_count(const float* __restrict__ rois, StreamGeom g, StreamWs ws) {
         for (int j = 0; j < kPer; ++j) {                      // thread t owns keys base + t * kPer + j; loads are independent
             const int k = base + t * kPer + j;
             h[j] = k < keys ? (unsigned)__ldcg(&ws.hist[k]) : 0u;
-            c[j] = k < keys ? (unsigned)__ldcg(&ws.cost[k]) + 2u : 0u;
+            c[j] = k < keys ? (unsigned)__ldcg(&ws.cost[k]) + kRowCost : 0u;
         }
         unsigned sh = 0, sc = 0;
 #pragma unroll
@@ -691,41 +692,49 @@ roi_align_stream_fwd(const StreamArgs a) {
             const uint4 yA = lds128(tbuf + 16 * 16);
             uint4 yB = yA;
             if (SR == 2) yB = lds128(tbuf + 17 * 16);
-            uint4 xA = lds128(tbuf), xB = xA;
-            if (SR == 2) xB = lds128(tbuf + 16);
             // row bases for this lane and the packed axis weights (uniform; hoisted out of the bin loop)
             const unsigned rt0 = lc + yA.z, rt1 = lc + yB.z;
             const u64 hh0 = pack2f(__uint_as_float(yA.x), __uint_as_float(yA.x)), ll0 = pack2f(__uint_as_float(yA.y), __uint_as_float(yA.y));
             const u64 hh1 = pack2f(__uint_as_float(yB.x), __uint_as_float(yB.x)), ll1 = pack2f(__uint_as_float(yB.y), __uint_as_float(yB.y));
-            for (int b = 0; b < npw; ++b) {
-                const uint4 cxA = xA, cxB = xB;
-                if (b + 1 < npw) {
-                    xA = lds128(tbuf + (unsigned)((b + 1) * SR) * 16u);
-                    if (SR == 2) xB = lds128(tbuf + (unsigned)((b + 1) * SR + 1) * 16u);
-                }
-                const u64 wxA = pack2f(__uint_as_float(cxA.x), __uint_as_float(cxA.y));
-                const u64 wxB = pack2f(__uint_as_float(cxB.x), __uint_as_float(cxB.y));
-                float acc = 0.f;
-                if (SR == 1) {
-                    const Taps t0 = load_taps<RB>(rt0 + cxA.z);
-                    acc = __fadd_rn(acc, sample_val(t0, hh0, ll0, wxA));
-                } else if (smask == 0xfu) {
-                    // all 16 taps are requested before the first one is used
+            unsigned tb = tbuf;                                   // this bin's x entries (broadcast reads)
+            unsigned sp = smem_addr(stage) + (unsigned)lane * 4u; // where this lane parks the bin's result
+            const unsigned tb_end = tbuf + (unsigned)npw * (SR * 16u);
+            if (SR == 2 && smask == 0xfu) {
+                // whole bins (the common case): all 16 taps are requested before the first one is used
+                do {
+                    const uint4 cxA = lds128(tb), cxB = lds128(tb + 16);
+                    const u64 wxA = pack2f(__uint_as_float(cxA.x), __uint_as_float(cxA.y));
+                    const u64 wxB = pack2f(__uint_as_float(cxB.x), __uint_as_float(cxB.y));
                     const Taps t0 = load_taps<RB>(rt0 + cxA.z);
                     const Taps t1 = load_taps<RB>(rt0 + cxB.z);
                     const Taps t2 = load_taps<RB>(rt1 + cxA.z);
                     const Taps t3 = load_taps<RB>(rt1 + cxB.z);
-                    acc = __fadd_rn(acc, sample_val(t0, hh0, ll0, wxA));        // the reference's order: iy outer, ix inner
+                    float acc = __fadd_rn(0.f, sample_val(t0, hh0, ll0, wxA));   // the reference's order: iy outer, ix inner
                     acc = __fadd_rn(acc, sample_val(t1, hh0, ll0, wxB));
                     acc = __fadd_rn(acc, sample_val(t2, hh1, ll1, wxA));
                     acc = __fadd_rn(acc, sample_val(t3, hh1, ll1, wxB));
-                } else {
-                    if (smask & 1u) acc = __fadd_rn(acc, sample_val(load_taps<RB>(rt0 + cxA.z), hh0, ll0, wxA));
-                    if (smask & 2u) acc = __fadd_rn(acc, sample_val(load_taps<RB>(rt0 + cxB.z), hh0, ll0, wxB));
-                    if (smask & 4u) acc = __fadd_rn(acc, sample_val(load_taps<RB>(rt1 + cxA.z), hh1, ll1, wxA));
-                    if (smask & 8u) acc = __fadd_rn(acc, sample_val(load_taps<RB>(rt1 + cxB.z), hh1, ll1, wxB));
-                }
-                stage[b * kStageStride + lane] = __fmul_rn(acc, kInvCount);       // count 1 / 4: exact, == the reference's division
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sp), "f"(__fmul_rn(acc, kInvCount)) : "memory");   // count 4: exact
+                    tb += 32u; sp += kStageStride * 4u;
+                } while (tb != tb_end);
+            } else {
+                do {
+                    const uint4 cxA = lds128(tb);
+                    uint4 cxB = cxA;
+                    if (SR == 2) cxB = lds128(tb + 16);
+                    const u64 wxA = pack2f(__uint_as_float(cxA.x), __uint_as_float(cxA.y));
+                    const u64 wxB = pack2f(__uint_as_float(cxB.x), __uint_as_float(cxB.y));
+                    float acc = 0.f;
+                    if (SR == 1) {
+                        acc = __fadd_rn(acc, sample_val(load_taps<RB>(rt0 + cxA.z), hh0, ll0, wxA));
+                    } else {
+                        if (smask & 1u) acc = __fadd_rn(acc, sample_val(load_taps<RB>(rt0 + cxA.z), hh0, ll0, wxA));
+                        if (smask & 2u) acc = __fadd_rn(acc, sample_val(load_taps<RB>(rt0 + cxB.z), hh0, ll0, wxB));
+                        if (smask & 4u) acc = __fadd_rn(acc, sample_val(load_taps<RB>(rt1 + cxA.z), hh1, ll1, wxA));
+                        if (smask & 8u) acc = __fadd_rn(acc, sample_val(load_taps<RB>(rt1 + cxB.z), hh1, ll1, wxB));
+                    }
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sp), "f"(__fmul_rn(acc, kInvCount)) : "memory");   // count 1 / 4: exact
+                    tb += SR * 16u; sp += kStageStride * 4u;
+                } while (tb != tb_end);
             }
             __syncwarp();
             // flush: lanes = (channel within a group of 4, bin) -> a store's lanes are consecutive bins of one channel
@@ -910,6 +919,7 @@ int roi_align_forward_stream(const float* bottom, float scale, int N, int R, int
     }
 #define B200_STREAM_LAUNCH(SRV, MV, AV) roi_align_stream_fwd<SRV, MV, AV><<<g.pieces, kStreamThreads, smem, stream>>>(a)
 #define B200_STREAM_LAUNCH_M(SRV, AV) (m == 1 ? B200_STREAM_LAUNCH(SRV, 1, AV) : m == 2 ? B200_STREAM_LAUNCH(SRV, 2, AV) : B200_STREAM_LAUNCH(SRV, 3, AV))
+    if (option_get(kOptStreamPhases) == 'p') return finish_launch(2);          // timing probe: prepass only (output undefined)
     if (sr == 1) { if (async) B200_STREAM_LAUNCH_M(1, true); else B200_STREAM_LAUNCH_M(1, false); }
     else         { if (async) B200_STREAM_LAUNCH_M(2, true); else B200_STREAM_LAUNCH_M(2, false); }
 #undef B200_STREAM_LAUNCH_M

@@ -13,9 +13,11 @@ Configuration: the reference reads `cfg[TRAIN|TEST].RPN_{PRE,POST}_NMS_TOP_N, RP
 global config at call time; pass that object as `cfg=` to do the same, or give the four values per mode as keyword
 arguments (`train=dict(...)`, `test=dict(...)`); defaults are the reference's (lib/core/config.py:127-141, 200-214).
 
-Documented differences (see oracle/proposals.py): equal scores are ordered by ascending (h, w, a) index (the
-reference's argpartition/argsort order of ties is unspecified), and NMS suppresses at IoU > thresh with the CUDA
-kernel's rounding (the reference's host NMS uses >=); results on the golden vectors are identical.
+Documented differences (see oracle/proposals.py): the order of EQUAL scores is unspecified, as in the reference
+(its argpartition/argsort, our torch.topk; only the full stable sort taken when pre_nms_topN covers every anchor orders
+ties by ascending (h, w, a) index), and NMS suppresses at IoU > thresh with the CUDA kernel's rounding (the reference's
+host NMS uses >=); results on the golden vectors are identical.  All images of a call -- and, through
+generate_proposals_batched, all FPN levels of a step -- share ONE batched NMS launch pair and ONE host read.
 """
 import numpy as np
 import torch
@@ -57,37 +59,23 @@ class GenerateProposalsOp(nn.Module):
     def forward(self, rpn_cls_prob, rpn_bbox_pred, im_info):
         """rpn_cls_prob (N, A, H, W), rpn_bbox_pred (N, 4A, H, W) CUDA fp32; im_info (N, 3) [height, width, scale] (any
         device).  Returns numpy arrays like the reference: rois (R, 5) [batch, x1, y1, x2, y2], roi_probs (R, 1)."""
+        return generate_proposals_batched([self], [rpn_cls_prob], [rpn_bbox_pred], im_info)[0]
+
+    def _decode_images(self, rpn_cls_prob, rpn_bbox_pred, info):
+        """top-k + decode for every image of this level: list of (dets (k, 5), valid (k,)) CUDA tensors, nothing synchronised."""
         if not rpn_cls_prob.is_cuda:
             raise NotImplementedError("GenerateProposalsOp (B200) needs CUDA tensors; the host path is the reference's own")
+        A = rpn_cls_prob.size(1)
+        if A != self._num_anchors or rpn_bbox_pred.size(1) != 4 * A:
+            raise ValueError("score map has %d anchors per cell and the deltas %d channels, but the op was built with %d anchors"
+                             % (A, rpn_bbox_pred.size(1), self._num_anchors))
         scores = rpn_cls_prob.detach().float()
         deltas = rpn_bbox_pred.detach().float().contiguous()
-        info = im_info.detach().cpu().numpy().astype(np.float32) if torch.is_tensor(im_info) else np.asarray(im_info, np.float32)
         pre, post, thresh, min_size = self._mode_params()
-        per_image = [self.proposals_for_one_image(info[i], deltas[i], scores[i], pre, post, thresh, min_size)
-                     for i in range(scores.size(0))]
-        # one D2H per image, after all images have been enqueued
-        rois = np.empty((0, 5), dtype=np.float32)
-        probs = np.empty((0, 1), dtype=np.float32)
-        t_rois, t_probs = [], []
-        for i, (dets, valid, keep, num) in enumerate(per_image):
-            n = int(num.item()) if num is not None else dets.size(0)
-            k = keep[:n].long() if keep is not None else torch.arange(dets.size(0), device=dets.device)
-            k = k[valid[k] != 0]
-            if thresh > 0 and post > 0:
-                k = k[:post]
-            if self._return_tensors:
-                d = dets[k]
-                t_rois.append(torch.cat([torch.full((d.size(0), 1), float(i), device=d.device), d[:, :4]], dim=1))
-                t_probs.append(d[:, 4:5])
-                continue
-            d = dets[k].cpu().numpy()
-            rois = np.append(rois, np.hstack((np.full((d.shape[0], 1), i, dtype=np.float32), d[:, :4])), axis=0)
-            probs = np.append(probs, d[:, 4:5], axis=0)
-        if self._return_tensors:
-            return torch.cat(t_rois, dim=0), torch.cat(t_probs, dim=0)
-        return rois, probs
+        return [self.proposals_for_one_image(info[i], deltas[i], scores[i], pre, post, thresh, min_size, run_nms=False)[:2]
+                for i in range(scores.size(0))]
 
-    def proposals_for_one_image(self, im_info, bbox_deltas, scores, pre_nms_topN, post_nms_topN, nms_thresh, min_size):
+    def proposals_for_one_image(self, im_info, bbox_deltas, scores, pre_nms_topN, post_nms_topN, nms_thresh, min_size, run_nms=True):
         """Device part for one image: returns (dets (k, 5), valid (k), keep indices, number kept) as CUDA tensors."""
         A, H, W = scores.shape
         dev = scores.device
@@ -108,7 +96,72 @@ class GenerateProposalsOp(nn.Module):
                                                 float(im_info[0]), float(im_info[1]), min_size_scaled, dets.data_ptr(),
                                                 valid.data_ptr(), torch.cuda.current_stream().cuda_stream),
                        "b200_proposal_decode")
-        if nms_thresh > 0 and k > 0:
+        if run_nms and nms_thresh > 0 and k > 0:
             keep, num = ops.nms_raw(dets, float(nms_thresh))
             return dets, valid, keep, num
         return dets, valid, None, None
+
+
+def generate_proposals_batched(op_list, cls_probs, bbox_preds, im_info):
+    """All (level, image) proposal sets of one step with ONE batched NMS (b200_nms_batched: one mask launch over every
+    problem's tiles, one scan CTA per problem) and ONE device-to-host read of the kept counts -- the reference runs them one
+    after the other on the host (lib/modeling/FPN.py loops the levels, generate_proposals.py:91-99 the images).
+
+    op_list[l] is the GenerateProposalsOp of level l; cls_probs[l] / bbox_preds[l] its (N, A, H, W) / (N, 4A, H, W) maps.
+    Returns [(rois, roi_probs)] per level, exactly what op_list[l](cls_probs[l], bbox_preds[l], im_info) returns (numpy
+    arrays, or CUDA tensors for ops built with return_tensors=True)."""
+    info = im_info.detach().cpu().numpy().astype(np.float32) if torch.is_tensor(im_info) else np.asarray(im_info, np.float32)
+    per_level = [op._decode_images(p, d, info) for op, p, d in zip(op_list, cls_probs, bbox_preds)]
+    params = [op._mode_params() for op in op_list]
+    # problems that go through NMS, grouped by threshold (one batched call per distinct threshold; normally one)
+    keep_of = {}
+    by_thresh = {}
+    for l, (imgs, (pre, post, thresh, min_size)) in enumerate(zip(per_level, params)):
+        for i, (dets, valid) in enumerate(imgs):
+            if thresh > 0 and dets.size(0) > 0:
+                by_thresh.setdefault(float(thresh), []).append((l, i))
+    for thresh, probs in by_thresh.items():
+        for c0 in range(0, len(probs), 64):                                     # b200_nms_batched takes up to 64 problems
+            chunk = probs[c0:c0 + 64]
+            counts = [int(per_level[l][i][0].size(0)) for l, i in chunk]
+            if max(counts) > 13000:                                             # beyond the pipelined scan: one call per problem
+                for (l, i) in chunk:
+                    keep, num = ops.nms_raw(per_level[l][i][0], thresh)
+                    keep_of[(l, i)] = (keep, num, 0, 0)
+                continue
+            cat = torch.cat([per_level[l][i][0] for l, i in chunk], dim=0) if len(chunk) > 1 else per_level[chunk[0][0]][chunk[0][1]][0]
+            keep, num = ops.nms_batched_raw(cat, counts, thresh)
+            off = 0
+            for j, (l, i) in enumerate(chunk):
+                keep_of[(l, i)] = (keep, num, off, j)
+                off += counts[j]
+    # ONE host read of every kept count
+    nums = {}
+    if keep_of:
+        keys = list(keep_of)
+        stacked = torch.stack([keep_of[k][1][keep_of[k][3]] for k in keys]).cpu().numpy()
+        nums = {k: int(v) for k, v in zip(keys, stacked)}
+    out = []
+    for l, (op, imgs, (pre, post, thresh, min_size)) in enumerate(zip(op_list, per_level, params)):
+        rois = np.empty((0, 5), dtype=np.float32)
+        probs = np.empty((0, 1), dtype=np.float32)
+        t_rois, t_probs = [], []
+        for i, (dets, valid) in enumerate(imgs):
+            if (l, i) in keep_of:
+                keep, _, off, _ = keep_of[(l, i)]
+                k = keep[off:off + nums[(l, i)]].long()
+            else:
+                k = torch.arange(dets.size(0), device=dets.device)
+            k = k[valid[k] != 0]
+            if thresh > 0 and post > 0:
+                k = k[:post]
+            d = dets[k]
+            if op._return_tensors:
+                t_rois.append(torch.cat([torch.full((d.size(0), 1), float(i), device=d.device), d[:, :4]], dim=1))
+                t_probs.append(d[:, 4:5])
+                continue
+            d = d.cpu().numpy()
+            rois = np.append(rois, np.hstack((np.full((d.shape[0], 1), i, dtype=np.float32), d[:, :4])), axis=0)
+            probs = np.append(probs, d[:, 4:5], axis=0)
+        out.append((torch.cat(t_rois, dim=0), torch.cat(t_probs, dim=0)) if op._return_tensors else (rois, probs))
+    return out

@@ -325,6 +325,33 @@ class _RoICrop(Function):
 # ------------------------------------------------------------------------------------------------
 # NMS
 # ------------------------------------------------------------------------------------------------
+def nms_batched_raw(dets, counts, thresh):
+    """`len(counts)` independent NMS problems in one pair of launches.  dets: (sum(counts), >=4) rows of the problems back to
+    back, each problem score-sorted; counts: host ints.  Returns (keep int32 (sum(counts),), num_out int32 (P,)) on the
+    device: problem p's kept indices (relative to its first row) sit at keep[offset_p : offset_p + num_out[p]]."""
+    import ctypes
+    _need_cuda_f32(dets, "dets")
+    if dets.dim() != 2 or dets.size(1) < 4:
+        raise ValueError("dets must be (N, >=4) = [x1, y1, x2, y2, score], got %s" % (tuple(dets.shape),))
+    counts = [int(c) for c in counts]
+    if sum(counts) != dets.size(0) or not counts:
+        raise ValueError("counts %s do not add up to %d rows" % (counts, dets.size(0)))
+    dets = dets.contiguous()
+    lib = _lib.load()
+    P = len(counts)
+    c_arr = (ctypes.c_int * P)(*counts)
+    keep = torch.empty((max(dets.size(0), 1),), dtype=torch.int32, device=dets.device)
+    num_out = torch.empty((P,), dtype=torch.int32, device=dets.device)
+    ws_bytes = int(lib.b200_nms_batched_workspace_bytes(ctypes.cast(c_arr, ctypes.c_void_p), P))
+    if ws_bytes == 0:
+        raise ValueError("b200_nms_batched: 1..64 problems expected, got %d" % P)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dets.device)
+    with torch.cuda.device(dets.device):
+        _lib.check(lib.b200_nms_batched(dets.data_ptr(), ctypes.cast(c_arr, ctypes.c_void_p), P, dets.size(1), float(thresh), keep.data_ptr(),
+                                        num_out.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "b200_nms_batched")
+    return keep, num_out
+
+
 def nms_raw(dets, thresh):
     """Returns (keep int32 (N,), num_out int32 (1,)) on the device, no host sync."""
     _need_cuda_f32(dets, "dets")

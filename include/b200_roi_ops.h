@@ -160,12 +160,25 @@ B200_API int b200_nms(const float* boxes_dev, int boxes_num, int boxes_dim, floa
              int* keep_out_dev, int* num_out_dev, void* workspace, size_t workspace_bytes,
              b200_stream_t stream);
 
+/* Several independent NMS problems in ONE pair of launches (mask kernel over all problems' tiles, one scan CTA per
+ * problem): the (image, FPN level) proposal sets of one step (lib/modeling/generate_proposals.py:91-99 runs them one
+ * after the other on the host).  Problem p has counts_host[p] score-sorted rows, stored back to back in boxes_dev;
+ * its kept indices (relative to its own first row) go to keep_out_dev + (sum of the counts before p), their number to
+ * num_out_dev[p].  counts_host is a HOST array (the counts are launch geometry); 1 <= num_problems <= 64 and every
+ * count <= ~13 800 (the pipelined scan's shared-memory limit), else B200_ROI_EINVAL -- loop over b200_nms then.
+ * Results per problem are bit-identical to b200_nms. */
+B200_API size_t b200_nms_batched_workspace_bytes(const int* counts_host, int num_problems);
+B200_API int b200_nms_batched(const float* boxes_dev, const int* counts_host, int num_problems, int boxes_dim,
+                              float nms_overlap_thresh, int* keep_out_dev, int* num_out_dev, void* workspace,
+                              size_t workspace_bytes, b200_stream_t stream);
+
 /* ---- introspection used by the benchmark / tests (no compute) ----------------------------------
  * Number of kernel launches the library has enqueued since load (all entry points). */
 B200_API unsigned long long b200_roi_ops_launch_count(void);
 /* Path-selection switches (A/B runs and tests): name is one of "B200_ROI_ALIGN_PATH" (auto|generic|tiled|stream),
  * "B200_ROI_ALIGN_BWD_PATH" (auto|generic|nhwc|rows), "B200_ROI_ALIGN_BWD_CPL" (4|2), "B200_FWD_ZERO" (dense|bins),
- * "B200_NMS_SCAN" (resolver|simple); value NULL or "" restores the default.  Each switch takes its initial value from the
+ * "B200_NMS_SCAN" (resolver|simple), "B200_STREAM_STAGE" (async|regs), "B200_STREAM_PHASES" (all|prepass: timing probe);
+ * value NULL or "" restores the default.  Each switch takes its initial value from the
  * environment variable of the same name, read once at first use -- no entry point calls getenv() on the hot path.
  * Returns 0, or B200_ROI_EINVAL for an unknown name. */
 B200_API int b200_roi_ops_set_option(const char* name, const char* value);

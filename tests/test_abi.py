@@ -99,6 +99,11 @@ def test_workspace_sizing_is_host_arithmetic(lib_option):
     assert lib.b200_roi_align_backward_workspace_bytes(0, 512, 256, 200, 272, 7, 7, 2) == 0
     assert lib.b200_roi_align_backward_workspace_bytes(1, 512, 252, 200, 272, 7, 7, 2) == 252 * 200 * 272 * 4     # C % 64 != 0 -> NHWC path
     assert lib.b200_roi_align_backward_workspace_bytes(1, 8, 256, 200, 272, 7, 7, 2) == 0      # tiny gather volume -> scalar atomics
+    # batched NMS: sum over problems of (mask words + transposed diagonal words), host arithmetic on a host array
+    counts = (ctypes.c_int * 3)(6000, 0, 64)
+    assert lib.b200_nms_batched_workspace_bytes(ctypes.cast(counts, ctypes.c_void_p), 3) == ((6000 * 94 + 94 * 64) + (64 + 64)) * 8 + 256
+    assert lib.b200_nms_batched_workspace_bytes(ctypes.cast(counts, ctypes.c_void_p), 0) == 0
+    assert lib.b200_nms_batched(None, ctypes.cast(counts, ctypes.c_void_p), 3, 5, ctypes.c_float(0.7), None, None, None, 0, None) == -1
     # NULL workspace is legal for the _ws entry points (generic kernels run); bad dims are still rejected first
     assert lib.b200_roi_align_forward_ws(None, 0.25, 1, 4, 10, 10, 3, 0, 7, 2, None, None, None, 0, None) == -1
     assert lib.b200_roi_align_backward_ws(None, 0.25, 1, 4, 10, -1, 3, 7, 7, 2, None, None, None, 0, None) == -1

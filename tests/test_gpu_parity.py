@@ -482,6 +482,62 @@ def test_nms_edge_cases():
     assert np.array_equal(nms_gpu(dev(b6), 0.7).cpu().numpy().reshape(-1), O.nms_cuda(b6[:, :5], 0.7))
 
 
+def test_nms_batched_equals_per_problem_calls():
+    """b200_nms_batched: the (image, level) proposal sets of one step in one pair of launches -- per problem bit-identical
+    to b200_nms / the oracle: sizes across the scan's REACH classes, an empty problem, a one-box problem, a dense chain."""
+    from detectron.pytorch_b200 import ops
+    probs = [cases.nms_case(1000, seed=1), cases.nms_case(2000, seed=2), np.zeros((0, 5), np.float32), cases.nms_chain_case(130),
+             cases.nms_case(1, seed=3), cases.nms_clustered_case(777, seed=5), cases.nms_case(6000, seed=4), cases.nms_case(65, seed=6)]
+    counts = [len(b) for b in probs]
+    keep, num = ops.nms_batched_raw(dev(np.concatenate(probs)), counts, 0.7)
+    keep = keep.cpu().numpy(); num = num.cpu().numpy()
+    off = 0
+    for b, c, k in zip(probs, counts, num):
+        ref = O.nms_cuda(b, 0.7) if c else np.zeros((0,), np.int64)
+        assert k == len(ref)
+        assert np.array_equal(keep[off:off + k], ref)
+        off += c
+    # ten FPN-like problems (5 levels x 2 images): same answers as ten separate calls
+    ten = [cases.nms_case(n, seed=20 + i) for i, n in enumerate([1000, 1000, 1000, 1000, 1000, 1000, 1000, 1000, 525, 525])]
+    keep, num = ops.nms_batched_raw(dev(np.concatenate(ten)), [len(b) for b in ten], 0.7)
+    keep = keep.cpu().numpy(); num = num.cpu().numpy(); off = 0
+    for b, k in zip(ten, num):
+        single = nms_gpu(dev(b), 0.7).cpu().numpy().reshape(-1)
+        assert np.array_equal(keep[off:off + k], single)
+        off += len(b)
+    with pytest.raises(ValueError):
+        ops.nms_batched_raw(dev(probs[0]), [10, 20], 0.7)
+
+
+def test_generate_proposals_batched_levels_equal_per_level_calls():
+    """generate_proposals_batched (all FPN levels x images through ONE batched NMS and one host read) returns exactly what
+    the per-level op calls return, and those equal the numpy restatement of the reference op."""
+    from detectron.pytorch_b200.modeling.generate_proposals import GenerateProposalsOp, generate_proposals_batched
+    from oracle import proposals as OP
+    rng = np.random.RandomState(3)
+    N, A = 2, 3
+    ops_l, probs_l, preds_l, refs = [], [], [], []
+    im_info = np.array([[320, 480, 1.5], [300, 400, 1.25]], dtype=np.float32)
+    for lvl, (H, W) in zip((2, 3, 4), ((80, 120), (40, 60), (20, 30))):
+        stride = 2 ** lvl
+        anchors = np.round((rng.uniform(-1, 1, (A, 4)) * 4 * stride + np.array([-3, -3, 3, 3]) * stride) * 2) / 2
+        scores = ((rng.permutation(N * A * H * W).astype(np.float32) + 0.5) / (N * A * H * W)).reshape(N, A, H, W)
+        deltas = (rng.standard_normal((N, 4 * A, H, W)) * 0.4).astype(np.float32)
+        mode = dict(RPN_PRE_NMS_TOP_N=600, RPN_POST_NMS_TOP_N=200, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=0)
+        ops_l.append(GenerateProposalsOp(anchors, 1.0 / stride, train=mode, test=mode))
+        probs_l.append(dev(scores)); preds_l.append(dev(deltas))
+        refs.append(OP.generate_proposals(scores, deltas, im_info, anchors, float(stride), 600, 200, 0.7, 0))
+    fused = generate_proposals_batched(ops_l, probs_l, preds_l, torch.from_numpy(im_info))
+    for (rois, probs), op, p, d, (rr, pp) in zip(fused, ops_l, probs_l, preds_l, refs):
+        r1, p1 = op(p, d, torch.from_numpy(im_info))
+        assert np.array_equal(rois, r1) and np.array_equal(probs, p1)
+        assert rois.shape == rr.shape
+        np.testing.assert_allclose(rois, rr, rtol=0, atol=1e-3)
+        assert np.array_equal(probs, pp)
+    with pytest.raises(ValueError):                       # the op is bound to its anchor count (ADVICE r1)
+        ops_l[0](probs_l[0][:, :2], preds_l[0], torch.from_numpy(im_info))
+
+
 def test_ops_honour_current_stream_and_noncontiguous_input():
     c, f, r, _ = cases.roi_case("cfg1_small")
     F = dev(np.transpose(f, (0, 1, 3, 2))).transpose(2, 3)   # non-contiguous view of the same values
