@@ -73,9 +73,10 @@ static size_t forward_workspace_bytes(int mode, int N, int R, int H, int W, int 
 }
 
 static bool tiled_pays_off(int R, int C, int H, int W, int PH, int PW) {
-    // the tiled path stages whole tiles; it wins once the gather volume dwarfs the map itself
-    const long long taps = (long long)R * C * PH * PW;
-    return taps >= (1LL << 18) && (long long)H * W >= 1024;
+    // the fast paths stream the whole map and pay a ~15 us prepass; they win once the gather volume dwarfs both
+    // (measured r03e: BASELINE cfg1, 0.4 M outputs, 32 us through the streaming path vs ~10 us generic)
+    const long long outputs = (long long)R * C * PH * PW;
+    return outputs >= 1500000LL && (long long)H * W >= 1024;
 }
 int nms(const float*, int, int, float, int*, int*, void*, size_t, cudaStream_t);
 size_t nms_batched_workspace_bytes(const int*, int);
@@ -107,7 +108,15 @@ static int backward_path_choice(int N, int R, int C, int H, int W, int PH, int P
     const int mode = backward_path_mode();
     if (mode == 1 || R <= 0) return 0;
     const bool pays = nhwc_pays_off(N, R, C, H, W, PH, PW, sr);
-    const bool rows_ok = roi_align_bwd_rows_workspace_bytes(N, R, C, H, W, PH, PW, sr) > 0;
+    bool rows_ok = roi_align_bwd_rows_workspace_bytes(N, R, C, H, W, PH, PW, sr) > 0;
+    if (rows_ok && mode != 3) {
+        // The gather path's parallelism is (image rows) x (32-cell tiles) x (128-channel blocks) warp items, each walking
+        // every unit of its row: few rows with many RoIs (FPN P4 / P5 with a thousand boxes, measured r03e: 315 us / 1 ms)
+        // leave most of the 1776 resident warps idle behind a few very long items.
+        const long long items = (long long)N * H * ((W + 31) / 32) * ((C + 127) / 128);
+        const long long units_per_row = 2LL * R * PH * (sr > 0 ? sr : 1) / ((long long)N * H);
+        if (items < 1200 || units_per_row > 160) rows_ok = false;
+    }
     if (mode == 3) return rows_ok ? 3 : 0;
     if (mode == 2) return 2;
     if (rows_ok && pays) return 3;

@@ -384,18 +384,18 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"     // %3: the hardware may park the thread this long (ns)
         "selp.u32 %0, 1, 0, p;\n"
-        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        "}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
     return ok != 0;
 }
-// try_wait suspends the thread in hardware for a bounded time per attempt.  A wait that is still pending after 2^22
+// try_wait suspends the thread in hardware for a bounded time per attempt.  A wait that is still pending after 2^20
 // attempts (seconds) is a protocol bug: trap (surfaces as a launch failure) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity, unsigned tag = 0u) {
     if (mbar_try_wait(bar, parity)) return;
     int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1 << 22)) {
+        if (++spins > (1 << 20)) {
             SDBG(6, 0xDEAD000000000000ull | ((u64)tag << 16) | ((u64)parity << 8) | (u64)((bar >> 3) & 0xff));
             __trap();
         }
@@ -685,8 +685,14 @@ roi_align_stream_fwd(const StreamArgs a) {
             const bool red = (cur.x >> 29) & 1u;
             const int key = cur.y & 0xffffu, end = key + (int)((cur.y >> 16) & 0xffu);
             const unsigned smask = (cur.y >> 24) & 0xfu;
-            acquire_to(key, 0x2000u);                           // entries are sorted by key: rows below it are done with
-            release_to(key);
+            // entries are sorted by key: rows below it are done with.  Rows this warp never needed are passed through one
+            // at a time (waited for, then released at once): holding them while waiting for later rows would starve the
+            // producers of slots whenever this warp's consecutive fragments lie more than K rows apart.
+            release_to(min(acq, key));
+            while (acq < key) {
+                acquire_to(acq + 1, 0x2000u);
+                release_to(acq);
+            }
             acquire_to(end, 0x2800u);                           // rows [key, end) must be resident
             SDBG(3, ((u64)cur.x << 32) | (u64)cur.y);
             const uint4 yA = lds128(tbuf + 16 * 16);

@@ -538,6 +538,55 @@ def test_generate_proposals_batched_levels_equal_per_level_calls():
         ops_l[0](probs_l[0][:, :2], preds_l[0], torch.from_numpy(im_info))
 
 
+def test_reference_named_launchers_compute():
+    """The compatibility libraries (include/b200_ref_launchers.h): the reference's launcher names and argument lists, called
+    the way the reference's *_cuda.c glue calls them (raw device pointers, current stream), against the oracle."""
+    import ctypes
+    from detectron.pytorch_b200 import build as B
+    lib = ctypes.CDLL(B.compat_lib_path("libb200_ref_launchers.so"))
+    leg = ctypes.CDLL(B.compat_lib_path("libb200_ref_launchers_legacy.so"))
+    c, f, r, dy = cases.roi_case("cfg1_small")
+    P, s, sr = c["P"], c["scale"], c["sr"]
+    N, C, H, W = c["shape"]
+    R = r.shape[0]
+    F, Rt, DY = dev(f), dev(r), dev(dy)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    out = torch.empty((R, C, P, P), device="cuda")
+    assert lib.ROIAlignForwardLaucher(vp(F), ctypes.c_float(s), R, H, W, C, P, P, sr, vp(Rt), vp(out), st) == 1
+    assert np.array_equal(out.cpu().numpy(), O.roi_align_forward(f, r, P, P, s, sr))
+    dx = torch.empty(c["shape"], device="cuda")
+    assert lib.ROIAlignBackwardLaucher(vp(DY), ctypes.c_float(s), N, R, H, W, C, P, P, sr, vp(Rt), vp(dx), st) == 1
+    np.testing.assert_allclose(dx.cpu().numpy(), O.roi_align_backward(dy, r, c["shape"], P, P, s, sr, acc64=True), **GRAD_TOL)
+    lout = torch.empty((R, C, P, P), device="cuda")
+    assert leg.ROIAlignForwardLaucher(vp(F), ctypes.c_float(s), R, H, W, C, P, P, vp(Rt), vp(lout), st) == 1
+    assert np.array_equal(lout.cpu().numpy(), O.roi_align_legacy_forward(f, r, P, P, s))
+    pout = torch.empty((R, C, P, P), device="cuda"); arg = torch.empty((R, C, P, P), dtype=torch.int32, device="cuda")
+    assert lib.ROIPoolForwardLaucher(vp(F), ctypes.c_float(s), R, H, W, C, P, P, vp(Rt), vp(pout), vp(arg), st) == 1
+    o_out, o_arg = O.roi_pool_forward(f, r, P, P, s)
+    assert np.array_equal(pout.cpu().numpy(), o_out) and np.array_equal(arg.cpu().numpy(), o_arg)
+    pdx = torch.empty(c["shape"], device="cuda")
+    assert lib.ROIPoolBackwardLaucher(vp(DY), ctypes.c_float(s), N, R, H, W, C, P, P, vp(Rt), vp(pdx), vp(arg), st) == 1
+    assert np.array_equal(pdx.cpu().numpy(), O.roi_pool_backward(dy, o_arg, r, c["shape"], P, P, s))
+    img, grid, go = cases.crop_case()
+    IM, GR = dev(img), dev(grid)
+    B_, Cc, ih, iw = img.shape
+    ob, oh, ow = grid.shape[0], grid.shape[1], grid.shape[2]
+    cout = torch.empty((ob, Cc, oh, ow), device="cuda")
+    assert lib.BilinearSamplerBHWD_updateOutput_cuda_kernel(Cc, ow, oh, ob, Cc, ih, iw, B_, vp(IM), Cc * ih * iw, ih * iw, iw, 1,
+                                                            vp(GR), oh * ow * 2, 1, ow * 2, 2, vp(cout), Cc * oh * ow, oh * ow, ow, 1, st) == 1
+    assert np.array_equal(cout.cpu().numpy(), O.roi_crop_forward(img, grid))
+    b = cases.nms_case(1000)
+    Bx = dev(b)
+    keep = torch.empty((1000,), dtype=torch.int32, device="cuda"); num = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    lib.nms_cuda_compute.restype = None
+    torch.cuda.synchronize()                                  # the launcher runs on the legacy default stream, like the reference
+    lib.nms_cuda_compute(vp(keep), vp(num), vp(Bx), 1000, 5, ctypes.c_float(0.7))
+    torch.cuda.synchronize()
+    k = int(num.item())
+    assert np.array_equal(keep[:k].cpu().numpy(), O.nms_cuda(b, 0.7))
+
+
 def test_ops_honour_current_stream_and_noncontiguous_input():
     c, f, r, _ = cases.roi_case("cfg1_small")
     F = dev(np.transpose(f, (0, 1, 3, 2))).transpose(2, 3)   # non-contiguous view of the same values
