@@ -54,6 +54,11 @@ _SIGNATURES = {
     # (boxes, n, dim, thresh, keep_out, num_out, workspace, workspace_bytes, stream)
     "b200_nms": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.c_void_p, ctypes.c_size_t, _stream_t]),
+    # (L, heights_host, widths_host, N, R, PH, PW, sr)
+    "b200_roi_align_fpn_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5),
+    # (L, bottoms_host, heights_host, widths_host, scales_host, roi_begin_host, N, R, C, PH, PW, sr, rois, top_rows, top, ws, ws_bytes, stream)
+    "b200_roi_align_forward_fpn": (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int] * 6 +
+                                   [_c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t, _stream_t]),
     "b200_nms_batched_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int]),
     # (boxes, counts_host, P, dim, thresh, keep_out, num_out, workspace, workspace_bytes, stream)
     "b200_nms_batched": (ctypes.c_int, [_c_float_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,

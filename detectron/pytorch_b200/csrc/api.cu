@@ -52,6 +52,9 @@ void nms_set_timing_buffer(unsigned long long*);
 void roi_align_stream_set_debug_buffer(unsigned long long*);
 int roi_align_forward_tiled(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
 size_t roi_align_stream_workspace_bytes(int, int, int, int, int, int, int);
+size_t roi_align_stream_fpn_workspace_bytes(int, const int*, const int*, int, int, int, int, int);
+int roi_align_forward_stream_fpn(int, const float* const*, const int*, const int*, const float*, const int*, int, int, int, int, int, int,
+                                 const float*, float*, const int*, void*, size_t, cudaStream_t);
 int roi_align_forward_stream(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
 
 // B200_ROI_ALIGN_PATH=generic|tiled|stream|auto (default auto) -- test/benchmark override of the forward dispatch
@@ -359,6 +362,32 @@ int b200_nms(const float* boxes_dev, int boxes_num, int boxes_dim, float nms_ove
     if (!num_out_dev || (boxes_num > 0 && (!boxes_dev || !keep_out_dev))) return B200_ROI_EINVAL;
     return nms(boxes_dev, boxes_num, boxes_dim, nms_overlap_thresh, keep_out_dev, num_out_dev, workspace,
                workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t b200_roi_align_fpn_workspace_bytes(int num_levels, const int* heights_host, const int* widths_host, int batch_size, int num_rois,
+                                          int aligned_height, int aligned_width, int sampling_ratio) {
+    if (num_levels < 1 || !heights_host || !widths_host || batch_size <= 0 || num_rois <= 0 || forward_path_mode() == 1 || forward_path_mode() == 2)
+        return 0;
+    return roi_align_stream_fpn_workspace_bytes(num_levels, heights_host, widths_host, batch_size, num_rois, aligned_height, aligned_width,
+                                                sampling_ratio);
+}
+
+int b200_roi_align_forward_fpn(int num_levels, const float* const* bottom_data_host, const int* heights_host, const int* widths_host,
+                               const float* spatial_scales_host, const int* level_roi_begin_host, int batch_size, int num_rois,
+                               int channels, int aligned_height, int aligned_width, int sampling_ratio, const float* bottom_rois,
+                               const int* top_rows, float* top_data, void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+    if (num_levels < 1 || !bottom_data_host || !heights_host || !widths_host || !spatial_scales_host || !level_roi_begin_host)
+        return B200_ROI_EINVAL;
+    if (batch_size <= 0 || num_rois <= 0 || channels <= 0 || aligned_height <= 0 || aligned_width <= 0 || !bottom_rois || !top_data)
+        return B200_ROI_EINVAL;
+    if (level_roi_begin_host[0] != 0 || level_roi_begin_host[num_levels] != num_rois) return B200_ROI_EINVAL;
+    for (int l = 0; l < num_levels; ++l)
+        if (!bottom_data_host[l] || level_roi_begin_host[l + 1] < level_roi_begin_host[l]) return B200_ROI_EINVAL;
+    const int rc = roi_align_forward_stream_fpn(num_levels, bottom_data_host, heights_host, widths_host, spatial_scales_host,
+                                                level_roi_begin_host, batch_size, num_rois, channels, aligned_height, aligned_width,
+                                                sampling_ratio, bottom_rois, top_data, top_rows, workspace, workspace_bytes,
+                                                (cudaStream_t)stream);
+    return rc == 1000 ? B200_ROI_EWORKSPACE : rc;
 }
 
 size_t b200_nms_batched_workspace_bytes(const int* counts_host, int num_problems) {

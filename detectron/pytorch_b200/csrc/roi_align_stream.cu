@@ -72,17 +72,38 @@ __device__ u64* g_stream_dbg = nullptr;
 #define SDBG(slot, val) do { } while (0)
 #endif
 
+constexpr int kMaxLevels = 6;                                 // feature maps served by one launch (FPN: P2..P6)
+constexpr int kMaxCols = 96;                                  // strip columns (level, image, strip) of one launch
+
+struct StreamLevel {                                          // one feature map of the pyramid (a plain call has one)
+    const float* bottom;                                      // (N, C, H, W)
+    float scale;
+    int H, W, S;                                              // S: strips per image
+    int q_base;                                               // its first strip column; column = q_base + image * S + strip
+    int roi_begin;                                            // its first RoI (RoIs are stored level-major)
+    int pad;
+};
+
 struct StreamGeom {
-    int N, R, C, H, W, PH, PW, sr;
+    int N, R, C, PH, PW, sr;
     int ny, nx;
-    int SX, WX, S, K;           // columns held per row (odd, 32 m + 1), strip core width, strips per image, ring depth
+    int SX, WX, K;              // columns held per row (odd, 32 m + 1), strip core width, ring depth
     int row_bytes;              // bytes of one ring slot = 32 * SX * 4
-    int Q, keys;                // strip columns = N * S, keys = Q * H
+    int L;                      // levels
+    int Q, keys;                // strip columns, keys = sum over columns of their rows
     int G;                      // 32-channel groups
     int pieces;                 // persistent CTAs
     int max_entries;
-    float scale;
+    StreamLevel lv[kMaxLevels];
+    int colstart[kMaxCols + 1]; // first key of every column (its rows are consecutive keys); colstart[Q] = keys
 };
+
+// level of RoI r / of strip column q (at most kMaxLevels entries: linear scan)
+__host__ __device__ __forceinline__ int level_of_roi(const StreamGeom& g, int r) {
+    int l = 0;
+    while (l + 1 < g.L && r >= g.lv[l + 1].roi_begin) ++l;
+    return l;
+}
 
 struct StreamWs {
     uint4* ytab;                // [R][ny] {hy, ly, byte offset of the ring slot of row y_low, 0}; the lower tap row is the NEXT slot
@@ -130,7 +151,7 @@ __device__ __forceinline__ AdjTap adj_axis(float v, int size) {
 // (equal on the clamped last row); xl: adjusted low cell per x sample.
 // emit(strip, key, end, pw0, npw, smask, red, zero_owner)
 template <int SR, class Emit>
-__device__ __forceinline__ void enum_row(const int* yl, const int* yh, const int* xl, int ph, const StreamGeom& g, Emit&& emit) {
+__device__ __forceinline__ void enum_row(const int* yl, const int* yh, const int* xl, int ph, const StreamGeom& g, int S, Emit&& emit) {
     const int i0 = ph * SR, i1 = i0 + SR - 1;
     int ngroups = 1;
     int key[2], end[2];
@@ -163,12 +184,12 @@ __device__ __forceinline__ void enum_row(const int* yl, const int* yh, const int
         };
         for (int pw = 0; pw < g.PW; ++pw) {
             const int j0 = pw * SR, j1 = j0 + SR - 1;
-            const int s0 = min(xl[j0] / g.WX, g.S - 1);
+            const int s0 = min(xl[j0] / g.WX, S - 1);
             if (SR == 1 || xl[j1] + 1 <= s0 * g.WX + g.SX - 1) {
                 push(s0, kXFull, pw);
             } else {                                   // x samples in different strips: one fragment per x sample
                 push(s0, 1u, pw);
-                push(min(xl[j1] / g.WX, g.S - 1), 2u, pw);
+                push(min(xl[j1] / g.WX, S - 1), 2u, pw);
             }
         }
         flush();
@@ -185,14 +206,15 @@ stream_count(const float* __restrict__ rois, StreamGeom g, StreamWs ws) {
     __shared__ int s_last;
     __shared__ unsigned s_h[kPrepThreads], s_c[kPrepThreads];
     const int r = blockIdx.x, t = threadIdx.x;
-    const XfromRoi geo = xfrom_roi(rois + 5 * (size_t)r, g.scale, g.PH, g.PW, g.sr);
+    const StreamLevel& lv = g.lv[level_of_roi(g, r)];
+    const XfromRoi geo = xfrom_roi(rois + 5 * (size_t)r, lv.scale, g.PH, g.PW, g.sr);
     if (t < g.ny + g.nx) {
         const bool isy = t < g.ny;
         const int s = isy ? t : t - g.ny;
         if (isy) {
             // rows exactly as the reference takes them (low == high == H - 1 on the clamped last row, weights (1, 0)): the
             // lower tap then reads whatever the next ring slot holds with weight 0 -- always finite, the ring starts zeroed
-            const AxisTap a = xfrom_axis(xfrom_coord(geo.start_h, geo.bin_h, s / SR, s % SR, SR), g.H);
+            const AxisTap a = xfrom_axis(xfrom_coord(geo.start_h, geo.bin_h, s / SR, s % SR, SR), lv.H);
             s_yl[s] = a.low; s_yh[s] = a.high;
             uint4 e;
             e.x = __float_as_uint(a.valid ? a.h : 0.f); e.y = __float_as_uint(a.valid ? a.l : 0.f);
@@ -200,7 +222,7 @@ stream_count(const float* __restrict__ rois, StreamGeom g, StreamWs ws) {
             e.w = 0u;
             ws.ytab[(size_t)r * g.ny + s] = e;
         } else {
-            const AdjTap a = adj_axis(xfrom_coord(geo.start_w, geo.bin_w, s / SR, s % SR, SR), g.W);
+            const AdjTap a = adj_axis(xfrom_coord(geo.start_w, geo.bin_w, s / SR, s % SR, SR), lv.W);
             s_xl[s] = a.low;
             uint4 e;
             e.x = __float_as_uint(a.h); e.y = __float_as_uint(a.l);
@@ -211,9 +233,9 @@ stream_count(const float* __restrict__ rois, StreamGeom g, StreamWs ws) {
     __syncthreads();
     const bool batch_ok = geo.batch >= 0 && geo.batch < g.N;
     if (batch_ok && t < g.PH) {
-        const int kbase = geo.batch * g.S;
-        enum_row<SR>(s_yl, s_yh, s_xl, t, g, [&](int s, int key, int end, int pw0, int npw, unsigned smask, int red, bool owner) {
-            const int k = (kbase + s) * g.H + key;
+        const int cbase = lv.q_base + geo.batch * lv.S;
+        enum_row<SR>(s_yl, s_yh, s_xl, t, g, lv.S, [&](int s, int key, int end, int pw0, int npw, unsigned smask, int red, bool owner) {
+            const int k = g.colstart[cbase + s] + key;
             atomicAdd(&ws.hist[k], 1);
             atomicAdd(&ws.cost[k], 2 + npw);
             (void)end; (void)pw0; (void)smask; (void)red; (void)owner;
@@ -290,27 +312,28 @@ stream_count(const float* __restrict__ rois, StreamGeom g, StreamWs ws) {
     for (int p = t; p <= g.pieces; p += kPrepThreads) {
         int L;
         if (p == 0) L = 0;
-        else if (p == g.pieces) L = g.Q * g.G * g.H;
+        else if (p == g.pieces) L = g.G * g.keys;
         else {
             const u64 target = grand / (u64)g.pieces * (u64)p + (grand % (u64)g.pieces) * (u64)p / (u64)g.pieces;
             int lo = 0, hi = g.Q - 1;
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
-                if ((u64)g.G * (u64)pre((size_t)mid * g.H) <= target) lo = mid; else hi = mid - 1;
+                if ((u64)g.G * (u64)pre((size_t)g.colstart[mid]) <= target) lo = mid; else hi = mid - 1;
             }
             const int q = lo;
-            const unsigned c0 = pre((size_t)q * g.H);
-            const unsigned colsum = pre((size_t)(q + 1) * g.H) - c0;      // >= 2 H > 0
+            const int k0 = g.colstart[q], Hq = g.colstart[q + 1] - k0;
+            const unsigned c0 = pre((size_t)k0);
+            const unsigned colsum = pre((size_t)k0 + Hq) - c0;              // >= kRowCost * Hq > 0
             u64 rem = target - (u64)g.G * (u64)c0;
             int gg = (int)(rem / colsum);
             if (gg > g.G - 1) gg = g.G - 1;
             rem -= (u64)gg * colsum;
-            int ylo = 0, yhi = g.H - 1;
+            int ylo = 0, yhi = Hq - 1;
             while (ylo < yhi) {
                 const int mid = (ylo + yhi + 1) >> 1;
-                if ((u64)(pre((size_t)q * g.H + mid) - c0) <= rem) ylo = mid; else yhi = mid - 1;
+                if ((u64)(pre((size_t)k0 + mid) - c0) <= rem) ylo = mid; else yhi = mid - 1;
             }
-            L = (q * g.G + gg) * g.H + ylo;
+            L = g.G * k0 + gg * Hq + ylo;                                   // linear order: (column, channel group, row)
         }
         ws.piece_start[p] = L;
     }
@@ -326,16 +349,17 @@ stream_fill(const float* __restrict__ rois, StreamGeom g, StreamWs ws, float* __
     __shared__ unsigned short s_zero[kAxisMaxS * kAxisMaxS];
     __shared__ int s_nzero;
     const int r = blockIdx.x, t = threadIdx.x;
-    const XfromRoi geo = xfrom_roi(rois + 5 * (size_t)r, g.scale, g.PH, g.PW, g.sr);
+    const StreamLevel& lv = g.lv[level_of_roi(g, r)];
+    const XfromRoi geo = xfrom_roi(rois + 5 * (size_t)r, lv.scale, g.PH, g.PW, g.sr);
     if (t == 0) s_nzero = 0;
     if (t < g.ny + g.nx) {
         const bool isy = t < g.ny;
         const int s = isy ? t : t - g.ny;
         if (isy) {
-            const AxisTap a = xfrom_axis(xfrom_coord(geo.start_h, geo.bin_h, s / SR, s % SR, SR), g.H);
+            const AxisTap a = xfrom_axis(xfrom_coord(geo.start_h, geo.bin_h, s / SR, s % SR, SR), lv.H);
             s_yl[s] = a.low; s_yh[s] = a.high;
         } else {
-            s_xl[s] = adj_axis(xfrom_coord(geo.start_w, geo.bin_w, s / SR, s % SR, SR), g.W).low;
+            s_xl[s] = adj_axis(xfrom_coord(geo.start_w, geo.bin_w, s / SR, s % SR, SR), lv.W).low;
         }
     }
     __syncthreads();
@@ -343,9 +367,9 @@ stream_fill(const float* __restrict__ rois, StreamGeom g, StreamWs ws, float* __
     const int bins = g.PH * g.PW;
     if (batch_ok) {
         if (t < g.PH) {
-            const int kbase = geo.batch * g.S;
-            enum_row<SR>(s_yl, s_yh, s_xl, t, g, [&](int s, int key, int end, int pw0, int npw, unsigned smask, int red, bool owner) {
-                const int k = (kbase + s) * g.H + key;
+            const int cbase = lv.q_base + geo.batch * lv.S;
+            enum_row<SR>(s_yl, s_yh, s_xl, t, g, lv.S, [&](int s, int key, int end, int pw0, int npw, unsigned smask, int red, bool owner) {
+                const int k = g.colstart[cbase + s] + key;
                 const int pos = ws.rowptr[k] + atomicAdd(&ws.cursor[k], 1);
                 if (pos < g.max_entries) ws.entries[pos] = pack_entry(r, t, pw0, npw, red, key, end, smask);
                 atomicMax(&ws.maxend[k], end);
@@ -426,28 +450,39 @@ struct StreamArgs {
     const int* rowptr;
     const int* maxend;
     const int* piece_start;
-    const float* bottom;
     float* out;
     const int* row_map;
-    int C, H, W, S, G, K, WX, PH, PW, ny, nx;
+    int C, G, K, WX, PH, PW, ny, nx, L, Q;
+    StreamLevel lv[kMaxLevels];
+    int colstart[kMaxCols + 1];
 };
 
 // one item = the part of one (strip column q, channel group) that lies in this CTA's piece
 struct Item {
-    int n, s, g, ya, yb, e0, e1, yhi, kbase;
+    int lvl, n, s, g, ya, yb, e0, e1, yhi, kbase;
 };
 
 // Decode the item that starts at linear index L (all lanes of the calling warp; yhi by warp reduction).
 __device__ __forceinline__ Item decode_item(int L, int L1, const StreamArgs& a, int lane) {
     Item it;
-    const int col = L / a.H;
-    it.ya = L - col * a.H;
-    const int q = col / a.G;
-    it.g = col - q * a.G;
-    it.n = q / a.S;
-    it.s = q - it.n * a.S;
-    it.yb = min(a.H, it.ya + (L1 - L));
-    it.kbase = q * a.H;
+    int lo = 0, hi = a.Q - 1;                                  // column: the last one whose first linear index is <= L
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (a.G * a.colstart[mid] <= L) lo = mid; else hi = mid - 1;
+    }
+    const int q = lo;
+    it.kbase = a.colstart[q];
+    const int Hq = a.colstart[q + 1] - it.kbase;
+    const int rem = L - a.G * it.kbase;
+    it.g = rem / Hq;
+    it.ya = rem - it.g * Hq;
+    it.yb = min(Hq, it.ya + (L1 - L));
+    int l = 0;
+    while (l + 1 < a.L && q >= a.lv[l + 1].q_base) ++l;
+    it.lvl = l;
+    const int qq = q - a.lv[l].q_base;
+    it.n = qq / a.lv[l].S;
+    it.s = qq - it.n * a.lv[l].S;
     it.e0 = __ldg(&a.rowptr[it.kbase + it.ya]);
     it.e1 = __ldg(&a.rowptr[it.kbase + it.yb]);
     int m = 0;
@@ -583,18 +618,20 @@ roi_align_stream_fwd(const StreamArgs a) {
         const int pw = warp - kConsumerWarps;
         unsigned ephase = 0xffffffffu;                // waiting for parity 1 on a fresh barrier passes immediately
         int turn = 0;                                 // stream row index modulo kProducerWarps
-        const size_t plane = (size_t)a.H * a.W;
         for (int L = L0; L < L1;) {
             const Item it = decode_item(L, L1, a, lane);
             L += it.yb - it.ya;
             SDBG(2, ((u64)it.ya << 48) | ((u64)it.yb << 32) | ((u64)it.yhi << 16) | (u64)(it.e1 - it.e0));
             if (it.e1 <= it.e0) continue;
             int slot = it.ya % a.K;
+            const StreamLevel& lv = a.lv[it.lvl];
+            const size_t plane = (size_t)lv.H * lv.W;
             const int x0 = it.s * a.WX;
             const int c0 = it.g * 32;
             const int cvalid = min(32, a.C - c0);
-            const int xw = a.W - x0;
-            const float* src = a.bottom + ((size_t)it.n * a.C + c0) * plane + (size_t)it.ya * a.W + x0;
+            const int xw = lv.W - x0;
+            const int rowlen = lv.W;
+            const float* src = lv.bottom + ((size_t)it.n * a.C + c0) * plane + (size_t)it.ya * lv.W + x0;
             for (int y = it.ya; y < it.yhi; ++y) {
                 if (turn == pw) {
                     const unsigned full = bars + 8u * slot, empty = bars + 8u * (kMaxSlots + slot);
@@ -607,7 +644,7 @@ roi_align_stream_fwd(const StreamArgs a) {
                 ephase ^= 1u << slot;
                 if (++slot == a.K) slot = 0;
                 if (++turn == kProducerWarps) turn = 0;
-                src += a.W;
+                src += rowlen;
             }
         }
         SDBG(0, 9);
@@ -785,15 +822,22 @@ struct StreamLayout {
     size_t ytab_off, xtab_off, zero_off, zero_bytes, rowptr_off, cpre_off, piece_off, entries_off, ws_bytes;
 };
 
-bool stream_geometry(int N, int R, int C, int H, int W, int PH, int PW, int sr, float scale, int sm_count, StreamGeom* g, StreamLayout* lay,
-                     unsigned* smem_bytes) {
+// One launch serves `levels` feature maps (FPN: the pyramid levels of one head; a plain call: one map).  All levels share the
+// batch size, the channel count, the pooled size, the ring geometry (SX, K) and therefore the kernel instantiation.
+// level_roi_begin: [levels + 1] first RoI of every level (RoIs are stored level-major), level_roi_begin[levels] = R.
+bool stream_geometry(int levels, const float* const* bottoms, const int* heights, const int* widths, const float* scales,
+                     const int* level_roi_begin, int N, int R, int C, int PH, int PW, int sr, int sm_count, StreamGeom* g,
+                     StreamLayout* lay, unsigned* smem_bytes) {
+    if (levels < 1 || levels > kMaxLevels) return false;
     if (sr < 1 || sr > 2 || PH * sr > kAxisMaxS || PW * sr > kAxisMaxS || PH > 31 || PW > 31) return false;
-    if (N <= 0 || R <= 0 || R > 65535 || H < 2 || W < 2 || H > 65535) return false;
+    if (N <= 0 || R <= 0 || R > 65535) return false;
     if ((long long)R * PH * PW * sr * sr >= (1LL << 28)) return false;
+    for (int l = 0; l < levels; ++l)
+        if (heights[l] < 2 || widths[l] < 2 || heights[l] > 65535) return false;
     // ring budget: everything but the per-warp staging, the barriers and the alignment slack
     const unsigned fixed = kConsumerWarps * kStageWordsPerWarp * 4 + 2 * kMaxSlots * 8 + 128;
     const unsigned ring_budget = kSmemBudget - fixed;
-    int best_sx = 0, best_s = 0, best_wx = 0, best_k = 0;
+    int best_sx = 0, best_wx = 0, best_k = 0;
     long best_score = -1;
     for (int m = 1; m <= 3; ++m) {                            // SX = 32 m + 1: odd channel stride, m coalesced chunks + 1 column
         const int sx = 32 * m + 1;
@@ -802,25 +846,46 @@ bool stream_geometry(int N, int R, int C, int H, int W, int PH, int PW, int sr, 
         if (k < 12) continue;
         const int hx = m >= 2 ? 9 : 5;                        // halo: bins whose x samples are <= hx + 1 cells apart stay whole
         const int wx = sx - 1 - hx;
-        int s = 1;
-        while ((s - 1) * wx + sx < W) ++s;                    // the last strip needs no halo
-        const long score = (long)s * sx;
-        if (best_score < 0 || score < best_score) { best_score = score; best_sx = sx; best_s = s; best_wx = wx; best_k = k; }
+        long score = 0;                                       // columns staged per row of every level, weighted by its rows
+        for (int l = 0; l < levels; ++l) {
+            int s = 1;
+            while ((s - 1) * wx + sx < widths[l]) ++s;        // the last strip needs no halo
+            score += (long)s * sx * heights[l];
+        }
+        if (best_score < 0 || score < best_score) { best_score = score; best_sx = sx; best_wx = wx; best_k = k; }
     }
     if (best_score < 0) return false;
-    g->N = N; g->R = R; g->C = C; g->H = H; g->W = W; g->PH = PH; g->PW = PW; g->sr = sr;
+    g->N = N; g->R = R; g->C = C; g->PH = PH; g->PW = PW; g->sr = sr;
     g->ny = PH * sr; g->nx = PW * sr;
-    g->SX = best_sx; g->WX = best_wx; g->S = best_s; g->K = best_k;
+    g->SX = best_sx; g->WX = best_wx; g->K = best_k;
     g->row_bytes = 128 * best_sx;
-    g->Q = N * best_s;
-    if ((long long)g->Q * H >= (1LL << 24)) return false;
-    g->keys = g->Q * H;
+    g->L = levels;
+    int q = 0;
+    long long keys = 0;
+    for (int l = 0; l < levels; ++l) {
+        StreamLevel& lv = g->lv[l];
+        lv.bottom = bottoms ? bottoms[l] : nullptr;
+        lv.scale = scales ? scales[l] : 1.f;
+        lv.H = heights[l]; lv.W = widths[l];
+        int s = 1;
+        while ((s - 1) * best_wx + best_sx < lv.W) ++s;
+        lv.S = s;
+        lv.q_base = q;
+        lv.roi_begin = level_roi_begin ? level_roi_begin[l] : 0;
+        lv.pad = 0;
+        if (q + N * s > kMaxCols) return false;
+        for (int c = 0; c < N * s; ++c) { g->colstart[q + c] = (int)keys; keys += lv.H; }
+        q += N * s;
+        if (keys >= (1LL << 24)) return false;
+    }
+    for (int l = levels; l < kMaxLevels; ++l) { g->lv[l] = g->lv[levels - 1]; g->lv[l].q_base = q; g->lv[l].roi_begin = R; }
+    g->Q = q; g->keys = (int)keys;
+    for (int c = q; c <= kMaxCols; ++c) g->colstart[c] = (int)keys;
     g->G = (C + 31) / 32;
     if (g->G < 1) g->G = 1;
-    if ((long long)g->Q * g->G * H >= (1LL << 30)) return false;
+    if (keys * g->G >= (1LL << 30)) return false;
     g->pieces = sm_count > 0 ? sm_count : kNumSMs;
     g->max_entries = R * PH * PW * sr * sr;                    // worst case: every sample its own fragment
-    g->scale = scale;
     size_t off = 0;
     lay->ytab_off = off; off = align_up_sz(off + (size_t)R * g->ny * 16, 256);
     lay->xtab_off = off; off = align_up_sz(off + (size_t)R * g->nx * 16, 256);
@@ -876,17 +941,22 @@ void roi_align_stream_set_debug_buffer(unsigned long long* host_pinned) {
 #endif
 }
 
-size_t roi_align_stream_workspace_bytes(int N, int R, int H, int W, int PH, int PW, int sr) {
+size_t roi_align_stream_fpn_workspace_bytes(int levels, const int* heights, const int* widths, int N, int R, int PH, int PW, int sr) {
     StreamGeom g;
     StreamLayout lay;
     unsigned smem = 0;
-    if (!stream_geometry(N, R, 32, H, W, PH, PW, sr, 1.f, kNumSMs, &g, &lay, &smem)) return 0;
+    if (!stream_geometry(levels, nullptr, heights, widths, nullptr, nullptr, N, R, 32, PH, PW, sr, kNumSMs, &g, &lay, &smem)) return 0;
     return lay.ws_bytes;
 }
 
+size_t roi_align_stream_workspace_bytes(int N, int R, int H, int W, int PH, int PW, int sr) {
+    return roi_align_stream_fpn_workspace_bytes(1, &H, &W, N, R, PH, PW, sr);
+}
+
 // returns B200_ROI_OK when the streaming path ran; 1000 when it does not apply (caller falls back)
-int roi_align_forward_stream(const float* bottom, float scale, int N, int R, int H, int W, int C, int PH, int PW, int sr,
-                             const float* rois, float* top, const int* row_map, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+int roi_align_forward_stream_fpn(int levels, const float* const* bottoms, const int* heights, const int* widths, const float* scales,
+                                 const int* level_roi_begin, int N, int R, int C, int PH, int PW, int sr, const float* rois, float* top,
+                                 const int* row_map, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     if (workspace == nullptr || C <= 0) return 1000;
     if ((long long)N * C >= (1LL << 31) || (long long)R * C * PH * PW >= (1LL << 31)) return 1000;
     int sm_count = 0;
@@ -894,7 +964,7 @@ int roi_align_forward_stream(const float* bottom, float scale, int N, int R, int
     StreamGeom g;
     StreamLayout lay;
     unsigned smem = 0;
-    if (!stream_geometry(N, R, C, H, W, PH, PW, sr, scale, sm_count, &g, &lay, &smem)) return 1000;
+    if (!stream_geometry(levels, bottoms, heights, widths, scales, level_roi_begin, N, R, C, PH, PW, sr, sm_count, &g, &lay, &smem)) return 1000;
     if (workspace_bytes < lay.ws_bytes) return 1000;
     unsigned char* wsb = (unsigned char*)workspace;
     StreamWs ws;
@@ -912,8 +982,10 @@ int roi_align_forward_stream(const float* bottom, float scale, int N, int R, int
     if (err != cudaSuccess) return (int)err;
     StreamArgs a;
     a.ytab = ws.ytab; a.xtab = ws.xtab; a.entries = ws.entries; a.rowptr = ws.rowptr; a.maxend = ws.maxend;
-    a.piece_start = ws.piece_start; a.bottom = bottom; a.out = top; a.row_map = row_map;
-    a.C = C; a.H = H; a.W = W; a.S = g.S; a.G = g.G; a.K = g.K; a.WX = g.WX; a.PH = PH; a.PW = PW; a.ny = g.ny; a.nx = g.nx;
+    a.piece_start = ws.piece_start; a.out = top; a.row_map = row_map;
+    a.C = C; a.G = g.G; a.K = g.K; a.WX = g.WX; a.PH = PH; a.PW = PW; a.ny = g.ny; a.nx = g.nx; a.L = g.L; a.Q = g.Q;
+    for (int l = 0; l < kMaxLevels; ++l) a.lv[l] = g.lv[l];
+    for (int c = 0; c <= kMaxCols; ++c) a.colstart[c] = g.colstart[c];
     const bool async = option_get(kOptStreamStage) != 'r';          // B200_STREAM_STAGE=regs selects LDG -> registers -> STS (A/B)
     const int m = (g.SX - 1) / 32;
     if (sr == 1) {
@@ -931,6 +1003,13 @@ int roi_align_forward_stream(const float* bottom, float scale, int N, int R, int
 #undef B200_STREAM_LAUNCH_M
 #undef B200_STREAM_LAUNCH
     return finish_launch(3);
+}
+
+int roi_align_forward_stream(const float* bottom, float scale, int N, int R, int H, int W, int C, int PH, int PW, int sr,
+                             const float* rois, float* top, const int* row_map, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    const int begin[2] = {0, R};
+    return roi_align_forward_stream_fpn(1, &bottom, &H, &W, &scale, begin, N, R, C, PH, PW, sr, rois, top, row_map, workspace,
+                                        workspace_bytes, stream);
 }
 
 }  // namespace b200

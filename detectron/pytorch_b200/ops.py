@@ -113,15 +113,45 @@ class _RoIAlignFPN(Function):
             inv = inv_h.to(dev, non_blocking=False)
         out = torch.empty((total, C, P[0], P[1]), dtype=torch.float32, device=dev)
         lib = _lib.load()
+        for f, r in zip(feats, rois):
+            _need_cuda_f32(f, "features"); _need_cuda_f32(r, "rois"); _rois_ok(r)
+            if f.size(1) != C or f.size(0) != feats[0].size(0):
+                raise ValueError("every pyramid level must have the same batch size and number of channels")
+        kept = [r.contiguous() for r in rois]
+        done = False
+        if total > 0:
+            # one launch sequence over the whole pyramid: levels without RoIs drop out, the rest go level-major
+            import ctypes
+            live = [l for l in range(num_levels) if counts[l] > 0]
+            fl = [feats[l].contiguous() for l in live]
+            Lc = len(live)
+            N = int(fl[0].size(0))
+            hs = (ctypes.c_int * Lc)(*[int(f.size(2)) for f in fl]); wd = (ctypes.c_int * Lc)(*[int(f.size(3)) for f in fl])
+            ws_bytes = int(lib.b200_roi_align_fpn_workspace_bytes(Lc, ctypes.cast(hs, ctypes.c_void_p), ctypes.cast(wd, ctypes.c_void_p), N,
+                                                                  total, P[0], P[1], sr))
+            if ws_bytes > 0:
+                ptrs = (ctypes.c_void_p * Lc)(*[f.data_ptr() for f in fl])
+                scs = (ctypes.c_float * Lc)(*[float(scales[l]) for l in live])
+                begins, acc = [], 0
+                for l in live:
+                    begins.append(acc); acc += counts[l]
+                begins.append(acc)
+                bg = (ctypes.c_int * (Lc + 1))(*begins)
+                all_rois = torch.cat([kept[l] for l in live], dim=0) if Lc > 1 else kept[live[0]]
+                # inv is indexed by the position in the FULL level-major order; empty levels contribute nothing, so it is the same order
+                ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+                with torch.cuda.device(dev):
+                    _lib.check(lib.b200_roi_align_forward_fpn(Lc, ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(hs, ctypes.c_void_p),
+                                                              ctypes.cast(wd, ctypes.c_void_p), ctypes.cast(scs, ctypes.c_void_p),
+                                                              ctypes.cast(bg, ctypes.c_void_p), N, total, C, P[0], P[1], sr,
+                                                              all_rois.data_ptr(), inv.data_ptr(), out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                                              _stream()), "b200_roi_align_forward_fpn")
+                done = True
         off = 0
-        kept = []
         with torch.cuda.device(dev):
-            for f, r, sc, n_l in zip(feats, rois, scales, counts):
-                if n_l:
-                    _need_cuda_f32(f, "features"); _need_cuda_f32(r, "rois"); _rois_ok(r)
-                    if f.size(1) != C:
-                        raise ValueError("every pyramid level must have the same number of channels")
-                    f = f.contiguous(); r = r.contiguous()
+            for f, r, sc, n_l in zip(feats, kept, scales, counts):
+                if n_l and not done:
+                    f = f.contiguous()
                     N, _, H, W = f.shape
                     ws_bytes = int(lib.b200_roi_align_workspace_bytes(N, n_l, H, W, P[0], P[1], sr))
                     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
@@ -130,9 +160,6 @@ class _RoIAlignFPN(Function):
                                                                   r.data_ptr(), rows.data_ptr(), out.data_ptr(),
                                                                   ws.data_ptr() if ws is not None else None, ws_bytes, _stream()),
                                "b200_roi_align_forward_indexed")
-                    kept.append(r)
-                else:
-                    kept.append(r)
                 off += n_l
         ctx.meta = (P, sr, [float(sc) for sc in scales], counts, [tuple(f.shape) for f in feats], num_levels)
         ctx.save_for_backward(inv, *kept)

@@ -160,6 +160,26 @@ B200_API int b200_nms(const float* boxes_dev, int boxes_num, int boxes_dim, floa
              int* keep_out_dev, int* num_out_dev, void* workspace, size_t workspace_bytes,
              b200_stream_t stream);
 
+/* ---- RoIAlign over a feature pyramid in ONE launch sequence -------------------------------------
+ * replaces the per-level loop + torch.cat + gather of Generalized_RCNN.roi_feature_transform,
+ * lib/modeling/model_builder.py:264-303: `num_levels` feature maps (same batch size and channel count, any H x W), the
+ * RoIs of all levels stored level-major in bottom_rois (level l owns rows level_roi_begin_host[l] .. [l + 1]), and
+ * top_rows[r] = the row of top_data RoI r is written to (the inverse of the reference's restore permutation; NULL:
+ * identity).  The four *_host arrays and bottom_data_host (device pointers of the maps) are HOST arrays read during the
+ * call.  One streaming kernel walks the strip columns of every level; results are bit-identical to per-level
+ * b200_roi_align_forward calls.  b200_roi_align_fpn_workspace_bytes(...) == 0 means "not applicable" (sampling_ratio
+ * outside {1, 2}, too many strip columns, path switched off): loop over b200_roi_align_forward_indexed instead;
+ * b200_roi_align_forward_fpn then returns B200_ROI_EWORKSPACE. */
+B200_API size_t b200_roi_align_fpn_workspace_bytes(int num_levels, const int* heights_host, const int* widths_host,
+                                                   int batch_size, int num_rois, int aligned_height, int aligned_width,
+                                                   int sampling_ratio);
+B200_API int b200_roi_align_forward_fpn(int num_levels, const float* const* bottom_data_host, const int* heights_host,
+                                        const int* widths_host, const float* spatial_scales_host,
+                                        const int* level_roi_begin_host, int batch_size, int num_rois, int channels,
+                                        int aligned_height, int aligned_width, int sampling_ratio,
+                                        const float* bottom_rois, const int* top_rows, float* top_data, void* workspace,
+                                        size_t workspace_bytes, b200_stream_t stream);
+
 /* Several independent NMS problems in ONE pair of launches (mask kernel over all problems' tiles, one scan CTA per
  * problem): the (image, FPN level) proposal sets of one step (lib/modeling/generate_proposals.py:91-99 runs them one
  * after the other on the host).  Problem p has counts_host[p] score-sorted rows, stored back to back in boxes_dev;

@@ -238,6 +238,30 @@ def test_roi_align_fpn_equals_per_level_loop_cat_and_restore(bwd, lib_option):
             assert a.grad is not None and torch.count_nonzero(a.grad) == 0
 
 
+def test_roi_align_fpn_single_launch_sequence_bit_exact():
+    """SURVEY 8f N2, second step: the whole pyramid in ONE launch sequence (count + fill + one streaming kernel over the strip
+    columns of every level) -- bit-identical to the per-level calls, 3 kernel launches instead of 3 per level."""
+    from detectron.pytorch_b200.modeling.roi_xfrom.roi_align.functions.roi_align_fpn import RoIAlignFPNFunction
+    rng = np.random.RandomState(12)
+    shapes = [(2, 96, 200, 336), (2, 96, 100, 168), (2, 96, 50, 84), (2, 96, 25, 42)]
+    scales = [1.0 / 4, 1.0 / 8, 1.0 / 16, 1.0 / 32]
+    counts = [400, 350, 120, 6]
+    for P in (7, 14):
+        feats = [S.make_features(sh, seed=40 + i) for i, sh in enumerate(shapes)]
+        rois = [S.make_rois(c, sh, sc, seed=50 + i, min_size=16 * 2 ** i, max_size=140 * 2 ** i).astype(np.float32)
+                for i, (c, sh, sc) in enumerate(zip(counts, shapes, scales))]
+        total = sum(counts)
+        restore = rng.permutation(total).astype(np.int32)
+        F = [dev(f) for f in feats]
+        before = _lib.launch_count()
+        out = RoIAlignFPNFunction(P, P, scales, 2)(F, [dev(r) for r in rois], restore)
+        assert _lib.launch_count() - before == 3
+        ref = np.concatenate([O.roi_align_forward(f, r, P, P, sc, 2) for f, r, sc in zip(feats, rois, scales)])[restore]
+        got = out.cpu().numpy()
+        np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-6)
+        assert np.mean(got == ref) > 0.999
+
+
 def test_roi_align_forward_linearity_and_determinism(fwd_path):
     cfg = S.CFG2
     P, s, sr = cfg["pooled"], cfg["scale"], cfg["sampling_ratio"]
