@@ -63,6 +63,12 @@ _SIGNATURES = {
     # (boxes, counts_host, P, dim, thresh, keep_out, num_out, workspace, workspace_bytes, stream)
     "b200_nms_batched": (ctypes.c_int, [_c_float_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _stream_t]),
+    # (dets, counts_host, P, sigma, Nt, score_thresh, method, inds_out, num_out, stream)
+    "b200_soft_nms_batched": (ctypes.c_int, [_c_float_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _stream_t]),
+    # (top, top_counts_host, all, all_counts_host, P, thresh, scoring, beta, out, stream)
+    "b200_box_voting_batched": (ctypes.c_int, [_c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
+                                               ctypes.c_int, ctypes.c_float, _c_float_p, _stream_t]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

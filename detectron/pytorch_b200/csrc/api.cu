@@ -83,6 +83,8 @@ static bool tiled_pays_off(int R, int C, int H, int W, int PH, int PW) {
 }
 int nms(const float*, int, int, float, int*, int*, void*, size_t, cudaStream_t);
 size_t nms_batched_workspace_bytes(const int*, int);
+int soft_nms_batched(float*, const int*, int, float, float, float, int, int*, int*, cudaStream_t);
+int box_voting_batched(const float*, const int*, const float*, const int*, int, float, int, float, float*, cudaStream_t);
 int nms_batched(const float*, const int*, int, int, float, int*, int*, void*, size_t, cudaStream_t);
 size_t roi_align_bwd_nhwc_workspace_bytes(int, int, int, int);
 int roi_align_backward_nhwc(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
@@ -119,6 +121,7 @@ static int backward_path_choice(int N, int R, int C, int H, int W, int PH, int P
         const long long items = (long long)N * H * ((W + 31) / 32) * ((C + 127) / 128);
         const long long units_per_row = 2LL * R * PH * (sr > 0 ? sr : 1) / ((long long)N * H);
         if (items < 1200 || units_per_row > 160) rows_ok = false;
+        if (PW != 7) rows_ok = false;       // 14 x 14 (mask head): 675 us through the gather path vs 530 us reference at P2, R = 256 (r03f)
     }
     if (mode == 3) return rows_ok ? 3 : 0;
     if (mode == 2) return 2;
@@ -404,6 +407,27 @@ int b200_nms_batched(const float* boxes_dev, const int* counts_host, int num_pro
     const int rc = nms_batched(boxes_dev, counts_host, num_problems, boxes_dim, nms_overlap_thresh, keep_out_dev, num_out_dev, workspace,
                                workspace_bytes, (cudaStream_t)stream);
     return rc == 1000 ? B200_ROI_EINVAL : rc;
+}
+
+int b200_soft_nms_batched(float* dets_dev, const int* counts_host, int num_problems, float sigma, float overlap_thresh,
+                          float score_thresh, int method, int* inds_out_dev, int* num_out_dev, b200_stream_t stream) {
+    if (!counts_host || num_problems < 1 || !num_out_dev) return B200_ROI_EINVAL;
+    long long total = 0;
+    for (int p = 0; p < num_problems && p < 128; ++p) total += counts_host[p] > 0 ? counts_host[p] : 0;
+    if (total > 0 && (!dets_dev || !inds_out_dev)) return B200_ROI_EINVAL;
+    return soft_nms_batched(dets_dev, counts_host, num_problems, sigma, overlap_thresh, score_thresh, method, inds_out_dev, num_out_dev,
+                            (cudaStream_t)stream);
+}
+
+int b200_box_voting_batched(const float* top_dets_dev, const int* top_counts_host, const float* all_dets_dev, const int* all_counts_host,
+                            int num_problems, float thresh, int scoring_method, float beta, float* out_dev, b200_stream_t stream) {
+    if (!top_counts_host || !all_counts_host || num_problems < 1) return B200_ROI_EINVAL;
+    long long total = 0;
+    for (int p = 0; p < num_problems && p < 128; ++p) total += top_counts_host[p] > 0 ? top_counts_host[p] : 0;
+    if (total > 0 && (!top_dets_dev || !all_dets_dev || !out_dev)) return B200_ROI_EINVAL;
+    if (scoring_method < 0 || scoring_method > 5) return B200_ROI_EINVAL;
+    return box_voting_batched(top_dets_dev, top_counts_host, all_dets_dev, all_counts_host, num_problems, thresh, scoring_method, beta, out_dev,
+                              (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -283,12 +283,11 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
                 if ((bm >> (pw * SR)) & ((1u << SR) - 1u)) Acc<CPL>::ldg(dyt + (g_off + (unsigned)pw * (unsigned)C), G[pw]);
             return bm;
         };
-        // B: apply the taps of one unit (records in stage buffer `slot`, gradients in G).  With two samples per bin the cells
-        // of the second sample are requested together with the first sample's (four 128-bit loads in flight instead of
-        // two); if the samples share a cell -- a warp-uniform test on the records -- the second pair is simply read
-        // again after the first sample's stores.
+        // B: apply the taps of one unit (records in stage buffer `slot`, gradients in G)
         auto stage_b = [&](int slot, const u64x (&G)[PW][HV], unsigned bm) {
-            auto one = [&](int j) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                if (!((bm >> j) & 1u)) continue;
                 int off_lo, off_hi, wl, wh;
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(off_lo), "=r"(off_hi), "=r"(wl), "=r"(wh)
                              : "r"(stage_s + slot * SB + j * 16));
@@ -302,44 +301,6 @@ roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restric
                 for (int q = 0; q < HV; ++q) { v[q] = fma2(G[j / SR][q], w_lo, v[q]); t[q] = fma2(G[j / SR][q], w_hi, t[q]); }
                 Acc<CPL>::st(a_lo, v);
                 Acc<CPL>::st(a_hi, t);
-            };
-            if (SR == 2) {
-#pragma unroll
-                for (int p = 0; p < PW; ++p) {
-                    const unsigned both = (bm >> (2 * p)) & 3u;
-                    if (both == 0u) continue;
-                    if (both != 3u) { if (both & 1u) one(2 * p); else one(2 * p + 1); continue; }
-                    int o0l, o0h, w0l, w0h, o1l, o1h, w1l, w1h;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o0l), "=r"(o0h), "=r"(w0l), "=r"(w0h)
-                                 : "r"(stage_s + slot * SB + (2 * p) * 16));
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o1l), "=r"(o1h), "=r"(w1l), "=r"(w1h)
-                                 : "r"(stage_s + slot * SB + (2 * p + 1) * 16));
-                    const unsigned a0l = lane_acc + o0l, a0h = lane_acc + o0h, a1l = lane_acc + o1l, a1h = lane_acc + o1h;
-                    u64x v0[HV], t0[HV], v1[HV], t1[HV];
-                    Acc<CPL>::ld(a0l, v0);
-                    Acc<CPL>::ld(a0h, t0);
-                    Acc<CPL>::ld(a1l, v1);
-                    Acc<CPL>::ld(a1h, t1);
-                    const u64x W0l = pack2(__int_as_float(w0l), __int_as_float(w0l)), W0h = pack2(__int_as_float(w0h), __int_as_float(w0h));
-                    const u64x W1l = pack2(__int_as_float(w1l), __int_as_float(w1l)), W1h = pack2(__int_as_float(w1h), __int_as_float(w1h));
-#pragma unroll
-                    for (int q = 0; q < HV; ++q) { v0[q] = fma2(G[p][q], W0l, v0[q]); t0[q] = fma2(G[p][q], W0h, t0[q]); }
-                    Acc<CPL>::st(a0l, v0);
-                    Acc<CPL>::st(a0h, t0);
-                    // real cells shared with the first sample (the scratch cell may repeat freely): read them again
-                    const bool clash = (o1l != kTrash && (o1l == o0l || o1l == o0h)) || (o1h != kTrash && (o1h == o0l || o1h == o0h));
-                    if (clash) { Acc<CPL>::ld(a1l, v1); Acc<CPL>::ld(a1h, t1); }
-#pragma unroll
-                    for (int q = 0; q < HV; ++q) { v1[q] = fma2(G[p][q], W1l, v1[q]); t1[q] = fma2(G[p][q], W1h, t1[q]); }
-                    Acc<CPL>::st(a1l, v1);
-                    Acc<CPL>::st(a1h, t1);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < NX; ++j) {
-                    if (!((bm >> j) & 1u)) continue;
-                    one(j);
-                }
             }
         };
 

@@ -379,6 +379,74 @@ def nms_batched_raw(dets, counts, thresh):
     return keep, num_out
 
 
+def nms_batched_chunked(dets, counts, thresh):
+    """nms_batched_raw for any number of problems (b200_nms_batched takes up to 64 per call): same return layout."""
+    counts = [int(c) for c in counts]
+    if len(counts) <= 64:
+        return nms_batched_raw(dets, counts, thresh)
+    keeps, nums, off = [], [], 0
+    for c0 in range(0, len(counts), 64):
+        chunk = counts[c0:c0 + 64]
+        n = sum(chunk)
+        if n == 0:
+            keeps.append(torch.empty((0,), dtype=torch.int32, device=dets.device))
+            nums.append(torch.zeros((len(chunk),), dtype=torch.int32, device=dets.device))
+        else:
+            k, m = nms_batched_raw(dets[off:off + n], chunk, thresh)
+            keeps.append(k[:n]); nums.append(m)
+        off += n
+    return torch.cat(keeps), torch.cat(nums)
+
+
+def soft_nms_batched(dets, counts, sigma=0.5, overlap_thresh=0.3, score_thresh=0.001, method=1):
+    """Soft-NMS (lib/utils/cython_nms.pyx:98-203) on `len(counts)` problems stored back to back in dets (sum(counts), 5).
+    Returns (dets_out, inds, num_out): problem p's survivors are dets_out[off_p : off_p + num_out[p]] (decayed scores, the
+    reference's output order), inds their original row indices within the problem."""
+    import ctypes
+    _need_cuda_f32(dets, "dets")
+    counts = [int(c) for c in counts]
+    if dets.dim() != 2 or dets.size(1) != 5 or sum(counts) != dets.size(0):
+        raise ValueError("dets must be (sum(counts), 5)")
+    lib = _lib.load()
+    out = dets.contiguous().clone()
+    P = len(counts)
+    inds = torch.empty((max(out.size(0), 1),), dtype=torch.int32, device=dets.device)
+    num_out = torch.empty((P,), dtype=torch.int32, device=dets.device)
+    offs = 0
+    for c0 in range(0, P, 128):
+        chunk = counts[c0:c0 + 128]
+        n = sum(chunk)
+        c_arr = (ctypes.c_int * len(chunk))(*chunk)
+        with torch.cuda.device(dets.device):
+            _lib.check(lib.b200_soft_nms_batched(out.data_ptr() + offs * 20, ctypes.cast(c_arr, ctypes.c_void_p), len(chunk), float(sigma),
+                                                 float(overlap_thresh), float(score_thresh), int(method), inds.data_ptr() + offs * 4,
+                                                 num_out.data_ptr() + c0 * 4, _stream()), "b200_soft_nms_batched")
+        offs += n
+    return out, inds, num_out
+
+
+def box_voting_batched(top_dets, top_counts, all_dets, all_counts, thresh, scoring=0, beta=1.0):
+    """Box voting (lib/utils/boxes.py:268-317) for `len(top_counts)` class problems; returns the refined top_dets."""
+    import ctypes
+    _need_cuda_f32(top_dets, "top_dets"); _need_cuda_f32(all_dets, "all_dets")
+    top_counts = [int(c) for c in top_counts]; all_counts = [int(c) for c in all_counts]
+    if len(top_counts) != len(all_counts) or sum(top_counts) != top_dets.size(0) or sum(all_counts) != all_dets.size(0):
+        raise ValueError("counts do not match the detection tensors")
+    lib = _lib.load()
+    top_dets = top_dets.contiguous(); all_dets = all_dets.contiguous()
+    out = torch.empty_like(top_dets)
+    to = ao = 0
+    for c0 in range(0, len(top_counts), 128):
+        tc, ac = top_counts[c0:c0 + 128], all_counts[c0:c0 + 128]
+        t_arr = (ctypes.c_int * len(tc))(*tc); a_arr = (ctypes.c_int * len(ac))(*ac)
+        with torch.cuda.device(top_dets.device):
+            _lib.check(lib.b200_box_voting_batched(top_dets.data_ptr() + to * 20, ctypes.cast(t_arr, ctypes.c_void_p),
+                                                   all_dets.data_ptr() + ao * 20, ctypes.cast(a_arr, ctypes.c_void_p), len(tc), float(thresh),
+                                                   int(scoring), float(beta), out.data_ptr() + to * 20, _stream()), "b200_box_voting_batched")
+        to += sum(tc); ao += sum(ac)
+    return out
+
+
 def nms_raw(dets, thresh):
     """Returns (keep int32 (N,), num_out int32 (1,)) on the device, no host sync."""
     _need_cuda_f32(dets, "dets")

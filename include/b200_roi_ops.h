@@ -192,6 +192,22 @@ B200_API int b200_nms_batched(const float* boxes_dev, const int* counts_host, in
                               float nms_overlap_thresh, int* keep_out_dev, int* num_out_dev, void* workspace,
                               size_t workspace_bytes, b200_stream_t stream);
 
+/* ---- test-time detection post-processing ------------------------------------------------------
+ * The per-class problems of lib/core/test.py:732-790 (box_results_with_nms_and_limit), batched like b200_nms_batched:
+ * problem p = the detections of one class, counts_host[p] rows of [x1, y1, x2, y2, score] stored back to back
+ * (1 <= num_problems <= 128).  Classic NMS goes through b200_nms_batched.
+ * b200_soft_nms_batched: lib/utils/cython_nms.pyx:98-203 step for step (method 1 linear, 2 gaussian, else hard), IN PLACE:
+ *   afterwards problem p's first num_out_dev[p] rows are its surviving detections with decayed scores, in the
+ *   reference's output order, and inds_out_dev holds their original row indices (relative to the problem).
+ * b200_box_voting_batched: lib/utils/boxes.py:268-317; top_dets (the NMS survivors) are replaced in out_dev by the
+ *   score-weighted average of all_dets rows with IoU >= thresh (cython_bbox.bbox_overlaps convention); scoring_method
+ *   0 ID, 1 AVG, 2 IOU_AVG, 3 TEMP_AVG, 4 GENERALIZED_AVG, 5 QUASI_SUM. */
+B200_API int b200_soft_nms_batched(float* dets_dev, const int* counts_host, int num_problems, float sigma, float overlap_thresh,
+                                   float score_thresh, int method, int* inds_out_dev, int* num_out_dev, b200_stream_t stream);
+B200_API int b200_box_voting_batched(const float* top_dets_dev, const int* top_counts_host, const float* all_dets_dev,
+                                     const int* all_counts_host, int num_problems, float thresh, int scoring_method, float beta,
+                                     float* out_dev, b200_stream_t stream);
+
 /* ---- introspection used by the benchmark / tests (no compute) ----------------------------------
  * Number of kernel launches the library has enqueued since load (all entry points). */
 B200_API unsigned long long b200_roi_ops_launch_count(void);
