@@ -9,7 +9,8 @@ namespace b200 {
 unsigned long long g_launch_count = 0;
 
 static const char* const kOptionNames[kNumOptions] = {"B200_ROI_ALIGN_PATH", "B200_ROI_ALIGN_BWD_PATH", "B200_ROI_ALIGN_BWD_CPL",
-                                                      "B200_FWD_ZERO", "B200_NMS_SCAN", "B200_STREAM_STAGE", "B200_STREAM_PHASES"};
+                                                      "B200_FWD_ZERO", "B200_NMS_SCAN", "B200_STREAM_STAGE", "B200_STREAM_PHASES",
+                                                      "B200_FPN_PATH"};
 static int g_options[kNumOptions];
 static std::once_flag g_options_once;
 
@@ -369,7 +370,8 @@ int b200_nms(const float* boxes_dev, int boxes_num, int boxes_dim, float nms_ove
 
 size_t b200_roi_align_fpn_workspace_bytes(int num_levels, const int* heights_host, const int* widths_host, int batch_size, int num_rois,
                                           int aligned_height, int aligned_width, int sampling_ratio) {
-    if (num_levels < 1 || !heights_host || !widths_host || batch_size <= 0 || num_rois <= 0 || forward_path_mode() == 1 || forward_path_mode() == 2)
+    if (num_levels < 1 || !heights_host || !widths_host || batch_size <= 0 || num_rois <= 0 || forward_path_mode() == 1 || forward_path_mode() == 2 ||
+        option_get(kOptFpnPath) == 'l')
         return 0;
     return roi_align_stream_fpn_workspace_bytes(num_levels, heights_host, widths_host, batch_size, num_rois, aligned_height, aligned_width,
                                                 sampling_ratio);

@@ -29,6 +29,7 @@ enum Option {
     kOptNmsScan,          // B200_NMS_SCAN            = resolver | simple
     kOptStreamStage,      // B200_STREAM_STAGE        = async (cp.async) | regs (LDG -> registers -> STS)
     kOptStreamPhases,     // B200_STREAM_PHASES       = all | prepass (timing probe: the main kernel is not launched)
+    kOptFpnPath,          // B200_FPN_PATH            = fused (one launch sequence over the level table) | levels (per-level calls)
     kNumOptions
 };
 int option_get(Option which);

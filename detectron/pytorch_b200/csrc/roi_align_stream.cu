@@ -72,6 +72,25 @@ __device__ u64* g_stream_dbg = nullptr;
 #define SDBG(slot, val) do { } while (0)
 #endif
 
+// Timing build (-DB200_STREAM_TIMING, tools/stream_timing.py): every warp leaves SM clock stamps and wait-cycle totals in a
+// DEVICE buffer registered the same way ([CTA][warp][8] u64).  Compiled out by default.
+#ifdef B200_STREAM_TIMING
+__device__ u64* g_stream_tim = nullptr;
+#define STIM_DECL u64 stim_wait = 0, stim_n0 = 0, stim_n1 = 0, stim_first = 0, stim_comp = 0, stim_c0 = 0
+#define STIM_CLOCK() ((u64)clock64())
+#define STIM(slot, val)                                                                                      \
+    do {                                                                                                     \
+        if (g_stream_tim != nullptr && (threadIdx.x & 31) == 0)                                              \
+            g_stream_tim[((size_t)blockIdx.x * (kConsumerWarps + kProducerWarps) + (threadIdx.x >> 5)) * 8 + (slot)] = (u64)(val); \
+    } while (0)
+#define STIM_DO(stmt) do { stmt; } while (0)
+#else
+#define STIM_DECL
+#define STIM_CLOCK() 0ull
+#define STIM(slot, val) do { } while (0)
+#define STIM_DO(stmt) do { } while (0)
+#endif
+
 constexpr int kMaxLevels = 6;                                 // feature maps served by one launch (FPN: P2..P6)
 constexpr int kMaxCols = 96;                                  // strip columns (level, image, strip) of one launch
 
@@ -396,6 +415,9 @@ stream_fill(const float* __restrict__ rois, StreamGeom g, StreamWs ws, float* __
 // ------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + cp.async
 // ------------------------------------------------------------------------------------------------
+// Watchdog evidence: a wait that is half way to the trap leaves a record here ([CTA][32] u64; host-pinned, optional).
+__device__ u64* g_stream_dead = nullptr;
+
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -415,11 +437,27 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
 }
 // try_wait suspends the thread in hardware for a bounded time per attempt.  A wait that is still pending after 2^20
 // attempts (seconds) is a protocol bug: trap (surfaces as a launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity, unsigned tag = 0u) {
+#ifdef B200_STREAM_WATCH
+#define WCTX(expr) (expr)
+#else
+#define WCTX(expr) 0ull
+#endif
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity, unsigned tag = 0u, u64 ctx0 = 0ull, u64 ctx1 = 0ull) {
     if (mbar_try_wait(bar, parity)) return;
     int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1 << 20)) {
+        ++spins;
+        if (spins == (1 << 19) && g_stream_dead != nullptr && (threadIdx.x & 31) == 0) {
+            // half way to the trap: say who is stuck on what (host-pinned buffer registered by the caller, else nothing)
+            g_stream_dead[blockIdx.x * 32 + (threadIdx.x >> 5)] =
+                0xDEAD000000000000ull | ((u64)tag << 16) | ((u64)parity << 8) | (u64)((bar >> 3) & 0xff);
+#ifdef B200_STREAM_WATCH
+            g_stream_dead[148 * 32 + (blockIdx.x * 32 + (threadIdx.x >> 5)) * 2] = ctx0;
+            g_stream_dead[148 * 32 + (blockIdx.x * 32 + (threadIdx.x >> 5)) * 2 + 1] = ctx1;
+#endif
+            __threadfence_system();
+        }
+        if (spins > (1 << 20)) {
             SDBG(6, 0xDEAD000000000000ull | ((u64)tag << 16) | ((u64)parity << 8) | (u64)((bar >> 3) & 0xff));
             __trap();
         }
@@ -610,6 +648,8 @@ roi_align_stream_fwd(const StreamArgs a) {
     __syncthreads();
     const int L0 = __ldg(&a.piece_start[blockIdx.x]), L1 = __ldg(&a.piece_start[blockIdx.x + 1]);
     SDBG(0, 1); SDBG(1, ((u64)(unsigned)L0 << 32) | (unsigned)L1);
+    STIM_DECL;
+    STIM(0, STIM_CLOCK()); STIM(7, ((u64)(unsigned)L0 << 32) | (unsigned)L1);
 
     if (warp >= kConsumerWarps) {
         // =============================== producers ===============================
@@ -633,9 +673,19 @@ roi_align_stream_fwd(const StreamArgs a) {
             const int rowlen = lv.W;
             const float* src = lv.bottom + ((size_t)it.n * a.C + c0) * plane + (size_t)it.ya * lv.W + x0;
             for (int y = it.ya; y < it.yhi; ++y) {
+                // EVERY producer waits for EVERY row's slot, not only for the rows it stages: successive uses of a slot can
+                // belong to different producer warps (K % kProducerWarps != 0, or an item boundary), and a parity wait that
+                // runs two phases ahead of its barrier passes at once -- a producer that skipped the wait of use k - 1 could
+                // overtake the warp that stages it and overwrite use k - 2.  Having seen use k - 2 released here, the test
+                // for use k can only be one phase ahead (measured: K = 15, four producers, rows 2 and 17 of one item).
+                const unsigned full = bars + 8u * slot, empty = bars + 8u * (kMaxSlots + slot);
+                STIM_DO(stim_n1 = STIM_CLOCK());
+                mbar_wait(empty, (ephase >> slot) & 1u, 0x1000u + (unsigned)y,
+                          WCTX(((u64)it.ya << 48) | ((u64)it.yb << 32) | ((u64)it.yhi << 16) | (u64)(it.lvl << 12) | (u64)(it.g << 8) | (u64)it.s),
+                          WCTX(((u64)ephase << 32) | (u64)(unsigned)(L - (it.yb - it.ya))));
+                STIM_DO(stim_wait += STIM_CLOCK() - stim_n1);
                 if (turn == pw) {
-                    const unsigned full = bars + 8u * slot, empty = bars + 8u * (kMaxSlots + slot);
-                    mbar_wait(empty, (ephase >> slot) & 1u, 0x1000u + (unsigned)y);
+                    STIM_DO(++stim_n0; if (!stim_first) stim_first = STIM_CLOCK());
                     SDBG(4, ((u64)y << 32) | (u64)slot);
                     stage_row<M, ASYNC>(src, plane, ring + (unsigned)slot * (unsigned)RB, xw, cvalid, lane);
                     if (slot == 0) stage_row<M, ASYNC>(src, plane, ring + (unsigned)a.K * (unsigned)RB, xw, cvalid, lane);   // mirror
@@ -648,6 +698,7 @@ roi_align_stream_fwd(const StreamArgs a) {
             }
         }
         SDBG(0, 9);
+        STIM(1, stim_first); STIM(2, STIM_CLOCK()); STIM(3, stim_wait); STIM(4, stim_n0);
         return;
     }
 
@@ -674,7 +725,11 @@ roi_align_stream_fwd(const StreamArgs a) {
         // phase bits in step with the producers)
         auto acquire_to = [&](int row_end, unsigned tag) {
             while (acq < row_end) {
-                mbar_wait(bars + 8u * acq_slot, (fphase >> acq_slot) & 1u, tag + (unsigned)acq);
+                STIM_DO(stim_n1 = STIM_CLOCK());
+                mbar_wait(bars + 8u * acq_slot, (fphase >> acq_slot) & 1u, tag + (unsigned)acq,
+                          WCTX(((u64)it.ya << 48) | ((u64)it.yb << 32) | ((u64)it.yhi << 16) | (u64)(it.lvl << 12) | (u64)(it.g << 8) | (u64)it.s),
+                          WCTX(((u64)fphase << 32) | ((u64)(unsigned)rel << 16) | (u64)(unsigned)row_end));
+                STIM_DO(stim_wait += STIM_CLOCK() - stim_n1);
                 fphase ^= 1u << acq_slot;
                 ++acq;
                 if (++acq_slot == a.K) acq_slot = 0;
@@ -686,7 +741,8 @@ roi_align_stream_fwd(const StreamArgs a) {
                     int rs = rel_slot;
                     for (int y = rel; y < row_end; ++y) { mbar_arrive(bars + 8u * (kMaxSlots + rs)); if (++rs == a.K) rs = 0; }
                 }
-                rel_slot = (rel_slot + (row_end - rel)) % a.K;
+                rel_slot += row_end - rel;                     // one wrap at most in the common case: no division
+                while (rel_slot >= a.K) rel_slot -= a.K;
                 rel = row_end;
             }
         };
@@ -699,8 +755,10 @@ roi_align_stream_fwd(const StreamArgs a) {
         auto load_tab = [&](const uint2& en) -> uint4 {
             const int rn = en.x & 0xffffu, phn = (en.x >> 16) & 31u, pwn = (en.x >> 21) & 31u, nn = (int)((en.x >> 26) & 7u) + 1;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (lane < nn * SR) v = __ldg(a.xtab + (size_t)rn * a.nx + pwn * SR + lane);
-            else if (lane >= 16 && lane < 16 + SR) v = __ldg(a.ytab + (size_t)rn * a.ny + phn * SR + (lane - 16));
+            const bool isx = lane < nn * SR;                   // one predicated load: the two tables differ in base and index only
+            const uint4* base = isx ? a.xtab : a.ytab;
+            const int idx = isx ? rn * a.nx + pwn * SR + lane : rn * a.ny + phn * SR + (lane - 16);
+            if (isx || (lane >= 16 && lane < 16 + SR)) v = __ldg(base + idx);
             return v;
         };
         int e = it.e0 + warp;
@@ -732,6 +790,7 @@ roi_align_stream_fwd(const StreamArgs a) {
             }
             acquire_to(end, 0x2800u);                           // rows [key, end) must be resident
             SDBG(3, ((u64)cur.x << 32) | (u64)cur.y);
+            STIM_DO(++stim_n0; stim_c0 = STIM_CLOCK(); if (!stim_first) stim_first = stim_c0);
             const uint4 yA = lds128(tbuf + 16 * 16);
             uint4 yB = yA;
             if (SR == 2) yB = lds128(tbuf + 17 * 16);
@@ -786,7 +845,12 @@ roi_align_stream_fwd(const StreamArgs a) {
                 float* dst = a.out + ((size_t)orow * a.C + c0) * bins + ph * a.PW + pw0 + fb;
                 const float* src = stage + fb * kStageStride + chsub;
                 const int cmax = a.C - c0 - chsub;               // channel 4*cb + chsub is real iff 4*cb < cmax
-                if (!red) {
+                if (!red && cmax + chsub >= 32) {                        // a full channel group: no predicates, one pointer walk
+                    float* d = dst + (size_t)chsub * bins;
+                    const size_t step = (size_t)bins * 4;
+#pragma unroll
+                    for (int cb = 0; cb < 8; ++cb) { *d = src[4 * cb]; d += step; }
+                } else if (!red) {
 #pragma unroll
                     for (int cb = 0; cb < 8; ++cb)
                         if (4 * cb < cmax) dst[(size_t)(4 * cb + chsub) * bins] = src[4 * cb];
@@ -797,6 +861,7 @@ roi_align_stream_fwd(const StreamArgs a) {
                 }
             }
             __syncwarp();
+            STIM_DO(stim_comp += STIM_CLOCK() - stim_c0);
             e = e_next;
         }
         // item tail: nothing more to read -- give back what is held, then pass the remaining rows through one by one
@@ -811,6 +876,7 @@ roi_align_stream_fwd(const StreamArgs a) {
         SDBG(0, 6);
     }
     SDBG(0, 9);
+    STIM(1, stim_first); STIM(2, STIM_CLOCK()); STIM(3, stim_wait); STIM(4, stim_n0); STIM(5, stim_comp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -934,10 +1000,12 @@ bool stream_device_info(int* sm_count) {
 }  // namespace
 
 void roi_align_stream_set_debug_buffer(unsigned long long* host_pinned) {
-#ifdef B200_STREAM_DEBUG
+#if defined(B200_STREAM_DEBUG)
     cudaMemcpyToSymbol(g_stream_dbg, &host_pinned, sizeof(host_pinned));
+#elif defined(B200_STREAM_TIMING)
+    cudaMemcpyToSymbol(g_stream_tim, &host_pinned, sizeof(host_pinned));
 #else
-    (void)host_pinned;
+    cudaMemcpyToSymbol(g_stream_dead, &host_pinned, sizeof(host_pinned));      // [CTA][32] u64 watchdog records
 #endif
 }
 

@@ -28,6 +28,7 @@
 // Semantics: lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu (reference) :16-63, :65-121.
 #include "roi_align_tiled.cuh"
 #include <stdlib.h>
+#include <mutex>
 
 namespace b200 {
 
@@ -370,10 +371,12 @@ int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int 
     int* tile_count = zero + 4;
     unsigned* tile_list = (unsigned*)(ws + p.tile_list_off);
 
+    static std::mutex attr_mu;              // several host threads may make their first call at once
     static bool attr_set[64] = {false};     // per device: the attribute lives in the device's context
     static int sm_count[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1000;
+    std::unique_lock<std::mutex> attr_lock(attr_mu);
     if (!attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(roi_align_tiled_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (228 * 1024 - kTiledCtasPerSM * 1024) / kTiledCtasPerSM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_align_tiled_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (228 * 1024 - kTiledCtasPerSM * 1024) / kTiledCtasPerSM);
@@ -383,6 +386,8 @@ int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int 
         if (e != cudaSuccess) return (int)e;
         attr_set[dev] = true;
     }
+    const int sms = sm_count[dev];
+    attr_lock.unlock();
     cudaError_t err = cudaMemsetAsync(zero, 0, p.zero_bytes, stream);
     if (err != cudaSuccess) return (int)err;
     // The bins the main kernel accumulates into must start at zero.  With a dense output one memset of the whole tensor
@@ -398,7 +403,7 @@ int roi_align_forward_tiled(const float* bottom, float scale, int N, int R, int 
                                                whole ? 0 : 1);
     const int n_cgroups = (C + kCG - 1) / kCG;
     const int n_work = p.tiles_total * n_cgroups;
-    const int grid = n_work < kTiledCtasPerSM * sm_count[dev] ? n_work : kTiledCtasPerSM * sm_count[dev];      // persistent CTAs
+    const int grid = n_work < kTiledCtasPerSM * sms ? n_work : kTiledCtasPerSM * sms;      // persistent CTAs
 #define B200_LAUNCH_TILED(SRV)                                                                                              \
     roi_align_tiled_fwd<SRV><<<grid, kTiledThreads, p.smem_bytes, stream>>>(bottom, ytab, xtab, work_counter, tile_count,   \
         tile_list, R * p.groups_max, top, N, R, C, H, W, PH, PW, p.ny, p.nx, p.core_h, p.core_w, p.tile_h, p.tiles_y, p.tiles_x, \
