@@ -10,7 +10,7 @@ unsigned long long g_launch_count = 0;
 
 static const char* const kOptionNames[kNumOptions] = {"B200_ROI_ALIGN_PATH", "B200_ROI_ALIGN_BWD_PATH", "B200_ROI_ALIGN_BWD_CPL",
                                                       "B200_FWD_ZERO", "B200_NMS_SCAN", "B200_STREAM_STAGE", "B200_STREAM_PHASES",
-                                                      "B200_FPN_PATH"};
+                                                      "B200_FPN_PATH", "B200_STRIP_ROWCOST", "B200_STRIP_PDL"};
 static int g_options[kNumOptions];
 static std::once_flag g_options_once;
 
@@ -57,15 +57,22 @@ size_t roi_align_stream_fpn_workspace_bytes(int, const int*, const int*, int, in
 int roi_align_forward_stream_fpn(int, const float* const*, const int*, const int*, const float*, const int*, int, int, int, int, int, int,
                                  const float*, float*, const int*, void*, size_t, cudaStream_t);
 int roi_align_forward_stream(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
+size_t roi_align_strip_workspace_bytes(int, int, int, int, int, int, int);
+size_t roi_align_strip_fpn_workspace_bytes(int, const int*, const int*, int, int, int, int, int);
+int roi_align_forward_strip_fpn(int, const float* const*, const int*, const int*, const float*, const int*, int, int, int, int, int, int,
+                                const float*, float*, const int*, void*, size_t, cudaStream_t);
+int roi_align_forward_strip(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
+void roi_align_strip_set_debug_buffer(unsigned long long*);
 
 // B200_ROI_ALIGN_PATH=generic|tiled|stream|auto (default auto) -- test/benchmark override of the forward dispatch
-//   0 auto: streaming-strip path (TMA) -> tiled path -> generic, each when it applies
-//   1 generic only; 2 tiled (-> generic); 3 stream (-> generic)
+//   0 auto: quad-strip path -> streaming-strip path -> tiled path -> generic, each when it applies
+//   1 generic only; 2 tiled (-> generic); 3 stream (-> generic); 4 quad strip (-> generic)
 static int forward_path_mode() {
     const int e = option_get(kOptFwdPath);
     if (e == 'g') return 1;
     if (e == 't') return 2;
     if (e == 's') return 3;
+    if (e == 'q') return 4;
     return 0;
 }
 
@@ -73,7 +80,9 @@ static size_t forward_workspace_bytes(int mode, int N, int R, int H, int W, int 
     if (mode == 1) return 0;
     const size_t a = (mode == 3 || mode == 0) ? roi_align_stream_workspace_bytes(N, R, H, W, PH, PW, sr) : 0;
     const size_t b = (mode == 2 || mode == 0) ? roi_align_tiled_workspace_bytes(N, R, H, W, PH, PW, sr) : 0;
-    return a > b ? a : b;
+    const size_t c = (mode == 4 || mode == 0) ? roi_align_strip_workspace_bytes(N, R, H, W, PH, PW, sr) : 0;
+    const size_t ab = a > b ? a : b;
+    return ab > c ? ab : c;
 }
 
 static bool tiled_pays_off(int R, int C, int H, int W, int PH, int PW) {
@@ -157,6 +166,7 @@ void b200_roi_ops_debug_timing_buffer(void* device_u64x16) {
     roi_align_tiled_set_timing_buffer((unsigned long long*)device_u64x16);
     nms_set_timing_buffer((unsigned long long*)device_u64x16);
     roi_align_stream_set_debug_buffer((unsigned long long*)device_u64x16);      // -DB200_STREAM_DEBUG builds only
+    roi_align_strip_set_debug_buffer((unsigned long long*)device_u64x16);       // watchdog records of the quad-strip path
 }
 
 size_t b200_roi_align_workspace_bytes(int batch_size, int num_rois, int height, int width, int aligned_height,
@@ -182,6 +192,12 @@ int b200_roi_align_forward_indexed(const float* bottom_data, float spatial_scale
     if (num_rois > 0 && channels > 0 && (!bottom_data || !bottom_rois || !top_data)) return B200_ROI_EINVAL;
     const int mode = forward_path_mode();
     const bool pays = tiled_pays_off(num_rois, channels, height, width, aligned_height, aligned_width);
+    if (workspace != nullptr && (mode == 4 || (mode == 0 && pays))) {
+        const int rc = roi_align_forward_strip(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
+                                               aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data, top_rows,
+                                               workspace, workspace_bytes, (cudaStream_t)stream);
+        if (rc != 1000) return rc;
+    }
     if (workspace != nullptr && (mode == 3 || (mode == 0 && pays))) {
         const int rc = roi_align_forward_stream(bottom_data, spatial_scale, batch_size, num_rois, height, width, channels,
                                                 aligned_height, aligned_width, sampling_ratio, bottom_rois, top_data, top_rows,
@@ -373,8 +389,11 @@ size_t b200_roi_align_fpn_workspace_bytes(int num_levels, const int* heights_hos
     if (num_levels < 1 || !heights_host || !widths_host || batch_size <= 0 || num_rois <= 0 || forward_path_mode() == 1 || forward_path_mode() == 2 ||
         option_get(kOptFpnPath) == 'l')
         return 0;
-    return roi_align_stream_fpn_workspace_bytes(num_levels, heights_host, widths_host, batch_size, num_rois, aligned_height, aligned_width,
-                                                sampling_ratio);
+    const size_t a = roi_align_stream_fpn_workspace_bytes(num_levels, heights_host, widths_host, batch_size, num_rois, aligned_height,
+                                                          aligned_width, sampling_ratio);
+    const size_t b = forward_path_mode() == 3 ? 0 : roi_align_strip_fpn_workspace_bytes(num_levels, heights_host, widths_host, batch_size, num_rois,
+                                                                                        aligned_height, aligned_width, sampling_ratio);
+    return a > b ? a : b;
 }
 
 int b200_roi_align_forward_fpn(int num_levels, const float* const* bottom_data_host, const int* heights_host, const int* widths_host,
@@ -388,10 +407,17 @@ int b200_roi_align_forward_fpn(int num_levels, const float* const* bottom_data_h
     if (level_roi_begin_host[0] != 0 || level_roi_begin_host[num_levels] != num_rois) return B200_ROI_EINVAL;
     for (int l = 0; l < num_levels; ++l)
         if (!bottom_data_host[l] || level_roi_begin_host[l + 1] < level_roi_begin_host[l]) return B200_ROI_EINVAL;
-    const int rc = roi_align_forward_stream_fpn(num_levels, bottom_data_host, heights_host, widths_host, spatial_scales_host,
-                                                level_roi_begin_host, batch_size, num_rois, channels, aligned_height, aligned_width,
-                                                sampling_ratio, bottom_rois, top_data, top_rows, workspace, workspace_bytes,
-                                                (cudaStream_t)stream);
+    int rc = 1000;
+    if (forward_path_mode() != 3)
+        rc = roi_align_forward_strip_fpn(num_levels, bottom_data_host, heights_host, widths_host, spatial_scales_host,
+                                         level_roi_begin_host, batch_size, num_rois, channels, aligned_height, aligned_width,
+                                         sampling_ratio, bottom_rois, top_data, top_rows, workspace, workspace_bytes,
+                                         (cudaStream_t)stream);
+    if (rc == 1000)
+        rc = roi_align_forward_stream_fpn(num_levels, bottom_data_host, heights_host, widths_host, spatial_scales_host,
+                                          level_roi_begin_host, batch_size, num_rois, channels, aligned_height, aligned_width,
+                                          sampling_ratio, bottom_rois, top_data, top_rows, workspace, workspace_bytes,
+                                          (cudaStream_t)stream);
     return rc == 1000 ? B200_ROI_EWORKSPACE : rc;
 }
 

@@ -22,7 +22,7 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 // be changed afterwards through b200_roi_ops_set_option() -- the hot path never calls getenv().
 // The value is the first character of the string ('\0' = auto / default).
 enum Option {
-    kOptFwdPath = 0,      // B200_ROI_ALIGN_PATH      = auto | generic | tiled | stream
+    kOptFwdPath = 0,      // B200_ROI_ALIGN_PATH      = auto | generic | tiled | stream | quad (roi_align_strip.cu, the default fast path)
     kOptBwdPath,          // B200_ROI_ALIGN_BWD_PATH  = auto | generic | nhwc | rows
     kOptBwdCpl,           // B200_ROI_ALIGN_BWD_CPL   = 4 | 2
     kOptFwdZero,          // B200_FWD_ZERO            = dense | bins
@@ -30,6 +30,8 @@ enum Option {
     kOptStreamStage,      // B200_STREAM_STAGE        = async (cp.async) | regs (LDG -> registers -> STS)
     kOptStreamPhases,     // B200_STREAM_PHASES       = all | prepass (timing probe: the main kernel is not launched)
     kOptFpnPath,          // B200_FPN_PATH            = fused (one launch sequence over the level table) | levels (per-level calls)
+    kOptStripRowCost,     // B200_STRIP_ROWCOST       = 0..9: cost of streaming a row in the partition model = 8 d + 4 (default 24)
+    kOptStripPdl,         // B200_STRIP_PDL           = 1 | 0: programmatic dependent launch of the main kernel behind the prepass
     kNumOptions
 };
 int option_get(Option which);

@@ -37,15 +37,16 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-@pytest.fixture(params=["generic", "tiled", "tiled-rows", "stream"])
+@pytest.fixture(params=["generic", "tiled", "tiled-rows", "stream", "quad"])
 def fwd_path(request, lib_option):
     """Force the RoIAlign forward AND backward dispatch (b200_roi_ops_set_option):
     generic = RoI-centric kernels (scalar atomics in the backward), tiled = feature-map-stationary
     forward + vector-reduction (NHWC scratch) backward, tiled-rows = same forward + row-stationary gather
     backward (falls back to the scalar-atomic kernel for shapes it does not cover), stream = cp.async streaming-strip
-    forward (falls back to the generic kernel for shapes it does not cover) + the default backward."""
-    lib_option("B200_ROI_ALIGN_PATH", {"generic": "generic", "tiled": "tiled", "tiled-rows": "tiled", "stream": "stream"}[request.param])
-    lib_option("B200_ROI_ALIGN_BWD_PATH", {"generic": "generic", "tiled": "nhwc", "tiled-rows": "rows", "stream": "auto"}[request.param])
+    forward (falls back to the generic kernel for shapes it does not cover) + the default backward, quad = the quad-strip
+    forward (roi_align_strip.cu, the default fast path; same fallback) + the default backward."""
+    lib_option("B200_ROI_ALIGN_PATH", {"generic": "generic", "tiled": "tiled", "tiled-rows": "tiled", "stream": "stream", "quad": "quad"}[request.param])
+    lib_option("B200_ROI_ALIGN_BWD_PATH", {"generic": "generic", "tiled": "nhwc", "tiled-rows": "rows", "stream": "auto", "quad": "auto"}[request.param])
     return request.param
 
 
@@ -75,7 +76,7 @@ def assert_fwd_matches(out, ref, path):
     """generic path: bit-exact.  tiled path: bit-exact except bins whose samples straddle two tiles,
     which add <= 4 partial means in a different association (~1 ulp): |a-b| <= 1e-6 + 1e-6*|b|.
     stream path: bit-exact except the rare bins whose samples cannot be resident together (two partial sums)."""
-    if path == "stream":
+    if path in ("stream", "quad"):
         np.testing.assert_allclose(out, ref, rtol=1e-6, atol=1e-6)
         assert np.mean(out == ref) > 0.9
     elif path.startswith("tiled"):
@@ -255,7 +256,7 @@ def test_roi_align_fpn_single_launch_sequence_bit_exact():
         F = [dev(f) for f in feats]
         before = _lib.launch_count()
         out = RoIAlignFPNFunction(P, P, scales, 2)(F, [dev(r) for r in rois], restore)
-        assert _lib.launch_count() - before == 3
+        assert _lib.launch_count() - before == 2          # prep + main of the quad-strip path, whole pyramid
         ref = np.concatenate([O.roi_align_forward(f, r, P, P, sc, 2) for f, r, sc in zip(feats, rois, scales)])[restore]
         got = out.cpu().numpy()
         np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-6)
@@ -270,7 +271,7 @@ def test_roi_align_forward_linearity_and_determinism(fwd_path):
     fn = RoIAlignFunction(P, P, s, sr)
     a, b, ab = fn(F1, R), fn(F2, R), fn(F1 + F2, R)
     torch.testing.assert_close(ab, a + b, rtol=1e-5, atol=1e-5)
-    if fwd_path in ("generic", "stream"):                  # stream: at most two partial sums per element -> order-independent
+    if fwd_path in ("generic", "stream", "quad"):                  # stream: at most two partial sums per element -> order-independent
         assert torch.equal(fn(F1, R), a)                   # run-to-run bit-identical
         assert torch.equal(fn(2 * F1, R), 2 * a)           # scaling by a power of two is exact
     else:                                                  # bins split over 4 tiles add 3 partials atomically
@@ -316,12 +317,16 @@ STREAM_CASES = {
 }
 
 
+STRIP_LAUNCHES = {"stream": 3, "quad": 2}       # count + fill + main / prep + main (memsets are not counted)
+
+
+@pytest.mark.parametrize("path", ["stream", "quad"])
 @pytest.mark.parametrize("name", sorted(STREAM_CASES))
-def test_roi_align_stream_path(name, lib_option):
+def test_roi_align_stream_path(name, path, lib_option):
     """Streaming-strip forward (cp.async + mbarrier ring) vs the oracle: every bin whose samples fit the strip halo / the ring is computed by one
     lane in the reference's order -> bit-exact; bins cut into two partial sums (huge boxes) agree to 1e-6.  The launch
-    counter proves the streaming kernels ran (count + fill + main) and not a fallback."""
-    lib_option("B200_ROI_ALIGN_PATH", "stream")
+    counter proves the streaming kernels ran (count + fill + main, or prep + main for the quad-strip generation) and not a fallback."""
+    lib_option("B200_ROI_ALIGN_PATH", path)
     shape, s, P, sr, n, lo, hi = STREAM_CASES[name]
     f = S.make_features(shape, seed=3)
     r = np.concatenate([S.make_rois(n, shape, s, seed=4, min_size=lo, max_size=hi), S.make_edge_rois(shape, s)]).astype(np.float32)
@@ -330,7 +335,7 @@ def test_roi_align_stream_path(name, lib_option):
     ref = O.roi_align_forward(f, rr, P, P, s, sr); ref[5] = 0
     before = _lib.launch_count()
     out = RoIAlignFunction(P, P, s, sr)(dev(f), dev(r)).cpu().numpy()
-    assert _lib.launch_count() - before == 3
+    assert _lib.launch_count() - before == STRIP_LAUNCHES[path]
     np.testing.assert_allclose(out, ref, rtol=1e-6, atol=1e-6)
     per_roi_exact = (out == ref).reshape(out.shape[0], -1).all(axis=1)
     assert per_roi_exact[:n].mean() > 0.9, "bins of ordinary RoIs must be bit-exact"
@@ -338,16 +343,17 @@ def test_roi_align_stream_path(name, lib_option):
     assert np.array_equal(out, out2)              # deterministic, split bins included
 
 
-def test_roi_align_stream_cfg2_bit_exact(lib_option):
+@pytest.mark.parametrize("path", ["stream", "quad"])
+def test_roi_align_stream_cfg2_bit_exact(path, lib_option):
     """BASELINE cfg2 through the streaming path: no bin needs a split at this geometry except a handful -> the result is
     bit-identical to the reference kernel's (and to the oracle) on > 99.9 % of the elements, 1e-6 on the rest."""
-    lib_option("B200_ROI_ALIGN_PATH", "stream")
+    lib_option("B200_ROI_ALIGN_PATH", path)
     cfg = S.CFG2
     P, s, sr = cfg["pooled"], cfg["scale"], cfg["sampling_ratio"]
     f = S.make_features(cfg["shape"]); r = S.make_rois(cfg["rois"], cfg["shape"], s)
     before = _lib.launch_count()
     out = RoIAlignFunction(P, P, s, sr)(dev(f), dev(r)).cpu().numpy()
-    assert _lib.launch_count() - before == 3
+    assert _lib.launch_count() - before == STRIP_LAUNCHES[path]
     ref = O.roi_align_forward(f, r, P, P, s, sr)
     np.testing.assert_allclose(out, ref, rtol=1e-6, atol=1e-6)
     assert np.mean(out == ref) > 0.999
