@@ -32,6 +32,7 @@
 //
 // Semantics: lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu (reference) :16-63, :65-121.
 #include "common.cuh"
+#include <cuda.h>                                              // CUtensorMap types only: the encoder is fetched with cudaGetDriverEntryPoint
 #include <mutex>
 #include <string.h>
 
@@ -39,11 +40,21 @@ namespace b200 {
 
 namespace {
 
-constexpr int kCW = 16;                                       // consumer warps
-constexpr int kThreads = 32 * (kCW + 1);                      // + one producer warp
+#ifndef B200_STRIP_CONSUMERS
+#define B200_STRIP_CONSUMERS 16
+#endif
+constexpr int kCW = B200_STRIP_CONSUMERS;                     // consumer warps (<= 32: their marks are read by one warp)
+#ifndef B200_STRIP_PRODUCERS
+#define B200_STRIP_PRODUCERS 4
+#endif
+constexpr int kPW = B200_STRIP_PRODUCERS;                     // producer warps (stream row i is staged by warp i % kPW)
+constexpr int kThreads = 32 * (kCW + kPW);
 constexpr int kFragBins = 8;                                  // bins per fragment (two passes of 4)
 constexpr int kCell = 144;                                    // bytes per staged cell: 32 channels + 16 B pad
-constexpr int kDepth = 6;                                     // rows the producer keeps in flight
+#ifndef B200_STRIP_DEPTH
+#define B200_STRIP_DEPTH 2
+#endif
+constexpr int kDepth = B200_STRIP_DEPTH;                      // rows every producer warp keeps in flight
 constexpr int kMaxLevels = 6;
 constexpr int kMaxCols = 96;
 constexpr int kAxisMaxS = 32;
@@ -370,6 +381,26 @@ strip_prep(const float* __restrict__ rois, StripGeom g, StripWs ws, float* __res
 // ------------------------------------------------------------------------------------------------
 __device__ u64* g_strip_dead = nullptr;                       // optional host-pinned watchdog records ([CTA][32] u64)
 
+// Timing build (-DB200_STRIP_TIMING, tools/strip_timing.py): every warp leaves [start ns, first work ns, end ns, wait cycles,
+// work items, busy cycles] in a DEVICE buffer registered with b200_roi_ops_debug_timing_buffer ([CTA][warp][8] u64).
+#ifdef B200_STRIP_TIMING
+__device__ u64* g_strip_tim = nullptr;
+__device__ __forceinline__ u64 gtime_ns() { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TIM_DECL u64 tim_start = gtime_ns(), tim_first = 0, tim_wait = 0, tim_n = 0, tim_busy = 0, tim_c = 0
+#define TIM_DO(stmt) do { stmt; } while (0)
+#define TIM_FLUSH()                                                                                                   \
+    do {                                                                                                              \
+        if (g_strip_tim != nullptr && (threadIdx.x & 31) == 0) {                                                      \
+            u64* tp = g_strip_tim + ((size_t)blockIdx.x * (kCW + kPW) + (threadIdx.x >> 5)) * 8;                       \
+            tp[0] = tim_start; tp[1] = tim_first; tp[2] = gtime_ns(); tp[3] = tim_wait; tp[4] = tim_n; tp[5] = tim_busy; \
+        }                                                                                                             \
+    } while (0)
+#else
+#define TIM_DECL
+#define TIM_DO(stmt) do { } while (0)
+#define TIM_FLUSH() do { } while (0)
+#endif
+
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async4(unsigned dst, const float* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
@@ -385,9 +416,39 @@ __device__ __forceinline__ int lds_acquire(unsigned addr) {
     asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ int4 lds_acquire4(unsigned addr) {
+    int4 v;
+    asm volatile("ld.acquire.cta.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts_release(unsigned addr, int v) {
     asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+// ---- mbarrier + TMA (row staging through the tensor-memory accelerator) ----
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"     // %3: the hardware may park the thread this long (ns)
+        "selp.u32 %0, 1, 0, p;\n"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(10000u) : "memory");
+    return ok != 0;
+}
+// One row of one (image, strip, 32-channel group) as a 4-D box (4 columns, 32 channels, SX / 4 column quads, 1 row) of the
+// x-quad view of the map: lands as [quad][channel][4 floats]; rows / quads / channels beyond the map are zero-filled.
+__device__ __forceinline__ void tma_load_row(unsigned dst, const CUtensorMap* map, unsigned bar, int chan, int xquad, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"((u64)map), "r"(bar), "r"(0), "r"(chan), "r"(xquad), "r"(y) : "memory");
+}
+
 // Low-water marks are published with a plain volatile store: shared-memory instructions of one warp are performed in program
 // order, so the store cannot overtake the (converged, __syncwarp'ed) tap loads that precede it -- a release fence here would
 // also wait for the fragment's global stores (MEMBAR per fragment).
@@ -446,8 +507,13 @@ struct StripArgs {
     const int* row_map;
     int C, G, K, WX, PH, PW, ny, nx, L, Q;
     unsigned magicK;                                          // floor(2^32 / K) + 1: i / K == umulhi(i, magicK) for i < 2^32 / K
+    int tma;                                                  // rows are staged by TMA + transposer warps (else: cp.async producers)
     StripLevel lv[kMaxLevels];
     int colstart[kMaxCols + 1];
+};
+
+struct alignas(64) StripMaps {
+    CUtensorMap m[kMaxLevels];                                // x-quad view of every level's feature map (TMA mode)
 };
 
 struct Item {
@@ -487,27 +553,31 @@ __device__ __forceinline__ Item decode_item(int L, int L1, const StripArgs& a, i
     return it;
 }
 
-// Stage row y of one (image, strip, channel group) into a ring slot.  lane = (xi = lane / 4: column within an octet,
-// ci = lane % 4: channel within a quad).  src: (channel c0 + ci, row y, column x0 + xi); dst: slot + xi * kCell + ci * 4.
+// Stage row y of one (image, strip, channel group) into a ring slot.  lane = column within a 32-column chunk: every request
+// reads 128 contiguous bytes of one channel row (one or two cache lines -- the L1 tracks outstanding misses per line, so a
+// request that gathered four channels x 32 bytes kept four times fewer bytes in flight: measured r04a); the transposing
+// write of each returning 32-byte sector hits 8 distinct banks (bank = 4 x + c with the 36-word cell pitch).
+// src: (channel c0, row y, column x0 + lane); dst: slot + lane * kCell.
 template <int XO>
-__device__ __forceinline__ void stage_row(const float* __restrict__ src, size_t plane4, unsigned dst, bool interior, bool row_ok,
-                                          int xw, int cvalid, int xi, int ci) {
+__device__ __forceinline__ void stage_row(const float* __restrict__ src, size_t plane, unsigned dst, bool interior, bool row_ok,
+                                          int xw, int cvalid, int lane) {
+    constexpr int M = XO / 4;                                  // 32-column chunks
     if (interior) {
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) {
 #pragma unroll
-        for (int cq = 0; cq < 8; ++cq) {
-            const float* p = src + (size_t)cq * plane4;
-#pragma unroll
-            for (int xo = 0; xo < XO; ++xo) cp_async4(dst + (unsigned)(xo * 8 * kCell + cq * 16), p + 8 * xo);
+            for (int m = 0; m < M; ++m) cp_async4(dst + (unsigned)(m * 32 * kCell + c * 4), src + 32 * m);
+            src += plane;
         }
     } else {
-#pragma unroll 2
-        for (int cq = 0; cq < 8; ++cq) {
-            const bool cok = row_ok && (4 * cq + ci) < cvalid;
-            const float* p = src + (size_t)(cok ? cq : 0) * plane4;
+#pragma unroll 4
+        for (int c = 0; c < 32; ++c) {
+            const bool cok = row_ok && c < cvalid;
+            const float* p = src + (size_t)(cok ? c : 0) * plane;
 #pragma unroll
-            for (int xo = 0; xo < XO; ++xo) {
-                const bool ok = cok && (8 * xo + xi) < xw;
-                cp_async4_if(dst + (unsigned)(xo * 8 * kCell + cq * 16), ok ? p + 8 * xo : src, ok);
+            for (int m = 0; m < M; ++m) {
+                const bool ok = cok && (32 * m + lane) < xw;
+                cp_async4_if(dst + (unsigned)(m * 32 * kCell + c * 4), ok ? p + 32 * m : src, ok);
             }
         }
     }
@@ -521,26 +591,142 @@ struct FragTab {
 
 template <int SR, int XO>
 __global__ void __launch_bounds__(kThreads, 1)
-roi_align_strip_fwd(const StripArgs a) {
+roi_align_strip_fwd(const __grid_constant__ StripMaps maps, const StripArgs a) {
     constexpr int SX = 8 * XO;
     constexpr int RB = SX * kCell;                                // bytes of one ring slot
     extern __shared__ unsigned char smem_raw[];
     const unsigned ring = (smem_addr(smem_raw) + 127u) & ~127u;
     // ring: K logical slots + a mirror of slot 0 behind slot K - 1 (row y + 1 is always the next physical slot)
-    const unsigned ctl = ring + (unsigned)(a.K + 1) * (unsigned)RB;      // pub[16] (consumer low-water marks), ready
-    const unsigned pub = ctl, ready_addr = ctl + 64u;
+    // control words: pub[32] (consumer low-water marks); next[kPW] (per producer: stream index of its first row not yet landed)
+    const unsigned ctl = ring + (unsigned)(a.K + 1) * (unsigned)RB;
+    const unsigned pub = ctl, next_addr = ctl + 128u, full_bar = ctl + 256u;       // full_bar[K]: TMA completion per slot
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (a.tma && tid == 0) {
+        for (int k = 0; k < a.K; ++k) mbar_init(full_bar + 8u * k, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (tid < kCW) sts_release(pub + 4u * tid, 0);
-    if (tid == kCW) sts_release(ready_addr, 0);
+    if (tid >= kCW && tid < kCW + 4) {                         // next[w]: cp.async mode: producer w; TMA mode: transposer w (warp kCW + 1 + w)
+        const int w = tid - kCW;
+        sts_release(next_addr + 4u * w, w < (a.tma ? kPW - 1 : kPW) ? w : 0x7fffffff);
+    }
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");             // the prepass's results are visible from here on
-    const int L0 = __ldg(&a.piece_start[blockIdx.x]), L1 = __ldg(&a.piece_start[blockIdx.x + 1]);
+    // NOT __ldg: a read-only (.nc) load carries no dependence on the wait above and was hoisted to the top of the kernel,
+    // where the prepass had not written the piece table yet (r04a: stale / garbage piece bounds on a fresh workspace)
+    int L0, L1;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(L0) : "l"(a.piece_start + blockIdx.x) : "memory");
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(L1) : "l"(a.piece_start + blockIdx.x + 1) : "memory");
+    TIM_DECL;
 
-    if (warp == kCW) {
-        // =============================== producer ===============================
-        const int xi = lane >> 2, ci = lane & 3;
-        int i = 0, slot = 0;                                   // stream row index, its slot (i % K)
-        int published = 0;                                     // value of `ready`
+    if (warp >= kCW && a.tma) {
+        // =============================== TMA issuer + transposers ===============================
+        // Warp kCW issues ONE cp.async.bulk.tensor per row (lane 0) as soon as the slot is free -- the whole free part of the
+        // ring is in flight, at no LSU cost.  The box lands as [column quad][channel][4 columns] in the slot's own memory;
+        // transposer warp t (rows i % T == t) waits for the slot's mbarrier, pulls the row through its registers (LDS.128,
+        // lane = channel: 512 contiguous bytes per request) and rewrites it IN PLACE as [column][channel] with the 36-word
+        // cell pitch (STS.32, lane = channel: 128 contiguous bytes), highest columns first -- a cell's new place (144 x) is
+        // never below the not yet read part of the row (< 128 x) -- then publishes next[t] like a cp.async producer.
+        constexpr int T = kPW - 1;
+        constexpr unsigned kRowBytes = (unsigned)SX * 128u;
+        const int role = warp - kCW;                           // 0: issuer, 1 .. T: transposers
+        int i = 0, slot = 0, turn = 0;
+        int low = 0;                                           // issuer: last observed min(consumer marks, transposer marks)
+        unsigned use_parity = 0;                               // parity of the current use of `slot` = (i / K) & 1
+        for (int L = L0; L < L1;) {
+            const Item it = decode_item(L, L1, a, lane);
+            L += it.yb - it.ya;
+            if (it.e1 <= it.e0) continue;
+            const int chan = it.n * a.C + it.g * 32;
+            const int xquad = (it.s * a.WX) >> 2;
+            for (int y = it.ya; y < it.yhi; ++y) {
+                if (role == 0) {
+                    if (i >= a.K && low <= i - a.K) {              // row i - K must be transposed AND done with by every consumer
+                        unsigned spins = 0;
+                        TIM_DO(tim_c = clock64());
+                        for (;;) {
+                            int v = 0x7fffffff;
+                            if (lane < kCW) v = lds_acquire(pub + 4u * lane);
+                            else if (lane < kCW + T && lane < 32) v = lds_acquire(next_addr + 4u * (lane - kCW));
+                            low = __reduce_min_sync(0xffffffffu, v);
+                            if (low > i - a.K) break;
+                            __nanosleep(100);
+                            if (++spins == (1u << 21)) watchdog_note(3u, ((u64)(unsigned)i << 20) | (u64)(unsigned)low);
+                            if (spins > (1u << 22)) __trap();
+                        }
+                        TIM_DO(tim_wait += clock64() - tim_c);
+                    }
+                    TIM_DO(if (!tim_first) tim_first = gtime_ns(); ++tim_n);
+                    if (lane == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy accesses of the slot are done
+                        const unsigned bar = full_bar + 8u * slot;
+                        mbar_expect_tx(bar, kRowBytes);
+                        tma_load_row(ring + (unsigned)slot * (unsigned)RB, &maps.m[it.lvl], bar, chan, xquad, y);
+                    }
+                } else if (turn == role - 1) {
+                    const unsigned bar = full_bar + 8u * slot;
+                    TIM_DO(tim_c = clock64());
+                    if (!mbar_try_wait(bar, use_parity)) {
+                        unsigned spins = 0;
+                        while (!mbar_try_wait(bar, use_parity)) {
+                            if (++spins == (1u << 19)) watchdog_note(4u, ((u64)(unsigned)i << 20) | (u64)slot);
+                            if (spins > (1u << 20)) __trap();
+                        }
+                    }
+                    TIM_DO(tim_wait += clock64() - tim_c; if (!tim_first) tim_first = gtime_ns(); ++tim_n; tim_c = clock64());
+                    const unsigned sbase = ring + (unsigned)slot * (unsigned)RB;
+                    const unsigned rd = sbase + (unsigned)lane * 16u, wr = sbase + (unsigned)lane * 4u;
+                    const unsigned wr2 = ring + (unsigned)a.K * (unsigned)RB + (unsigned)lane * 4u;      // mirror of slot 0
+#pragma unroll
+                    for (int q0 = SX / 4 - 8; q0 >= 0; q0 -= 8) {                // 8 column quads (32 columns) per batch, highest first
+                        uint4 v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "r"(rd + (unsigned)((q0 + j) * 512)));
+                        __syncwarp();                                              // every lane has read the batch before any lane overwrites it
+#pragma unroll
+                        for (int j = 7; j >= 0; --j) {
+                            const unsigned o = (unsigned)((q0 + j) * 4 * kCell);
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr + o), "r"(v[j].x) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr + o + kCell), "r"(v[j].y) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr + o + 2 * kCell), "r"(v[j].z) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr + o + 3 * kCell), "r"(v[j].w) : "memory");
+                            if (slot == 0) {
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr2 + o), "r"(v[j].x) : "memory");
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr2 + o + kCell), "r"(v[j].y) : "memory");
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr2 + o + 2 * kCell), "r"(v[j].z) : "memory");
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr2 + o + 3 * kCell), "r"(v[j].w) : "memory");
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) sts_release(next_addr + 4u * (role - 1), i + T);
+                    TIM_DO(tim_busy += clock64() - tim_c);
+                }
+                ++i;
+                if (++slot == a.K) { slot = 0; use_parity ^= 1u; }
+                if (++turn == T) turn = 0;
+            }
+        }
+        if (role > 0) {
+            __syncwarp();
+            if (lane == 0) sts_release(next_addr + 4u * (role - 1), 0x7fffffff);
+        }
+        TIM_FLUSH();
+        return;
+    }
+    if (warp >= kCW) {
+        // =============================== producers (cp.async mode) ===============================
+        // Stream row i (all items of the piece, in order) is staged by producer warp i % kPW.  A warp's rows land in order
+        // (cp.async groups of one thread), so it publishes next = the stream index of its first row that has not landed;
+        // rows [0, min over the producers of next) are resident.
+        const int pw = warp - kCW;
+        const unsigned my_next = next_addr + 4u * pw;
+        int i = 0, slot = 0, turn = 0;                         // stream row index, its slot (i % K), i % kPW
+        int committed = 0, landed = 0;                         // this warp's rows: staged / known to have landed
         int minpub = 0;                                        // last observed minimum of the consumers' marks
         for (int L = L0; L < L1;) {
             const Item it = decode_item(L, L1, a, lane);
@@ -553,46 +739,55 @@ roi_align_strip_fwd(const StripArgs a) {
             const int cvalid = min(32, a.C - c0);
             const int xw = lv.W - x0;
             const bool full = cvalid == 32 && xw >= SX;
-            const float* src = lv.bottom + ((size_t)it.n * a.C + c0 + (ci < cvalid ? ci : 0)) * plane + (size_t)it.ya * lv.W + x0 + (xi < xw ? xi : 0);
+            const float* src = lv.bottom + ((size_t)it.n * a.C + c0) * plane + (size_t)it.ya * lv.W + x0 + (lane < xw ? lane : 0);
             for (int y = it.ya; y < it.yhi; ++y) {
-                if (i >= a.K && minpub <= i - a.K) {
-                    // the slot still holds row i - K: everything committed so far must be visible before this warp blocks
-                    cp_async_wait<0>();
-                    __threadfence_block();
-                    __syncwarp();
-                    if (published < i) { published = i; if (lane == 0) sts_release(ready_addr, i); }
-                    unsigned spins = 0;
-                    for (;;) {
-                        const int v = lane < kCW ? lds_acquire(pub + 4u * lane) : 0x7fffffff;
-                        minpub = __reduce_min_sync(0xffffffffu, v);
-                        if (minpub > i - a.K) break;
-                        __nanosleep(40);
-                        if (++spins == (1u << 22)) watchdog_note(1u, ((u64)(unsigned)i << 20) | (u64)(unsigned)minpub);
-                        if (spins > (1u << 23)) __trap();
+                if (turn == pw) {
+                    if (i >= a.K && minpub <= i - a.K) {
+                        // the slot still holds row i - K: everything this warp committed must be visible before it blocks
+                        cp_async_wait<0>();
+                        __threadfence_block();
+                        __syncwarp();
+                        if (landed < committed) { landed = committed; if (lane == 0) sts_release(my_next, pw + landed * kPW); }
+                        unsigned spins = 0;
+                        TIM_DO(tim_c = clock64());
+                        for (;;) {
+                            const int v = lane < kCW ? lds_acquire(pub + 4u * lane) : 0x7fffffff;
+                            minpub = __reduce_min_sync(0xffffffffu, v);
+                            if (minpub > i - a.K) break;
+                            __nanosleep(100);
+                            if (++spins == (1u << 21)) watchdog_note(1u, ((u64)(unsigned)i << 20) | (u64)(unsigned)minpub);
+                            if (spins > (1u << 22)) __trap();
+                        }
+                        TIM_DO(tim_wait += clock64() - tim_c);
                     }
+                    TIM_DO(if (!tim_first) tim_first = gtime_ns(); ++tim_n; tim_c = clock64());
+                    const bool row_ok = y < lv.H;
+                    const float* srow = src + (size_t)(row_ok ? y - it.ya : 0) * lv.W;
+                    const unsigned dst = ring + (unsigned)slot * (unsigned)RB + (unsigned)(lane * kCell);
+                    stage_row<XO>(srow, plane, dst, full && row_ok, row_ok, xw, cvalid, lane);
+                    if (slot == 0)
+                        stage_row<XO>(srow, plane, ring + (unsigned)a.K * (unsigned)RB + (unsigned)(lane * kCell), full && row_ok, row_ok, xw, cvalid, lane);
+                    cp_async_commit();
+                    ++committed;
+                    if (committed - landed > kDepth) {             // all but this warp's kDepth newest rows have landed
+                        cp_async_wait<kDepth>();
+                        __threadfence_block();
+                        __syncwarp();
+                        landed = committed - kDepth;
+                        if (lane == 0) sts_release(my_next, pw + landed * kPW);
+                    }
+                    TIM_DO(tim_busy += clock64() - tim_c);
                 }
-                const bool row_ok = y < lv.H;
-                const unsigned dst = ring + (unsigned)slot * (unsigned)RB + (unsigned)(xi * kCell + ci * 4);
-                stage_row<XO>(src, 4 * plane, dst, full && row_ok, row_ok, xw, cvalid, xi, ci);
-                if (slot == 0)
-                    stage_row<XO>(src, 4 * plane, ring + (unsigned)a.K * (unsigned)RB + (unsigned)(xi * kCell + ci * 4), full && row_ok, row_ok, xw, cvalid, xi, ci);
-                cp_async_commit();
                 ++i;
                 if (++slot == a.K) slot = 0;
-                if (row_ok && y + 1 < lv.H) src += lv.W;       // never step past the map
-                if (i - published > kDepth) {                  // rows [0, i - kDepth) have landed
-                    cp_async_wait<kDepth>();
-                    __threadfence_block();
-                    __syncwarp();
-                    published = i - kDepth;
-                    if (lane == 0) sts_release(ready_addr, published);
-                }
+                if (++turn == kPW) turn = 0;
             }
         }
         cp_async_wait<0>();
         __threadfence_block();
         __syncwarp();
-        if (lane == 0) sts_release(ready_addr, i);
+        if (lane == 0) sts_release(my_next, 0x7fffffff);
+        TIM_FLUSH();
         return;
     }
 
@@ -602,7 +797,7 @@ roi_align_strip_fwd(const StripArgs a) {
     constexpr float kInvCount = 1.f / (float)(SR * SR);
     const u64 inv2 = pack2f(kInvCount, kInvCount);
     const u64 zero2 = pack2f(0.f, 0.f);
-    int ready_c = 0;                                           // cached value of `ready`
+    int ready_c = 0;                                           // cached: rows [0, ready_c) of the stream are resident
     int ibase = 0;                                             // stream index of the current item's first row
 
     auto load_tab = [&](const uint2& en) -> FragTab<SR> {
@@ -652,14 +847,18 @@ roi_align_strip_fwd(const StripArgs a) {
             const int i_last = irel + end - 1;
             if (i_last >= ready_c) {
                 unsigned spins = 0;
+                TIM_DO(tim_c = clock64());
                 for (;;) {
-                    ready_c = lds_acquire(ready_addr);
+                    const int4 nx4 = lds_acquire4(next_addr);
+                    ready_c = min(min(nx4.x, nx4.y), min(nx4.z, nx4.w));
                     if (ready_c > i_last) break;
-                    __nanosleep(20);
-                    if (++spins == (1u << 22)) watchdog_note(2u, ((u64)(unsigned)i_last << 20) | (u64)(unsigned)ready_c);
-                    if (spins > (1u << 23)) __trap();
+                    __nanosleep(200);                          // a starved consumer must not crowd the producers' LDGSTS out of the MIO queue
+                    if (++spins == (1u << 20)) watchdog_note(2u, ((u64)(unsigned)i_last << 20) | (u64)(unsigned)ready_c);
+                    if (spins > (1u << 21)) __trap();
                 }
+                TIM_DO(tim_wait += clock64() - tim_c);
             }
+            TIM_DO(if (!tim_first) tim_first = gtime_ns(); ++tim_n; tim_c = clock64());
             // row bases (uniform): slot of y_low; the lower tap row is the next physical slot
             unsigned rt[SR];
             u64 hh[SR], ll[SR];
@@ -723,12 +922,14 @@ roi_align_strip_fwd(const StripArgs a) {
                     }
                 }
             }
+            TIM_DO(tim_busy += clock64() - tim_c);
             e = e_next;
         }
         ibase += it.yhi - it.ya;
     }
     __syncwarp();
     if (lane == 0) sts_volatile(pub + 4u * warp, 0x7fffffff);       // nothing more to read
+    TIM_FLUSH();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -749,7 +950,7 @@ bool strip_geometry(int levels, const float* const* bottoms, const int* heights,
     if ((long long)R * PH * PW * sr * sr >= (1LL << 28)) return false;
     for (int l = 0; l < levels; ++l)
         if (heights[l] < 2 || widths[l] < 2 || heights[l] > 65000) return false;
-    const unsigned fixed = 128 + 128;                          // control words + alignment slack
+    const unsigned fixed = 128 + 256 + 8 * kMaxK;              // alignment slack + control words (pub[32], next[4]) + TMA barriers
     int best_sx = 0, best_wx = 0, best_k = 0;
     long best_score = -1;
     static const int kSx[3] = {32, 64, 96}, kHalo[3] = {8, 8, 16};
@@ -811,6 +1012,36 @@ bool strip_geometry(int levels, const float* const* bottoms, const int* heights,
     return true;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// x-quad view of one NCHW level: dims (x % 4, n * C + c, x / 4, y), box (4, 32, SX / 4, 1).  Needs W % 4 == 0 and a 16-byte
+// aligned base; the innermost start coordinate is always 0, so no tile load is ever misaligned (tools/tma_probe4.cu).
+bool make_quad_map(CUtensorMap* map, const float* bottom, int N, int C, int H, int W, int SX) {
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode || (W & 3) || ((uintptr_t)bottom & 15u) || kPW < 2) return false;
+    const cuuint64_t dims[4] = {4, (cuuint64_t)N * (cuuint64_t)C, (cuuint64_t)(W / 4), (cuuint64_t)H};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * (cuuint64_t)H * 4, 16, (cuuint64_t)W * 4};
+    const cuuint32_t box[4] = {4, 32, (cuuint32_t)(SX / 4), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)bottom, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct StripDevice {
     bool ok = false;
     int sm_count = 0;
@@ -847,7 +1078,11 @@ bool strip_device_info(StripDevice* out) {
 }  // namespace
 
 void roi_align_strip_set_debug_buffer(unsigned long long* host_pinned) {
+#ifdef B200_STRIP_TIMING
+    cudaMemcpyToSymbol(g_strip_tim, &host_pinned, sizeof(host_pinned));       // device buffer [CTA][warp][8] u64
+#else
     cudaMemcpyToSymbol(g_strip_dead, &host_pinned, sizeof(host_pinned));      // [CTA][32] u64 watchdog records
+#endif
 }
 
 size_t roi_align_strip_fpn_workspace_bytes(int levels, const int* heights, const int* widths, int N, int R, int PH, int PW, int sr) {
@@ -908,6 +1143,11 @@ int roi_align_forward_strip_fpn(int levels, const float* const* bottoms, const i
     a.piece_start = ws.piece_start; a.out = top; a.row_map = row_map;
     a.C = C; a.G = g.G; a.K = g.K; a.WX = g.WX; a.PH = PH; a.PW = PW; a.ny = g.ny; a.nx = g.nx; a.L = g.L; a.Q = g.Q;
     a.magicK = 0xffffffffu / (unsigned)g.K + 1u;
+    StripMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    bool tma = option_get(kOptStreamStage) != 'a';              // B200_STREAM_STAGE=async: cp.async producers (A/B, and the fallback)
+    for (int l = 0; tma && l < levels; ++l) tma = make_quad_map(&maps.m[l], bottoms[l], N, C, heights[l], widths[l], g.SX);
+    a.tma = tma ? 1 : 0;
     for (int l = 0; l < kMaxLevels; ++l) a.lv[l] = g.lv[l];
     for (int c = 0; c <= kMaxCols; ++c) a.colstart[c] = g.colstart[c];
 
@@ -923,7 +1163,7 @@ int roi_align_forward_strip_fpn(int levels, const float* const* bottoms, const i
     cfg.attrs = attr;
     cfg.numAttrs = option_get(kOptStripPdl) == '0' ? 0 : 1;                    // B200_STRIP_PDL=0: plain stream order
     const int xo = g.SX / 8;
-#define B200_STRIP_LAUNCH(SRV, XOV) err = cudaLaunchKernelEx(&cfg, roi_align_strip_fwd<SRV, XOV>, a)
+#define B200_STRIP_LAUNCH(SRV, XOV) err = cudaLaunchKernelEx(&cfg, roi_align_strip_fwd<SRV, XOV>, maps, a)
     if (sr == 1) { if (xo == 4) B200_STRIP_LAUNCH(1, 4); else if (xo == 8) B200_STRIP_LAUNCH(1, 8); else B200_STRIP_LAUNCH(1, 12); }
     else         { if (xo == 4) B200_STRIP_LAUNCH(2, 4); else if (xo == 8) B200_STRIP_LAUNCH(2, 8); else B200_STRIP_LAUNCH(2, 12); }
 #undef B200_STRIP_LAUNCH
