@@ -41,7 +41,7 @@ namespace b200 {
 namespace {
 
 #ifndef B200_STRIP_CONSUMERS
-#define B200_STRIP_CONSUMERS 16
+#define B200_STRIP_CONSUMERS 12
 #endif
 constexpr int kCW = B200_STRIP_CONSUMERS;                     // consumer warps (<= 32: their marks are read by one warp)
 #ifndef B200_STRIP_PRODUCERS
@@ -50,7 +50,9 @@ constexpr int kCW = B200_STRIP_CONSUMERS;                     // consumer warps 
 constexpr int kPW = B200_STRIP_PRODUCERS;                     // producer warps (stream row i is staged by warp i % kPW)
 constexpr int kThreads = 32 * (kCW + kPW);
 constexpr int kFragBins = 8;                                  // bins per fragment (two passes of 4)
-constexpr int kCell = 144;                                    // bytes per staged cell: 32 channels + 16 B pad
+// bytes per staged cell (template parameter CELL of the main kernel): 128 when rows are staged by TMA (the transposer writes
+// 128 aligned bytes per column), 144 = 32 channels + 16 B pad with cp.async producers (bank = 4 x + c for the transposing write)
+constexpr int kCellTma = 128, kCellAsync = 144;
 #ifndef B200_STRIP_DEPTH
 #define B200_STRIP_DEPTH 2
 #endif
@@ -78,8 +80,8 @@ struct StripLevel {
 struct StripGeom {
     int N, R, C, PH, PW, sr;
     int ny, nx;
-    int SX, WX, K;                                            // columns per slot (8 XO), strip core width, ring depth
-    int L, Q, keys, G, pieces, max_entries;
+    int SX, WX, K, cell;                                      // columns per slot (8 XO), strip core width, ring depth, bytes per cell
+    int L, Q, keys, G, pieces, max_entries, cap_r;            // cap_r: fragments one RoI can have at most
     unsigned row_cost;
     StripLevel lv[kMaxLevels];
     int colstart[kMaxCols + 1];
@@ -93,15 +95,16 @@ __host__ __device__ __forceinline__ int level_of_roi(const StripGeom& g, int r) 
 
 struct StripWs {
     uint4* ytab;                // [R][ny] {hy, ly, y_low, 0}
-    uint4* xtab;                // [R][nx] {hx, lx, x_low * kCell, 0}
+    uint4* xtab;                // [R][nx] {hx, lx, x_low * cell, 0}
     int* hist;                  // [keys]  fragments per key          (zero block)
     int* cost;                  // [keys]                             (zero block)
-    int* cursor;                // [keys]                             (zero block)
     int* maxend;                // [keys]                             (zero block)
     int* ticket;                // [4]                                (zero block)
     int* rowptr;                // [keys + 1]
     int* piece_start;           // [pieces + 1]
     uint2* entries;
+    uint4* tmp;                 // [R][cap_r] {key index, rank within the key, record}: phase 1 -> phase 3 of the prepass
+    int* tmpcnt;                // [R] fragments of the RoI (-1: batch index out of range)
 };
 
 // fragment record: x = r | ph << 16 | pw0 << 21 | (npw - 1) << 26 | red << 29 ; y = key | (end - key) << 16 | smask << 24
@@ -189,7 +192,8 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 template <int SR>
 __global__ void __launch_bounds__(kPrepThreads)
 strip_prep(const float* __restrict__ rois, StripGeom g, StripWs ws, float* __restrict__ out, const int* __restrict__ row_map) {
-    extern __shared__ unsigned s_dyn[];                       // [keys + 1] fragment prefix, [keys + 1] cost prefix
+    extern __shared__ unsigned s_dyn[];                       // [keys + 1] fragment prefix, [keys + 1] cost prefix, [cap_r][3] fragment list
+    __shared__ int s_nlist;
     __shared__ int s_yl[kAxisMaxS], s_xl[kAxisMaxS];
     __shared__ unsigned short s_zero[kAxisMaxS * kAxisMaxS];
     __shared__ int s_nzero;
@@ -198,6 +202,7 @@ strip_prep(const float* __restrict__ rois, StripGeom g, StripWs ws, float* __res
     const int keys = g.keys;
     unsigned* s_pre = s_dyn;
     unsigned* s_cpre = s_dyn + (keys + 1);
+    unsigned* s_list = s_dyn + 2 * (keys + 1);               // {key index, record.x, record.y} per fragment of the current RoI
 
     auto axes = [&](int r, bool write_tables) -> XfromRoi {   // per-RoI axis tables (all IEEE divisions live here)
         const StripLevel& lv = g.lv[level_of_roi(g, r)];
@@ -220,7 +225,7 @@ strip_prep(const float* __restrict__ rois, StripGeom g, StripWs ws, float* __res
                 if (write_tables) {
                     uint4 e;
                     e.x = __float_as_uint(a.h); e.y = __float_as_uint(a.l);
-                    e.z = (unsigned)(a.low * kCell); e.w = 0u;
+                    e.z = (unsigned)(a.low * g.cell); e.w = 0u;
                     ws.xtab[(size_t)r * g.nx + s] = e;
                 }
             }
@@ -228,22 +233,36 @@ strip_prep(const float* __restrict__ rois, StripGeom g, StripWs ws, float* __res
         return geo;
     };
 
-    // ---- phase 1: tables, histogram
+    // ---- phase 1: tables; the RoI's fragments are listed in shared memory by the bin-row threads, then ALL threads take one
+    // fragment each: rank within its key (the returning atomic's latency is paid once and hides behind the grid barrier),
+    // cost / extent atomics, and a temporary record that phase 3 only has to drop into the CSR
     for (int r = blockIdx.x; r < g.R; r += gridDim.x) {
-        __syncthreads();                                      // s_yl / s_xl of the previous RoI are no longer read
+        __syncthreads();                                      // s_yl / s_xl / s_list of the previous RoI are no longer read
         const XfromRoi geo = axes(r, true);
+        if (t == 0) s_nlist = 0;
         __syncthreads();
         const StripLevel& lv = g.lv[level_of_roi(g, r)];
-        if (geo.batch >= 0 && geo.batch < g.N && t < g.PH) {
+        const bool batch_ok = geo.batch >= 0 && geo.batch < g.N;
+        if (batch_ok && t < g.PH) {
             const int cbase = lv.q_base + geo.batch * lv.S;
             enum_row<SR>(s_yl, s_xl, t, g, lv.S, [&](int s, int key, int end, int pw0, int npw, unsigned smask, int red, bool owner) {
-                const int k = g.colstart[cbase + s] + key;
-                atomicAdd(&ws.hist[k], 1);
-                atomicAdd(&ws.cost[k], (int)(kFragCost + kPassCost * (unsigned)((npw + 3) >> 2)));
-                atomicMax(&ws.maxend[k], end);
-                (void)pw0; (void)smask; (void)red; (void)owner;
+                const int idx = atomicAdd(&s_nlist, 1);
+                const uint2 e = pack_entry(r, t, pw0, npw, red, key, end, smask);
+                s_list[3 * idx] = (unsigned)(g.colstart[cbase + s] + key); s_list[3 * idx + 1] = e.x; s_list[3 * idx + 2] = e.y;
+                (void)owner;
             });
         }
+        __syncthreads();
+        const int n = s_nlist;
+        for (int idx = t; idx < n; idx += kPrepThreads) {
+            const unsigned k = s_list[3 * idx], ex = s_list[3 * idx + 1], ey = s_list[3 * idx + 2];
+            const int npw = (int)((ex >> 26) & 7u) + 1, end = (int)(ey & 0xffffu) + (int)((ey >> 16) & 0xffu);
+            const int rank = atomicAdd(&ws.hist[k], 1);
+            atomicAdd(&ws.cost[k], (int)(kFragCost + kPassCost * (unsigned)((npw + 3) >> 2)));
+            atomicMax(&ws.maxend[k], end);
+            ws.tmp[(size_t)r * g.cap_r + idx] = make_uint4(k, (unsigned)rank, ex, ey);
+        }
+        if (t == 0) ws.tmpcnt[r] = batch_ok ? n : -1;
     }
     // ---- grid barrier (the grid is sized to be resident: see the launcher)
     __syncthreads();
@@ -332,33 +351,25 @@ strip_prep(const float* __restrict__ rois, StripGeom g, StripWs ws, float* __res
             ws.piece_start[p] = L;
         }
     }
-    // ---- phase 3: fragment records into the CSR; zero-fill of the elements that are accumulated with red.add
+    // ---- phase 3: fragment records into the CSR (position = row pointer + rank); zero-fill of the elements that are
+    // accumulated with red.add (the bins of the fragments that hold a split bin's first sample)
     const int bins = g.PH * g.PW;
-    const bool single = (int)gridDim.x >= g.R;                // one RoI per CTA: its s_yl / s_xl are still valid
     for (int r = blockIdx.x; r < g.R; r += gridDim.x) {
-        XfromRoi geo;
-        if (single) {
-            geo = xfrom_roi(rois + 5 * (size_t)r, g.lv[level_of_roi(g, r)].scale, g.PH, g.PW, g.sr);
-        } else {
-            __syncthreads();
-            geo = axes(r, false);
-        }
+        __syncthreads();
         if (t == 0) s_nzero = 0;
         __syncthreads();
-        const StripLevel& lv = g.lv[level_of_roi(g, r)];
-        const bool batch_ok = geo.batch >= 0 && geo.batch < g.N;
-        if (batch_ok) {
-            if (t < g.PH) {
-                const int cbase = lv.q_base + geo.batch * lv.S;
-                enum_row<SR>(s_yl, s_xl, t, g, lv.S, [&](int s, int key, int end, int pw0, int npw, unsigned smask, int red, bool owner) {
-                    const int k = g.colstart[cbase + s] + key;
-                    const int pos = (int)s_pre[k] + atomicAdd(&ws.cursor[k], 1);
-                    if (pos < g.max_entries) ws.entries[pos] = pack_entry(r, t, pw0, npw, red, key, end, smask);
-                    if (owner) {
-                        const int z = atomicAdd(&s_nzero, npw);
-                        for (int i = 0; i < npw; ++i) s_zero[z + i] = (unsigned short)(t * g.PW + pw0 + i);
-                    }
-                });
+        const int n = __ldcg(&ws.tmpcnt[r]);
+        if (n >= 0) {
+            for (int idx = t; idx < n; idx += kPrepThreads) {
+                const uint4 rec = __ldcg(&ws.tmp[(size_t)r * g.cap_r + idx]);
+                const int pos = (int)s_pre[rec.x] + (int)rec.y;
+                if (pos < g.max_entries) ws.entries[pos] = make_uint2(rec.z, rec.w);
+                const bool owner = ((rec.z >> 29) & 1u) && ((rec.w >> 24) & 1u);
+                if (owner) {
+                    const int ph = (rec.z >> 16) & 31u, pw0 = (rec.z >> 21) & 31u, npw = (int)((rec.z >> 26) & 7u) + 1;
+                    const int z = atomicAdd(&s_nzero, npw);
+                    for (int i = 0; i < npw; ++i) s_zero[z + i] = (unsigned short)(ph * g.PW + pw0 + i);
+                }
             }
         } else {
             for (int i = t; i < bins; i += kPrepThreads) s_zero[i] = (unsigned short)i;       // the reference would read out of bounds
@@ -478,19 +489,19 @@ __device__ __forceinline__ Quad lds_quad(unsigned at) {
 }
 
 // The four taps of one sample for this lane's four channels: rows (slot, next slot) x cells (x_low, x_low + 1).
-template <int RB>
+template <int RB, int CELL>
 struct Taps4 {
     Quad v1, v2, v3, v4;
     __device__ __forceinline__ void load(unsigned at) {
-        v1 = lds_quad<0>(at); v2 = lds_quad<kCell>(at); v3 = lds_quad<RB>(at); v4 = lds_quad<RB + kCell>(at);
+        v1 = lds_quad<0>(at); v2 = lds_quad<CELL>(at); v3 = lds_quad<RB>(at); v4 = lds_quad<RB + CELL>(at);
     }
 };
 
 // One bilinear sample, the reference's rounding recipe per channel:
 // val = FFMA(v4, w4, FFMA(v3, w3, FFMA(v1, w1, FMUL(v2, w2)))), w1 = hy*hx, w2 = hy*lx, w3 = ly*hx, w4 = ly*lx;
 // then acc = FADD(acc, val).  hh / ll: (hy, hy) / (ly, ly); xh / xl: (hx, hx) / (lx, lx).
-template <int RB>
-__device__ __forceinline__ void sample_acc(const Taps4<RB>& t, u64 hh, u64 ll, u64 xh, u64 xl, u64& acc_lo, u64& acc_hi) {
+template <int RB, int CELL>
+__device__ __forceinline__ void sample_acc(const Taps4<RB, CELL>& t, u64 hh, u64 ll, u64 xh, u64 xl, u64& acc_lo, u64& acc_hi) {
     const u64 w1 = mul2(hh, xh), w2 = mul2(hh, xl), w3 = mul2(ll, xh), w4 = mul2(ll, xl);
     acc_lo = add2(acc_lo, fma2(t.v4.lo, w4, fma2(t.v3.lo, w3, fma2(t.v1.lo, w1, mul2(t.v2.lo, w2)))));
     acc_hi = add2(acc_hi, fma2(t.v4.hi, w4, fma2(t.v3.hi, w3, fma2(t.v1.hi, w1, mul2(t.v2.hi, w2)))));
@@ -557,8 +568,8 @@ __device__ __forceinline__ Item decode_item(int L, int L1, const StripArgs& a, i
 // reads 128 contiguous bytes of one channel row (one or two cache lines -- the L1 tracks outstanding misses per line, so a
 // request that gathered four channels x 32 bytes kept four times fewer bytes in flight: measured r04a); the transposing
 // write of each returning 32-byte sector hits 8 distinct banks (bank = 4 x + c with the 36-word cell pitch).
-// src: (channel c0, row y, column x0 + lane); dst: slot + lane * kCell.
-template <int XO>
+// src: (channel c0, row y, column x0 + lane); dst: slot + lane * CELL.
+template <int XO, int CELL>
 __device__ __forceinline__ void stage_row(const float* __restrict__ src, size_t plane, unsigned dst, bool interior, bool row_ok,
                                           int xw, int cvalid, int lane) {
     constexpr int M = XO / 4;                                  // 32-column chunks
@@ -566,7 +577,7 @@ __device__ __forceinline__ void stage_row(const float* __restrict__ src, size_t 
 #pragma unroll 8
         for (int c = 0; c < 32; ++c) {
 #pragma unroll
-            for (int m = 0; m < M; ++m) cp_async4(dst + (unsigned)(m * 32 * kCell + c * 4), src + 32 * m);
+            for (int m = 0; m < M; ++m) cp_async4(dst + (unsigned)(m * 32 * CELL + c * 4), src + 32 * m);
             src += plane;
         }
     } else {
@@ -577,7 +588,7 @@ __device__ __forceinline__ void stage_row(const float* __restrict__ src, size_t 
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 const bool ok = cok && (32 * m + lane) < xw;
-                cp_async4_if(dst + (unsigned)(m * 32 * kCell + c * 4), ok ? p + 32 * m : src, ok);
+                cp_async4_if(dst + (unsigned)(m * 32 * CELL + c * 4), ok ? p + 32 * m : src, ok);
             }
         }
     }
@@ -589,11 +600,11 @@ struct FragTab {
     uint4 y[SR];
 };
 
-template <int SR, int XO>
+template <int SR, int XO, int CELL>
 __global__ void __launch_bounds__(kThreads, 1)
 roi_align_strip_fwd(const __grid_constant__ StripMaps maps, const StripArgs a) {
     constexpr int SX = 8 * XO;
-    constexpr int RB = SX * kCell;                                // bytes of one ring slot
+    constexpr int RB = SX * CELL;                                 // bytes of one ring slot
     extern __shared__ unsigned char smem_raw[];
     const unsigned ring = (smem_addr(smem_raw) + 127u) & ~127u;
     // ring: K logical slots + a mirror of slot 0 behind slot K - 1 (row y + 1 is always the next physical slot)
@@ -626,8 +637,8 @@ roi_align_strip_fwd(const __grid_constant__ StripMaps maps, const StripArgs a) {
         // ring is in flight, at no LSU cost.  The box lands as [column quad][channel][4 columns] in the slot's own memory;
         // transposer warp t (rows i % T == t) waits for the slot's mbarrier, pulls the row through its registers (LDS.128,
         // lane = channel: 512 contiguous bytes per request) and rewrites it IN PLACE as [column][channel] with the 36-word
-        // cell pitch (STS.32, lane = channel: 128 contiguous bytes), highest columns first -- a cell's new place (144 x) is
-        // never below the not yet read part of the row (< 128 x) -- then publishes next[t] like a cp.async producer.
+        // cell pitch CELL (STS.32, lane = channel: 128 contiguous bytes), in batches of 32 columns, highest first -- a cell's new
+        // place (CELL x >= 128 x) is never below the not yet read part of the row -- then publishes next[t] like a cp.async producer.
         constexpr int T = kPW - 1;
         constexpr unsigned kRowBytes = (unsigned)SX * 128u;
         const int role = warp - kCW;                           // 0: issuer, 1 .. T: transposers
@@ -687,16 +698,16 @@ roi_align_strip_fwd(const __grid_constant__ StripMaps maps, const StripArgs a) {
                         __syncwarp();                                              // every lane has read the batch before any lane overwrites it
 #pragma unroll
                         for (int j = 7; j >= 0; --j) {
-                            const unsigned o = (unsigned)((q0 + j) * 4 * kCell);
+                            const unsigned o = (unsigned)((q0 + j) * 4 * CELL);
                             asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr + o), "r"(v[j].x) : "memory");
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr + o + kCell), "r"(v[j].y) : "memory");
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr + o + 2 * kCell), "r"(v[j].z) : "memory");
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr + o + 3 * kCell), "r"(v[j].w) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr + o + CELL), "r"(v[j].y) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr + o + 2 * CELL), "r"(v[j].z) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr + o + 3 * CELL), "r"(v[j].w) : "memory");
                             if (slot == 0) {
                                 asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr2 + o), "r"(v[j].x) : "memory");
-                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr2 + o + kCell), "r"(v[j].y) : "memory");
-                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr2 + o + 2 * kCell), "r"(v[j].z) : "memory");
-                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr2 + o + 3 * kCell), "r"(v[j].w) : "memory");
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr2 + o + CELL), "r"(v[j].y) : "memory");
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr2 + o + 2 * CELL), "r"(v[j].z) : "memory");
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wr2 + o + 3 * CELL), "r"(v[j].w) : "memory");
                             }
                         }
                         __syncwarp();
@@ -763,10 +774,10 @@ roi_align_strip_fwd(const __grid_constant__ StripMaps maps, const StripArgs a) {
                     TIM_DO(if (!tim_first) tim_first = gtime_ns(); ++tim_n; tim_c = clock64());
                     const bool row_ok = y < lv.H;
                     const float* srow = src + (size_t)(row_ok ? y - it.ya : 0) * lv.W;
-                    const unsigned dst = ring + (unsigned)slot * (unsigned)RB + (unsigned)(lane * kCell);
-                    stage_row<XO>(srow, plane, dst, full && row_ok, row_ok, xw, cvalid, lane);
+                    const unsigned dst = ring + (unsigned)slot * (unsigned)RB + (unsigned)(lane * CELL);
+                    stage_row<XO, CELL>(srow, plane, dst, full && row_ok, row_ok, xw, cvalid, lane);
                     if (slot == 0)
-                        stage_row<XO>(srow, plane, ring + (unsigned)a.K * (unsigned)RB + (unsigned)(lane * kCell), full && row_ok, row_ok, xw, cvalid, lane);
+                        stage_row<XO, CELL>(srow, plane, ring + (unsigned)a.K * (unsigned)RB + (unsigned)(lane * CELL), full && row_ok, row_ok, xw, cvalid, lane);
                     cp_async_commit();
                     ++committed;
                     if (committed - landed > kDepth) {             // all but this warp's kDepth newest rows have landed
@@ -818,7 +829,7 @@ roi_align_strip_fwd(const __grid_constant__ StripMaps maps, const StripArgs a) {
         const Item it = decode_item(L, L1, a, lane);
         L += it.yb - it.ya;
         if (it.e1 <= it.e0) continue;
-        const unsigned lane_base = ring + (unsigned)(q * 16) - (unsigned)(it.s * a.WX * kCell);
+        const unsigned lane_base = ring + (unsigned)(q * 16) - (unsigned)(it.s * a.WX * CELL);
         const int c0 = it.g * 32;
         const int cq = c0 + 4 * q;                             // this lane's first channel
         const int irel = ibase - it.ya;                        // stream index of row y = irel + y
@@ -885,21 +896,21 @@ roi_align_strip_fwd(const __grid_constant__ StripMaps maps, const StripArgs a) {
                         xo[s] = tb.x[pass][s].z;
                     }
                     if (SR == 1) {
-                        Taps4<RB> t0; t0.load(rt[0] + xo[0]);
-                        sample_acc<RB>(t0, hh[0], ll[0], xh[0], xl[0], acc_lo, acc_hi);
+                        Taps4<RB, CELL> t0; t0.load(rt[0] + xo[0]);
+                        sample_acc<RB, CELL>(t0, hh[0], ll[0], xh[0], xl[0], acc_lo, acc_hi);
                     } else if (smask == 0xfu) {
                         // whole bins (the common case): all 16 taps are requested before the first one is used
-                        Taps4<RB> t0, t1, t2, t3;
+                        Taps4<RB, CELL> t0, t1, t2, t3;
                         t0.load(rt[0] + xo[0]); t1.load(rt[0] + xo[SR - 1]); t2.load(rt[SR - 1] + xo[0]); t3.load(rt[SR - 1] + xo[SR - 1]);
-                        sample_acc<RB>(t0, hh[0], ll[0], xh[0], xl[0], acc_lo, acc_hi);                  // the reference's order: iy outer, ix inner
-                        sample_acc<RB>(t1, hh[0], ll[0], xh[SR - 1], xl[SR - 1], acc_lo, acc_hi);
-                        sample_acc<RB>(t2, hh[SR - 1], ll[SR - 1], xh[0], xl[0], acc_lo, acc_hi);
-                        sample_acc<RB>(t3, hh[SR - 1], ll[SR - 1], xh[SR - 1], xl[SR - 1], acc_lo, acc_hi);
+                        sample_acc<RB, CELL>(t0, hh[0], ll[0], xh[0], xl[0], acc_lo, acc_hi);                  // the reference's order: iy outer, ix inner
+                        sample_acc<RB, CELL>(t1, hh[0], ll[0], xh[SR - 1], xl[SR - 1], acc_lo, acc_hi);
+                        sample_acc<RB, CELL>(t2, hh[SR - 1], ll[SR - 1], xh[0], xl[0], acc_lo, acc_hi);
+                        sample_acc<RB, CELL>(t3, hh[SR - 1], ll[SR - 1], xh[SR - 1], xl[SR - 1], acc_lo, acc_hi);
                     } else {
-                        if (smask & 1u) { Taps4<RB> t; t.load(rt[0] + xo[0]); sample_acc<RB>(t, hh[0], ll[0], xh[0], xl[0], acc_lo, acc_hi); }
-                        if (smask & 2u) { Taps4<RB> t; t.load(rt[0] + xo[SR - 1]); sample_acc<RB>(t, hh[0], ll[0], xh[SR - 1], xl[SR - 1], acc_lo, acc_hi); }
-                        if (smask & 4u) { Taps4<RB> t; t.load(rt[SR - 1] + xo[0]); sample_acc<RB>(t, hh[SR - 1], ll[SR - 1], xh[0], xl[0], acc_lo, acc_hi); }
-                        if (smask & 8u) { Taps4<RB> t; t.load(rt[SR - 1] + xo[SR - 1]); sample_acc<RB>(t, hh[SR - 1], ll[SR - 1], xh[SR - 1], xl[SR - 1], acc_lo, acc_hi); }
+                        if (smask & 1u) { Taps4<RB, CELL> t; t.load(rt[0] + xo[0]); sample_acc<RB, CELL>(t, hh[0], ll[0], xh[0], xl[0], acc_lo, acc_hi); }
+                        if (smask & 2u) { Taps4<RB, CELL> t; t.load(rt[0] + xo[SR - 1]); sample_acc<RB, CELL>(t, hh[0], ll[0], xh[SR - 1], xl[SR - 1], acc_lo, acc_hi); }
+                        if (smask & 4u) { Taps4<RB, CELL> t; t.load(rt[SR - 1] + xo[0]); sample_acc<RB, CELL>(t, hh[SR - 1], ll[SR - 1], xh[0], xl[0], acc_lo, acc_hi); }
+                        if (smask & 8u) { Taps4<RB, CELL> t; t.load(rt[SR - 1] + xo[SR - 1]); sample_acc<RB, CELL>(t, hh[SR - 1], ll[SR - 1], xh[SR - 1], xl[SR - 1], acc_lo, acc_hi); }
                     }
                     acc_lo = mul2(acc_lo, inv2); acc_hi = mul2(acc_hi, inv2);          // count 1 / 4: exact
                     float v0, v1, v2, v3;
@@ -938,11 +949,11 @@ roi_align_strip_fwd(const __grid_constant__ StripMaps maps, const StripArgs a) {
 size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct StripLayout {
-    size_t ytab_off, xtab_off, zero_off, zero_bytes, rowptr_off, piece_off, entries_off, ws_bytes;
+    size_t ytab_off, xtab_off, zero_off, zero_bytes, rowptr_off, piece_off, entries_off, tmp_off, tmpcnt_off, ws_bytes;
 };
 
 bool strip_geometry(int levels, const float* const* bottoms, const int* heights, const int* widths, const float* scales,
-                    const int* level_roi_begin, int N, int R, int C, int PH, int PW, int sr, int sm_count, StripGeom* g,
+                    const int* level_roi_begin, int N, int R, int C, int PH, int PW, int sr, int sm_count, int cell, StripGeom* g,
                     StripLayout* lay, unsigned* smem_bytes) {
     if (levels < 1 || levels > kMaxLevels) return false;
     if (sr < 1 || sr > 2 || PH * sr > kAxisMaxS || PW * sr > kAxisMaxS || PH > 31 || PW > 31) return false;
@@ -956,7 +967,7 @@ bool strip_geometry(int levels, const float* const* bottoms, const int* heights,
     static const int kSx[3] = {32, 64, 96}, kHalo[3] = {8, 8, 16};
     for (int m = 0; m < 3; ++m) {
         const int sx = kSx[m];
-        int k = (int)((kSmemBudget - fixed) / (unsigned)(sx * kCell)) - 1;       // one physical slot is the mirror of slot 0
+        int k = (int)((kSmemBudget - fixed) / (unsigned)(sx * cell)) - 1;       // one physical slot is the mirror of slot 0
         if (k > kMaxK) k = kMaxK;
         if (k < 12) continue;
         const int wx = sx - kHalo[m];
@@ -971,7 +982,7 @@ bool strip_geometry(int levels, const float* const* bottoms, const int* heights,
     if (best_score < 0) return false;
     g->N = N; g->R = R; g->C = C; g->PH = PH; g->PW = PW; g->sr = sr;
     g->ny = PH * sr; g->nx = PW * sr;
-    g->SX = best_sx; g->WX = best_wx; g->K = best_k;
+    g->SX = best_sx; g->WX = best_wx; g->K = best_k; g->cell = cell;
     g->L = levels;
     int q = 0;
     long long keys = 0;
@@ -998,17 +1009,20 @@ bool strip_geometry(int levels, const float* const* bottoms, const int* heights,
     if (g->G < 1) g->G = 1;
     if (keys * g->G >= (1LL << 30)) return false;
     g->pieces = sm_count > 0 ? sm_count : kNumSMs;
-    g->max_entries = R * PH * PW * sr * sr;                    // worst case: every sample its own fragment
-    g->row_cost = 24u;
+    g->cap_r = PH * PW * sr * sr;                              // worst case: every sample its own fragment
+    g->max_entries = R * g->cap_r;
+    g->row_cost = 44u;
     size_t off = 0;
     lay->ytab_off = off; off = align_up_sz(off + (size_t)R * g->ny * 16, 256);
     lay->xtab_off = off; off = align_up_sz(off + (size_t)R * g->nx * 16, 256);
-    lay->zero_off = off; lay->zero_bytes = align_up_sz(((size_t)4 * g->keys + 4) * 4, 256); off += lay->zero_bytes;
+    lay->zero_off = off; lay->zero_bytes = align_up_sz(((size_t)3 * g->keys + 4) * 4, 256); off += lay->zero_bytes;
     lay->rowptr_off = off; off = align_up_sz(off + ((size_t)g->keys + 1) * 4, 256);
     lay->piece_off = off; off = align_up_sz(off + ((size_t)g->pieces + 1) * 4, 256);
     lay->entries_off = off; off = align_up_sz(off + (size_t)g->max_entries * 8, 256);
+    lay->tmp_off = off; off = align_up_sz(off + (size_t)g->max_entries * 16, 256);
+    lay->tmpcnt_off = off; off = align_up_sz(off + (size_t)R * 4, 256);
     lay->ws_bytes = off;
-    *smem_bytes = (unsigned)(g->K + 1) * (unsigned)(g->SX * kCell) + fixed;
+    *smem_bytes = (unsigned)(g->K + 1) * (unsigned)(g->SX * cell) + fixed;
     return true;
 }
 
@@ -1058,11 +1072,12 @@ bool strip_device_info(StripDevice* out) {
         const int max_dyn = (int)kSmemBudget;
         bool ok = cudaDeviceGetAttribute(&info[dev].sm_count, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess;
 #define B200_STRIP_ATTR(SRV, XOV) \
-        ok = ok && cudaFuncSetAttribute(roi_align_strip_fwd<SRV, XOV>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) == cudaSuccess
+        ok = ok && cudaFuncSetAttribute(roi_align_strip_fwd<SRV, XOV, kCellTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) == cudaSuccess; \
+        ok = ok && cudaFuncSetAttribute(roi_align_strip_fwd<SRV, XOV, kCellAsync>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) == cudaSuccess
         B200_STRIP_ATTR(1, 4); B200_STRIP_ATTR(1, 8); B200_STRIP_ATTR(1, 12);
         B200_STRIP_ATTR(2, 4); B200_STRIP_ATTR(2, 8); B200_STRIP_ATTR(2, 12);
 #undef B200_STRIP_ATTR
-        const int prep_dyn = 2 * (kMaxKeys + 1) * 4;
+        const int prep_dyn = 2 * (kMaxKeys + 1) * 4 + kAxisMaxS * kAxisMaxS * 12;
         ok = ok && cudaFuncSetAttribute(strip_prep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_dyn) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(strip_prep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_dyn) == cudaSuccess;
         if (!ok) {
@@ -1089,7 +1104,7 @@ size_t roi_align_strip_fpn_workspace_bytes(int levels, const int* heights, const
     StripGeom g;
     StripLayout lay;
     unsigned smem = 0;
-    if (!strip_geometry(levels, nullptr, heights, widths, nullptr, nullptr, N, R, 32, PH, PW, sr, kNumSMs, &g, &lay, &smem)) return 0;
+    if (!strip_geometry(levels, nullptr, heights, widths, nullptr, nullptr, N, R, 32, PH, PW, sr, kNumSMs, kCellAsync, &g, &lay, &smem)) return 0;
     return lay.ws_bytes;
 }
 
@@ -1108,7 +1123,11 @@ int roi_align_forward_strip_fpn(int levels, const float* const* bottoms, const i
     StripGeom g;
     StripLayout lay;
     unsigned smem = 0;
-    if (!strip_geometry(levels, bottoms, heights, widths, scales, level_roi_begin, N, R, C, PH, PW, sr, dev.sm_count, &g, &lay, &smem)) return 1000;
+    // rows by TMA when every level has an x-quad view (W % 4 == 0, 16-byte aligned base) -- else cp.async producers
+    bool tma = option_get(kOptStreamStage) != 'a' && encode_tiled_fn() != nullptr && kPW >= 2;      // B200_STREAM_STAGE=async: A/B
+    for (int l = 0; tma && l < levels; ++l) tma = (widths[l] & 3) == 0 && ((uintptr_t)bottoms[l] & 15u) == 0;
+    if (!strip_geometry(levels, bottoms, heights, widths, scales, level_roi_begin, N, R, C, PH, PW, sr, dev.sm_count,
+                        tma ? kCellTma : kCellAsync, &g, &lay, &smem)) return 1000;
     if (workspace_bytes < lay.ws_bytes) return 1000;
     const int rc_opt = option_get(kOptStripRowCost);
     if (rc_opt >= '0' && rc_opt <= '9') g.row_cost = 8u * (unsigned)(rc_opt - '0') + 4u;      // B200_STRIP_ROWCOST=0..9 (tuning)
@@ -1117,14 +1136,16 @@ int roi_align_forward_strip_fpn(int levels, const float* const* bottoms, const i
     ws.ytab = (uint4*)(wsb + lay.ytab_off);
     ws.xtab = (uint4*)(wsb + lay.xtab_off);
     int* zero = (int*)(wsb + lay.zero_off);
-    ws.hist = zero; ws.cost = zero + g.keys; ws.cursor = zero + 2 * (size_t)g.keys; ws.maxend = zero + 3 * (size_t)g.keys;
-    ws.ticket = zero + 4 * (size_t)g.keys;
+    ws.hist = zero; ws.cost = zero + g.keys; ws.maxend = zero + 2 * (size_t)g.keys;
+    ws.ticket = zero + 3 * (size_t)g.keys;
     ws.rowptr = (int*)(wsb + lay.rowptr_off);
     ws.piece_start = (int*)(wsb + lay.piece_off);
     ws.entries = (uint2*)(wsb + lay.entries_off);
+    ws.tmp = (uint4*)(wsb + lay.tmp_off);
+    ws.tmpcnt = (int*)(wsb + lay.tmpcnt_off);
 
     // prepass grid: one CTA per RoI when they are all resident at once (the kernel has a grid barrier), else a resident grid
-    const size_t prep_dyn = (size_t)2 * (g.keys + 1) * 4;
+    const size_t prep_dyn = (size_t)2 * (g.keys + 1) * 4 + (size_t)g.cap_r * 12;
     int per_sm = 0;
     cudaError_t err = sr == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_prep<1>, kPrepThreads, prep_dyn)
                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, strip_prep<2>, kPrepThreads, prep_dyn);
@@ -1145,8 +1166,8 @@ int roi_align_forward_strip_fpn(int levels, const float* const* bottoms, const i
     a.magicK = 0xffffffffu / (unsigned)g.K + 1u;
     StripMaps maps;
     memset(&maps, 0, sizeof(maps));
-    bool tma = option_get(kOptStreamStage) != 'a';              // B200_STREAM_STAGE=async: cp.async producers (A/B, and the fallback)
-    for (int l = 0; tma && l < levels; ++l) tma = make_quad_map(&maps.m[l], bottoms[l], N, C, heights[l], widths[l], g.SX);
+    for (int l = 0; tma && l < levels; ++l)
+        if (!make_quad_map(&maps.m[l], bottoms[l], N, C, heights[l], widths[l], g.SX)) return 1000;      // (the geometry was sized for TMA cells)
     a.tma = tma ? 1 : 0;
     for (int l = 0; l < kMaxLevels; ++l) a.lv[l] = g.lv[l];
     for (int c = 0; c <= kMaxCols; ++c) a.colstart[c] = g.colstart[c];
@@ -1163,7 +1184,8 @@ int roi_align_forward_strip_fpn(int levels, const float* const* bottoms, const i
     cfg.attrs = attr;
     cfg.numAttrs = option_get(kOptStripPdl) == '0' ? 0 : 1;                    // B200_STRIP_PDL=0: plain stream order
     const int xo = g.SX / 8;
-#define B200_STRIP_LAUNCH(SRV, XOV) err = cudaLaunchKernelEx(&cfg, roi_align_strip_fwd<SRV, XOV>, maps, a)
+#define B200_STRIP_LAUNCH(SRV, XOV) \
+    err = tma ? cudaLaunchKernelEx(&cfg, roi_align_strip_fwd<SRV, XOV, kCellTma>, maps, a) : cudaLaunchKernelEx(&cfg, roi_align_strip_fwd<SRV, XOV, kCellAsync>, maps, a)
     if (sr == 1) { if (xo == 4) B200_STRIP_LAUNCH(1, 4); else if (xo == 8) B200_STRIP_LAUNCH(1, 8); else B200_STRIP_LAUNCH(1, 12); }
     else         { if (xo == 4) B200_STRIP_LAUNCH(2, 4); else if (xo == 8) B200_STRIP_LAUNCH(2, 8); else B200_STRIP_LAUNCH(2, 12); }
 #undef B200_STRIP_LAUNCH

@@ -10,7 +10,7 @@ d=json.load(open(sys.argv[1])); k=d["kernels"]
 print("value %.0f RoIs/s fwd %.4f (%.3f) bwd %.4f (%.3f) nms %.4f e2e %.0f roofline %s %.3f" % (d["value"], k["fwd"]["ms"], k["fwd"]["frac_of_measured"], k["bwd"]["ms"], k["bwd"]["frac_of_measured"], k["nms_6000"]["ms"], d["e2e"]["value"], d["roofline"]["kernel"], d["roofline"]["frac"]))
 PY
 echo "== bench --impl reference"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference.json" 2>> "$OUT/bench.err"; cut -c1-300 "$OUT/bench_reference.json"
-echo "== X2 one GPU"; timeout 900 python tools/x2_cfg5.py --steps 3 --warmup 1 > "$OUT/x2_n1.json" 2> "$OUT/x2_n1.err"; echo "x2 rc=$?" | tee -a "$OUT/status.txt"; cat "$OUT/x2_n1.json"; tail -2 "$OUT/x2_n1.err"
+echo "== X2 one GPU"; [ "${3:-}" = "nox2" ] || timeout 900 python tools/x2_cfg5.py --steps 3 --warmup 1 > "$OUT/x2_n1.json" 2> "$OUT/x2_n1.err"; echo "x2 rc=$?" | tee -a "$OUT/status.txt"; cat "$OUT/x2_n1.json"; tail -2 "$OUT/x2_n1.err"
 echo "== X1"; timeout 900 python tools/x1_cfg4.py --iters 5 > "$OUT/x1_cfg4.json" 2>/dev/null; cat "$OUT/x1_cfg4.json"
 echo "== kernel matrix"; timeout 900 python tools/kernel_matrix.py --iters 30 > "$OUT/kernel_matrix.json" 2> "$OUT/kernel_matrix.log"; cat "$OUT/kernel_matrix.log"
 echo "== fpn probe"; timeout 600 python tools/fpn_probe.py 2>&1 | tail -8
@@ -33,6 +33,6 @@ PY
 if [ "${2:-}" = "ncu" ]; then
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file "$OUT/launches.csv" python bench.py --steps 4 --warmup 3 --no-graph --cpu-seconds 1 > "$OUT/ncu_launches.log" 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'roi_align_stream_fwd|roi_align_bwd_rows<' -s 8 -c 4 -o "$OUT/prof" -f python bench.py --steps 4 --warmup 3 --no-graph --cpu-seconds 1 > "$OUT/ncu_full.log" 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'roi_align_strip_fwd|strip_prep|roi_align_bwd_rows<' -s 9 -c 6 -o "$OUT/prof" -f python bench.py --steps 4 --warmup 3 --no-graph --cpu-seconds 1 > "$OUT/ncu_full.log" 2>&1
 fi
 cat "$OUT/status.txt"
