@@ -69,6 +69,18 @@ _SIGNATURES = {
     # (top, top_counts_host, all, all_counts_host, P, thresh, scoring, beta, out, stream)
     "b200_box_voting_batched": (ctypes.c_int, [_c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
                                                ctypes.c_int, ctypes.c_float, _c_float_p, _stream_t]),
+    # (boxes, N, query, K, out, stream)
+    "b200_bbox_overlaps": (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, ctypes.c_int, _c_float_p, _stream_t]),
+    # (boxes, N, gt, gt_classes, G, max_overlaps, argmax, max_classes, stream)
+    "b200_roi_assign": (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, ctypes.c_void_p, ctypes.c_int, _c_float_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, _stream_t]),
+    # (max_overlaps, N, fg, bg_hi, bg_lo, fg_inds, bg_inds, counts, stream)
+    "b200_roi_select": (ctypes.c_int, [_c_float_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p, _stream_t]),
+    # (boxes, gt, argmax, max_classes, keep, n, n_fg, weights4_host, reg_classes, agnostic, im_scale, batch_idx, labels, rois, targets, inside, outside, stream)
+    "b200_fast_rcnn_targets": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                              ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _stream_t]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

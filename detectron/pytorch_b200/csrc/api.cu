@@ -10,7 +10,7 @@ unsigned long long g_launch_count = 0;
 
 static const char* const kOptionNames[kNumOptions] = {"B200_ROI_ALIGN_PATH", "B200_ROI_ALIGN_BWD_PATH", "B200_ROI_ALIGN_BWD_CPL",
                                                       "B200_FWD_ZERO", "B200_NMS_SCAN", "B200_STREAM_STAGE", "B200_STREAM_PHASES",
-                                                      "B200_FPN_PATH", "B200_STRIP_ROWCOST", "B200_STRIP_PDL"};
+                                                      "B200_FPN_PATH", "B200_STRIP_ROWCOST", "B200_STRIP_PDL", "B200_BWD_TRCH"};
 static int g_options[kNumOptions];
 static std::once_flag g_options_once;
 
@@ -63,6 +63,12 @@ int roi_align_forward_strip_fpn(int, const float* const*, const int*, const int*
                                 const float*, float*, const int*, void*, size_t, cudaStream_t);
 int roi_align_forward_strip(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
 void roi_align_strip_set_debug_buffer(unsigned long long*);
+
+int bbox_overlaps(const float*, int, const float*, int, float*, cudaStream_t);
+int roi_assign(const float*, int, const float*, const int*, int, float*, int*, int*, cudaStream_t);
+int roi_select(const float*, int, float, float, float, int*, int*, int*, cudaStream_t);
+int fast_rcnn_targets(const float*, const float*, const int*, const int*, const int*, int, int, const float*, int, int, float, float, int*,
+                      float*, float*, float*, float*, cudaStream_t);
 
 // B200_ROI_ALIGN_PATH=generic|tiled|stream|auto (default auto) -- test/benchmark override of the forward dispatch
 //   0 auto: quad-strip path -> streaming-strip path -> tiled path -> generic, each when it applies
@@ -456,6 +462,44 @@ int b200_box_voting_batched(const float* top_dets_dev, const int* top_counts_hos
     if (scoring_method < 0 || scoring_method > 5) return B200_ROI_EINVAL;
     return box_voting_batched(top_dets_dev, top_counts_host, all_dets_dev, all_counts_host, num_problems, thresh, scoring_method, beta, out_dev,
                               (cudaStream_t)stream);
+}
+
+int b200_bbox_overlaps(const float* boxes_dev, int num_boxes, const float* query_boxes_dev, int num_query, float* overlaps_out_dev,
+                       b200_stream_t stream) {
+    if (num_boxes < 0 || num_query < 0) return B200_ROI_EINVAL;
+    if ((long long)num_boxes * num_query > 0 && (!boxes_dev || !query_boxes_dev || !overlaps_out_dev)) return B200_ROI_EINVAL;
+    return bbox_overlaps(boxes_dev, num_boxes, query_boxes_dev, num_query, overlaps_out_dev, (cudaStream_t)stream);
+}
+
+int b200_roi_assign(const float* boxes_dev, int num_boxes, const float* gt_boxes_dev, const int* gt_classes_dev, int num_gt,
+                    float* max_overlaps_out_dev, int* argmax_out_dev, int* max_classes_out_dev, b200_stream_t stream) {
+    if (num_boxes < 0 || num_gt < 0) return B200_ROI_EINVAL;
+    if (num_boxes > 0 && (!boxes_dev || !max_overlaps_out_dev || !argmax_out_dev || !max_classes_out_dev)) return B200_ROI_EINVAL;
+    if (num_boxes > 0 && num_gt > 0 && (!gt_boxes_dev || !gt_classes_dev)) return B200_ROI_EINVAL;
+    return roi_assign(boxes_dev, num_boxes, gt_boxes_dev, gt_classes_dev, num_gt, max_overlaps_out_dev, argmax_out_dev, max_classes_out_dev,
+                      (cudaStream_t)stream);
+}
+
+int b200_roi_select(const float* max_overlaps_dev, int num_boxes, float fg_thresh, float bg_thresh_hi, float bg_thresh_lo,
+                    int* fg_inds_out_dev, int* bg_inds_out_dev, int* counts_out_dev, b200_stream_t stream) {
+    if (num_boxes < 0 || !counts_out_dev) return B200_ROI_EINVAL;
+    if (num_boxes > 0 && (!max_overlaps_dev || !fg_inds_out_dev || !bg_inds_out_dev)) return B200_ROI_EINVAL;
+    return roi_select(max_overlaps_dev, num_boxes, fg_thresh, bg_thresh_hi, bg_thresh_lo, fg_inds_out_dev, bg_inds_out_dev, counts_out_dev,
+                      (cudaStream_t)stream);
+}
+
+int b200_fast_rcnn_targets(const float* boxes_dev, const float* gt_boxes_dev, const int* argmax_dev, const int* max_classes_dev,
+                           const int* keep_inds_dev, int num_keep, int num_fg, const float* bbox_reg_weights_host, int num_reg_classes,
+                           int cls_agnostic, float im_scale, float batch_idx, int* labels_out_dev, float* rois_out_dev,
+                           float* bbox_targets_out_dev, float* inside_weights_out_dev, float* outside_weights_out_dev,
+                           b200_stream_t stream) {
+    if (num_keep < 0 || num_fg < 0 || num_fg > num_keep || num_reg_classes < 1 || !bbox_reg_weights_host) return B200_ROI_EINVAL;
+    if (num_keep > 0 && (!boxes_dev || !argmax_dev || !max_classes_dev || !keep_inds_dev || !labels_out_dev || !rois_out_dev ||
+                         !bbox_targets_out_dev || !inside_weights_out_dev || !outside_weights_out_dev))
+        return B200_ROI_EINVAL;
+    return fast_rcnn_targets(boxes_dev, gt_boxes_dev, argmax_dev, max_classes_dev, keep_inds_dev, num_keep, num_fg, bbox_reg_weights_host,
+                             num_reg_classes, cls_agnostic, im_scale, batch_idx, labels_out_dev, rois_out_dev, bbox_targets_out_dev,
+                             inside_weights_out_dev, outside_weights_out_dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -32,6 +32,7 @@ enum Option {
     kOptFpnPath,          // B200_FPN_PATH            = fused (one launch sequence over the level table) | levels (per-level calls)
     kOptStripRowCost,     // B200_STRIP_ROWCOST       = 0..9: cost of streaming a row in the partition model = 8 d + 4 (default 24)
     kOptStripPdl,         // B200_STRIP_PDL           = 1 | 0: programmatic dependent launch of the main kernel behind the prepass
+    kOptBwdTrCh,          // B200_BWD_TRCH            = 2 (256) | 1 (128) | 6 (64): channels per CTA of the backward's dY transpose
     kNumOptions
 };
 int option_get(Option which);
@@ -92,6 +93,27 @@ __device__ __forceinline__ AxisTap xfrom_axis(float v, int size) {
     t.l = __fsub_rn(v, (float)t.low);
     t.h = __fsub_rn(1.f, t.l);
     return t;
+}
+
+// ---- IoU exactly as the reference's compiled Cython computes it (lib/utils/cython_bbox.pyx:52-72) ----------------------
+// The generated C adds the literal 1.0 as a DOUBLE: widths / heights are (double)(float difference) + 1.0, their products and the
+// union are formed in double (separate multiply and add: x86-64 baseline has no FMA) and rounded to float once on assignment
+// (box_area, iw, ih, ua are float variables); the final quotient (iw * ih) / ua is float.  Up to 2 ulp away from an all-float
+// evaluation -- enough to flip a threshold test.
+__device__ __forceinline__ float cython_area(float x1, float y1, float x2, float y2) {
+    return (float)__dmul_rn(__dadd_rn((double)__fsub_rn(x2, x1), 1.0), __dadd_rn((double)__fsub_rn(y2, y1), 1.0));
+}
+// b: the "boxes" row, q: the "query_boxes" row, qarea = cython_area(q)
+__device__ __forceinline__ float cython_iou(float bx1, float by1, float bx2, float by2, float qx1, float qy1, float qx2, float qy2,
+                                            float qarea) {
+    const float iw = (float)__dadd_rn((double)__fsub_rn(fminf(bx2, qx2), fmaxf(bx1, qx1)), 1.0);
+    if (!(iw > 0.f)) return 0.f;
+    const float ih = (float)__dadd_rn((double)__fsub_rn(fminf(by2, qy2), fmaxf(by1, qy1)), 1.0);
+    if (!(ih > 0.f)) return 0.f;
+    const float inter = __fmul_rn(iw, ih);
+    const double barea = __dmul_rn(__dadd_rn((double)__fsub_rn(bx2, bx1), 1.0), __dadd_rn((double)__fsub_rn(by2, by1), 1.0));
+    const float ua = (float)__dsub_rn(__dadd_rn(barea, (double)qarea), (double)inter);
+    return __fdiv_rn(inter, ua);
 }
 
 }  // namespace b200

@@ -106,21 +106,12 @@ box_voting_kernel(const float* __restrict__ top_all, const float* __restrict__ a
     float* out = out_all + (size_t)(top_b.off[p] + k) * 5;
     const int n = all_b.n[p];
     const float bx1 = top[0], by1 = top[1], bx2 = top[2], by2 = top[3];
-    const float barea = __fmul_rn(__fadd_rn(__fsub_rn(bx2, bx1), 1.f), __fadd_rn(__fsub_rn(by2, by1), 1.f));
     double sx1 = 0, sy1 = 0, sx2 = 0, sy2 = 0, sw = 0, s_temp = 0, s_iou_w = 0, s_iou_p = 0, s_gen = 0;
     int cnt = 0;
     for (int j = 0; j < n; ++j) {
         const float qx1 = all[j * 5], qy1 = all[j * 5 + 1], qx2 = all[j * 5 + 2], qy2 = all[j * 5 + 3], w = all[j * 5 + 4];
-        float ov = 0.f;
-        const float iw = __fadd_rn(__fsub_rn(fminf(bx2, qx2), fmaxf(bx1, qx1)), 1.f);
-        if (iw > 0.f) {
-            const float ih = __fadd_rn(__fsub_rn(fminf(by2, qy2), fmaxf(by1, qy1)), 1.f);
-            if (ih > 0.f) {
-                const float qarea = __fmul_rn(__fadd_rn(__fsub_rn(qx2, qx1), 1.f), __fadd_rn(__fsub_rn(qy2, qy1), 1.f));
-                const float inter = __fmul_rn(iw, ih);
-                ov = __fdiv_rn(inter, __fsub_rn(__fadd_rn(barea, qarea), inter));
-            }
-        }
+        // utils.boxes.box_voting: bbox_overlaps(top_boxes, all_boxes) -> the kept detection is the "boxes" row
+        const float ov = cython_iou(bx1, by1, bx2, by2, qx1, qy1, qx2, qy2, cython_area(qx1, qy1, qx2, qy2));
         if (ov >= thresh) {
             sx1 += (double)w * qx1; sy1 += (double)w * qy1; sx2 += (double)w * qx2; sy2 += (double)w * qy2; sw += w;
             ++cnt;

@@ -418,6 +418,8 @@ int roi_align_backward_rows(const float* top_diff, float scale, int N, int R, in
     unsigned char* ws = (unsigned char*)workspace;
     const int bins = PH * PW;
     int tr_ch = kTransposeChannelsMax;                       // as many channels per CTA as fit ~100 KB (two CTAs per SM)
+    const int tr_opt = option_get(kOptBwdTrCh);
+    if (tr_opt == '1') tr_ch = 128; else if (tr_opt == '6') tr_ch = 64;
     while (tr_ch > 32 && (size_t)tr_ch * (bins | 1) * sizeof(float) > 100 * 1024) tr_ch >>= 1;
     if (tr_ch > C) tr_ch = (C + 31) / 32 * 32;
     const size_t smem_tr = (size_t)tr_ch * (bins | 1) * sizeof(float);

@@ -211,9 +211,10 @@ B200_API int b200_box_voting_batched(const float* top_dets_dev, const int* top_c
 /* ---- introspection used by the benchmark / tests (no compute) ----------------------------------
  * Number of kernel launches the library has enqueued since load (all entry points). */
 B200_API unsigned long long b200_roi_ops_launch_count(void);
-/* Path-selection switches (A/B runs and tests): name is one of "B200_ROI_ALIGN_PATH" (auto|generic|tiled|stream),
+/* Path-selection switches (A/B runs and tests): name is one of "B200_ROI_ALIGN_PATH" (auto|generic|tiled|stream|quad),
  * "B200_ROI_ALIGN_BWD_PATH" (auto|generic|nhwc|rows), "B200_ROI_ALIGN_BWD_CPL" (4|2), "B200_FWD_ZERO" (dense|bins),
- * "B200_NMS_SCAN" (resolver|simple), "B200_STREAM_STAGE" (async|regs), "B200_STREAM_PHASES" (all|prepass: timing probe);
+ * "B200_NMS_SCAN" (resolver|simple), "B200_STREAM_STAGE" (tma|async|regs), "B200_STREAM_PHASES" (all|prepass: timing probe), "B200_STRIP_ROWCOST" (0..9),
+ * "B200_STRIP_PDL" (1|0), "B200_FPN_PATH" (fused|levels);
  * value NULL or "" restores the default.  Each switch takes its initial value from the
  * environment variable of the same name, read once at first use -- no entry point calls getenv() on the hot path.
  * Returns 0, or B200_ROI_EINVAL for an unknown name. */
@@ -232,6 +233,29 @@ B200_API void b200_roi_ops_debug_timing_buffer(void* device_u64x16);
 B200_API int b200_proposal_decode(const float* bbox_deltas, const float* anchors, const long long* order, const float* scores,
                          int num_candidates, int num_anchors, int height, int width, float feat_stride, float im_height,
                          float im_width, float min_size, float* dets_out, int* valid_out, b200_stream_t stream);
+
+/* ---- RoI label / regression-target generation on the device ---------------------------------
+ * The per-image host work of the reference's training data path, for proposals that already live on the GPU.  Boxes are
+ * float32 (x1, y1, x2, y2) rows in image pixels, exactly the roidb's `boxes`.
+ * b200_bbox_overlaps    lib/utils/cython_bbox.pyx:32-73: (N, K) IoU with the +1 pixel convention, bit-exact float32.
+ * b200_roi_assign       lib/datasets/json_dataset.py:429-463 + :514-531 without the (N, K) matrix: per box the best
+ *                       ground-truth overlap (0 when none is positive), its index (first maximum; -1) and class (0).
+ * b200_roi_select       lib/roi_data/fast_rcnn.py:138-151: ascending index lists of the foreground (>= fg_thresh) and
+ *                       background ([bg_lo, bg_hi)) boxes, counts_out = {num_fg, num_bg}.
+ * b200_fast_rcnn_targets  fast_rcnn.py:161-187 + :203-248 for the kept rows (the first num_fg are foreground): labels
+ *                       (int32), rois (batch_idx, box * im_scale), regression targets (utils/boxes.py:199-230) expanded
+ *                       to 4 * num_reg_classes columns, inside / outside weights.  bbox_reg_weights_host: 4 floats. */
+B200_API int b200_bbox_overlaps(const float* boxes_dev, int num_boxes, const float* query_boxes_dev, int num_query,
+                                float* overlaps_out_dev, b200_stream_t stream);
+B200_API int b200_roi_assign(const float* boxes_dev, int num_boxes, const float* gt_boxes_dev, const int* gt_classes_dev, int num_gt,
+                             float* max_overlaps_out_dev, int* argmax_out_dev, int* max_classes_out_dev, b200_stream_t stream);
+B200_API int b200_roi_select(const float* max_overlaps_dev, int num_boxes, float fg_thresh, float bg_thresh_hi, float bg_thresh_lo,
+                             int* fg_inds_out_dev, int* bg_inds_out_dev, int* counts_out_dev, b200_stream_t stream);
+B200_API int b200_fast_rcnn_targets(const float* boxes_dev, const float* gt_boxes_dev, const int* argmax_dev, const int* max_classes_dev,
+                                    const int* keep_inds_dev, int num_keep, int num_fg, const float* bbox_reg_weights_host,
+                                    int num_reg_classes, int cls_agnostic, float im_scale, float batch_idx, int* labels_out_dev,
+                                    float* rois_out_dev, float* bbox_targets_out_dev, float* inside_weights_out_dev,
+                                    float* outside_weights_out_dev, b200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,91 @@
+"""GPU: RoI label / target generation on the device, through the C ABI, against the golden vectors of the
+unmodified reference functions and against the numpy oracle on larger seeded inputs.
+Bit-exact: overlaps, assignments, labels, index lists, rois, weights.  Regression targets: dx / dy bit-exact, dw / dh within
+2 ulp (CUDA logf vs numpy's float32 log)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from detectron.pytorch_b200.roi_data import fast_rcnn as FR
+from oracle import targets as OT
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "targets.npz"))
+CASES = ["a", "b", "c"]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def roidb_boxes(c):
+    return np.concatenate([GOLD[c + "_gt"], GOLD[c + "_prop"]]).astype(np.float32)
+
+
+def assert_targets_close(got, ref):
+    assert np.array_equal(got == 0, ref == 0)
+    ulp = np.abs(got.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 2, "regression targets differ by %d ulp" % ulp.max()
+    cols = np.arange(got.shape[1]) % 4 < 2                                    # dx, dy: no transcendental -> exact
+    assert np.array_equal(got[:, cols], ref[:, cols])
+
+
+@pytest.mark.parametrize("c", CASES)
+def test_bbox_overlaps_vs_reference(c):
+    got = FR.bbox_overlaps(dev(GOLD[c + "_prop"]), dev(GOLD[c + "_gt"])).cpu().numpy()
+    assert np.array_equal(got, GOLD[c + "_overlaps"])
+
+
+def test_bbox_overlaps_large_vs_oracle_and_empty():
+    rng = np.random.RandomState(0)
+    a = np.sort(rng.uniform(0, 900, (3000, 2, 2)), axis=1).transpose(0, 2, 1).reshape(3000, 4)[:, [0, 2, 1, 3]].astype(np.float32)
+    b = np.sort(rng.uniform(0, 900, (700, 2, 2)), axis=1).transpose(0, 2, 1).reshape(700, 4)[:, [0, 2, 1, 3]].astype(np.float32)
+    assert np.array_equal(FR.bbox_overlaps(dev(a), dev(b)).cpu().numpy(), OT.bbox_overlaps(a, b))
+    assert tuple(FR.bbox_overlaps(dev(a[:0]), dev(b)).shape) == (0, 700)
+
+
+@pytest.mark.parametrize("c", CASES)
+def test_assignment_vs_reference_roidb(c):
+    mo, am, mc = FR.assign_rois(dev(roidb_boxes(c)), dev(GOLD[c + "_gt"]), dev(GOLD[c + "_gt_classes"]))
+    assert np.array_equal(mo.cpu().numpy(), GOLD[c + "_max_overlaps"])
+    assert np.array_equal(mc.cpu().numpy(), GOLD[c + "_max_classes"])
+    assert np.array_equal(am.cpu().numpy(), GOLD[c + "_box_to_gt"])
+
+
+@pytest.mark.parametrize("c", CASES)
+def test_sample_rois_vs_reference_blobs(c):
+    ncls, batch, agn = [int(v) for v in GOLD[c + "_cfg"]]
+    b = FR.sample_rois(dev(roidb_boxes(c)), dev(GOLD[c + "_gt"]), dev(GOLD[c + "_gt_classes"]), 1.5, 1, ncls, batch_size_per_im=batch,
+                       cls_agnostic_bbox_reg=bool(agn), fg_choice=GOLD[c + "_fg_choice"], bg_choice=GOLD[c + "_bg_choice"])
+    assert np.array_equal(b["labels_int32"].cpu().numpy(), GOLD[c + "_labels_int32"])
+    assert np.array_equal(b["rois"].cpu().numpy(), GOLD[c + "_rois"])
+    assert np.array_equal(b["bbox_inside_weights"].cpu().numpy(), GOLD[c + "_bbox_inside_weights"])
+    assert np.array_equal(b["bbox_outside_weights"].cpu().numpy(), GOLD[c + "_bbox_outside_weights"])
+    assert_targets_close(b["bbox_targets"].cpu().numpy(), GOLD[c + "_bbox_targets"])
+
+
+def test_sample_rois_device_draw_is_a_valid_minibatch():
+    """Without host-provided choices the draw is a torch.randperm on the device: sizes, membership and labels must still be
+    those of _sample_rois."""
+    c = "c"
+    ncls, batch, agn = [int(v) for v in GOLD[c + "_cfg"]]
+    boxes = roidb_boxes(c)
+    b = FR.sample_rois(dev(boxes), dev(GOLD[c + "_gt"]), dev(GOLD[c + "_gt_classes"]), 1.0, 0, ncls, batch_size_per_im=batch)
+    keep = b["keep_inds"].cpu().numpy()
+    mo = GOLD[c + "_max_overlaps"]
+    n_fg = min(int(round(0.25 * batch)), int((mo >= 0.5).sum()))
+    assert keep.size == n_fg + min(batch - n_fg, int(((mo < 0.5) & (mo >= 0)).sum()))
+    assert len(set(keep.tolist())) == keep.size
+    assert (mo[keep[:n_fg]] >= 0.5).all() and (mo[keep[n_fg:]] < 0.5).all()
+    lab = b["labels_int32"].cpu().numpy()
+    assert np.array_equal(lab[:n_fg], GOLD[c + "_max_classes"][keep[:n_fg]]) and (lab[n_fg:] == 0).all()
+
+
+def test_no_ground_truth_and_cpu_tensors():
+    boxes = dev(GOLD["a_prop"])
+    mo, am, mc = FR.assign_rois(boxes, None, None)
+    assert float(mo.abs().sum()) == 0 and int((am != -1).sum()) == 0 and int(mc.abs().sum()) == 0
+    with pytest.raises(NotImplementedError):
+        FR.bbox_overlaps(boxes.cpu(), boxes.cpu())
