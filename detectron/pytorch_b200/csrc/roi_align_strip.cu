@@ -57,6 +57,10 @@ constexpr int kCellTma = 128, kCellAsync = 144;
 #define B200_STRIP_DEPTH 2
 #endif
 constexpr int kDepth = B200_STRIP_DEPTH;                      // rows every producer warp keeps in flight
+#ifndef B200_STRIP_INFLIGHT
+#define B200_STRIP_INFLIGHT 8
+#endif
+constexpr int kInflight = B200_STRIP_INFLIGHT;                // TMA mode: rows issued but not yet transposed
 constexpr int kMaxLevels = 6;
 constexpr int kMaxCols = 96;
 constexpr int kAxisMaxS = 32;
@@ -643,7 +647,7 @@ roi_align_strip_fwd(const __grid_constant__ StripMaps maps, const StripArgs a) {
         constexpr unsigned kRowBytes = (unsigned)SX * 128u;
         const int role = warp - kCW;                           // 0: issuer, 1 .. T: transposers
         int i = 0, slot = 0, turn = 0;
-        int low = 0;                                           // issuer: last observed min(consumer marks, transposer marks)
+        int low_c = 0, low_t = 0;                              // issuer: last observed minimum of the consumer / transposer marks
         unsigned use_parity = 0;                               // parity of the current use of `slot` = (i / K) & 1
         for (int L = L0; L < L1;) {
             const Item it = decode_item(L, L1, a, lane);
@@ -653,17 +657,19 @@ roi_align_strip_fwd(const __grid_constant__ StripMaps maps, const StripArgs a) {
             const int xquad = (it.s * a.WX) >> 2;
             for (int y = it.ya; y < it.yhi; ++y) {
                 if (role == 0) {
-                    if (i >= a.K && low <= i - a.K) {              // row i - K must be transposed AND done with by every consumer
+                    // row i - K must be done with by every consumer (and transposed); at most kInflight rows are kept between issue
+                    // and transposition: the first rows a piece needs do not queue behind a ring-full of later ones in DRAM
+                    if ((i >= a.K && low_c <= i - a.K) || (i >= kInflight && low_t <= i - kInflight)) {
                         unsigned spins = 0;
                         TIM_DO(tim_c = clock64());
                         for (;;) {
-                            int v = 0x7fffffff;
-                            if (lane < kCW) v = lds_acquire(pub + 4u * lane);
-                            else if (lane < kCW + T && lane < 32) v = lds_acquire(next_addr + 4u * (lane - kCW));
-                            low = __reduce_min_sync(0xffffffffu, v);
-                            if (low > i - a.K) break;
-                            __nanosleep(100);
-                            if (++spins == (1u << 21)) watchdog_note(3u, ((u64)(unsigned)i << 20) | (u64)(unsigned)low);
+                            const int vc = lane < kCW ? lds_acquire(pub + 4u * lane) : 0x7fffffff;
+                            const int vt = lane < T ? lds_acquire(next_addr + 4u * lane) : 0x7fffffff;
+                            low_t = __reduce_min_sync(0xffffffffu, vt);
+                            low_c = min(__reduce_min_sync(0xffffffffu, vc), low_t);
+                            if (low_c > i - a.K && low_t > i - kInflight) break;
+                            __nanosleep(60);
+                            if (++spins == (1u << 21)) watchdog_note(3u, ((u64)(unsigned)i << 20) | (u64)(unsigned)low_c);
                             if (spins > (1u << 22)) __trap();
                         }
                         TIM_DO(tim_wait += clock64() - tim_c);

@@ -66,14 +66,21 @@ def find(sub):
     return hit[0] if hit else None
 
 
-t = {"roi_align_fwd": find("roi_align_tiled_fwd"), "roi_align_fwd_prep": find("roi_align_tiled_prep"),
-     "roi_align_bwd_main": find("roi_align_bwd_rows<"), "roi_align_bwd_tables": find("roi_align_bwd_rows_tables"),
-     "nms_mask": find("nms_mask"), "nms_scan": find("nms_scan")}
-if t["roi_align_bwd_main"] is not None and t["roi_align_bwd_tables"] is not None:
+# merged into the committed file: a session that did not capture a kernel keeps the previous session's number for it
+t = json.load(open("profiles/traffic.json")) if os.path.exists("profiles/traffic.json") else {}
+new = {"roi_align_fwd": find("roi_align_strip_fwd") or find("roi_align_stream_fwd") or find("roi_align_tiled_fwd"),
+       "roi_align_fwd_prep": find("strip_prep") or find("roi_align_tiled_prep"),
+       "roi_align_bwd_main": find("roi_align_bwd_rows<"), "roi_align_bwd_tables": find("roi_align_bwd_rows_tables"),
+       "nms_mask": find("nms_mask"), "nms_scan": find("nms_scan")}
+for k, v in new.items():
+    if v is not None:
+        t[k] = v
+        t["source_" + k] = "profiles/%s_ncu_kernels.csv" % tag
+if t.get("roi_align_bwd_main") is not None and t.get("roi_align_bwd_tables") is not None:
     t["roi_align_bwd"] = t["roi_align_bwd_main"] + t["roi_align_bwd_tables"]
-t["source"] = ("profiles/%s_ncu_kernels.csv (ncu --set full --clock-control none, per launch; roi_align_fwd = main forward kernel, "
-               "roi_align_bwd = tables/transpose kernel + main gather kernel; output bytes still L2-resident at kernel end -- most "
-               "of the 55.7 MB dX -- are not counted by dram__bytes_write)" % tag)
+t["source"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full --clock-control none (source_* names the capture "
+               "of each kernel); roi_align_fwd = main forward kernel, roi_align_bwd = tables/transpose kernel + main gather kernel; output "
+               "bytes still L2-resident at kernel end are not counted by dram__bytes_write")
 json.dump(t, open("profiles/traffic.json", "w"), indent=1)
 for f in os.listdir(src):
     if f.startswith("bench") and f.endswith(".json"):
