@@ -869,7 +869,7 @@ roi_align_strip_fwd(const __grid_constant__ StripMaps maps, const StripArgs a) {
                     const int4 nx4 = lds_acquire4(next_addr);
                     ready_c = min(min(nx4.x, nx4.y), min(nx4.z, nx4.w));
                     if (ready_c > i_last) break;
-                    __nanosleep(200);                          // a starved consumer must not crowd the producers' LDGSTS out of the MIO queue
+                    __nanosleep(a.tma ? 64u : 200u);           // cp.async mode: a starved consumer must not crowd the producers' LDGSTS out of the MIO queue
                     if (++spins == (1u << 20)) watchdog_note(2u, ((u64)(unsigned)i_last << 20) | (u64)(unsigned)ready_c);
                     if (spins > (1u << 21)) __trap();
                 }
