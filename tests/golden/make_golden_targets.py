@@ -109,5 +109,84 @@ def main():
     print("wrote", os.path.join(HERE, "targets.npz"))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--train-branch" not in sys.argv:
     main()
+
+
+def training_branch_golden():
+    """The reference's CollectAndDistributeFpnRpnProposalsOp.forward in TRAINING mode (lib/modeling/
+    collect_and_distribute_fpn_rpn_proposals.py:42-63), run unmodified on CPU: two images, five RPN levels of synthetic
+    proposals, FPN multilevel rois.  Writes tests/golden/collect_train.npz."""
+    tmp = tempfile.mkdtemp(prefix="ref_cython_")
+    MG.build_cython(tmp)
+    cfg = MG.import_reference(tmp)[0]
+    import types
+    import numpy.random as npr
+    import torch
+    for modname, attrs in (("matplotlib", {"use": lambda *a, **k: None}), ("pycocotools", {}), ("pycocotools.mask", {}),
+                           ("pycocotools.coco", {"COCO": object})):
+        if modname not in sys.modules:
+            m = types.ModuleType(modname)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[modname] = m
+    sys.modules["pycocotools"].mask = sys.modules["pycocotools.mask"]
+    import modeling.collect_and_distribute_fpn_rpn_proposals as CD
+    import roi_data.fast_rcnn as FR
+    cfg.FPN.FPN_ON = True; cfg.FPN.MULTILEVEL_ROIS = True; cfg.FPN.MULTILEVEL_RPN = True
+    cfg.MODEL.NUM_CLASSES = 81; cfg.MODEL.MASK_ON = False; cfg.MODEL.KEYPOINTS_ON = False; cfg.MODEL.CLS_AGNOSTIC_BBOX_REG = False
+    cfg.TRAIN.BATCH_SIZE_PER_IM = 128; cfg.TRAIN.RPN_POST_NMS_TOP_N = 600
+    out = {}
+    scales = np.asarray([1.5, 1.25], np.float32)
+    im_info = torch.from_numpy(np.stack([[800, 1216, scales[0]], [768, 1333, scales[1]]]).astype(np.float32))
+    roidb, gts = [], []
+    rng = np.random.RandomState(11)
+    roi_inputs, score_inputs = [], []
+    all_props = []
+    for i in range(2):
+        gt, gt_classes, prop = make_case(20 + i, 6 + i, 500, 81, im_w=800.0, im_h=520.0)
+        gts.append((gt, gt_classes))
+        n_gt = gt.shape[0]
+        gt_overlaps = np.zeros((n_gt, 81), np.float32); gt_overlaps[np.arange(n_gt), gt_classes] = 1.0
+        roidb.append(dict(boxes=gt.copy(), gt_classes=gt_classes.copy(), seg_areas=np.zeros(n_gt, np.float32),
+                          gt_overlaps=scipy.sparse.csr_matrix(gt_overlaps), is_crowd=np.zeros(n_gt, bool),
+                          box_to_gt_ind_map=np.arange(n_gt, dtype=np.int32)))
+        all_props.append(np.hstack([np.full((prop.shape[0], 1), i, np.float32), prop * scales[i]]).astype(np.float32))
+    props = np.concatenate(all_props)
+    perm = rng.permutation(props.shape[0])
+    props = props[perm]
+    scores = ((rng.permutation(props.shape[0]) + 0.5) / props.shape[0]).astype(np.float32)     # unique: no tie-order question
+    bounds = np.linspace(0, props.shape[0], 6).astype(int)
+    for l in range(5):
+        roi_inputs.append(props[bounds[l]:bounds[l + 1]]); score_inputs.append(scores[bounds[l]:bounds[l + 1]].reshape(-1, 1))
+    picks = []
+    orig_choice = npr.choice
+
+    def recording_choice(a, size=None, replace=True, p=None):
+        sel = orig_choice(a, size=size, replace=replace, p=p)
+        pos = {int(v): i for i, v in enumerate(np.asarray(a))}
+        picks.append(np.asarray([pos[int(v)] for v in np.atleast_1d(sel)], np.int64))
+        return sel
+    op = CD.CollectAndDistributeFpnRpnProposalsOp()
+    op.train()
+    npr.seed(5)
+    FR.npr.choice = recording_choice
+    try:
+        blobs = op.forward(roi_inputs + score_inputs, roidb, im_info)
+    finally:
+        FR.npr.choice = orig_choice
+    assert len(picks) == 4
+    for l in range(5):
+        out["rpn_rois_%d" % l] = roi_inputs[l]; out["rpn_probs_%d" % l] = score_inputs[l]
+    for i in range(2):
+        out["gt_%d" % i] = gts[i][0]; out["gt_classes_%d" % i] = gts[i][1]
+        out["fg_choice_%d" % i] = picks[2 * i]; out["bg_choice_%d" % i] = picks[2 * i + 1]
+    out["im_info"] = im_info.numpy()
+    for k, v in blobs.items():
+        out["blob_" + k] = np.asarray(v)
+    print("training branch blobs:", {k: np.asarray(v).shape for k, v in blobs.items()})
+    np.savez_compressed(os.path.join(HERE, "collect_train.npz"), **out)
+
+
+if __name__ == "__main__" and "--train-branch" in sys.argv:
+    training_branch_golden()

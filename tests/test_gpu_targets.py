@@ -88,3 +88,25 @@ def test_no_ground_truth_and_cpu_tensors():
     assert float(mo.abs().sum()) == 0 and int((am != -1).sum()) == 0 and int(mc.abs().sum()) == 0
     with pytest.raises(NotImplementedError):
         FR.bbox_overlaps(boxes.cpu(), boxes.cpu())
+
+
+def test_collect_and_distribute_training_branch_vs_reference_op():
+    """SURVEY 8f N1 remainder: CollectAndDistributeFpnRpnProposalsOp.forward in training mode -- proposals merged into the roidb,
+    labels / targets, FPN distribution -- on the device, against the blobs of the unmodified reference op run on CPU
+    (tests/golden/make_golden_targets.py --train-branch) with the same random draws."""
+    from detectron.pytorch_b200.modeling.collect_and_distribute_fpn_rpn_proposals import CollectAndDistributeFpnRpnProposalsOp
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "collect_train.npz"))
+    op = CollectAndDistributeFpnRpnProposalsOp(rpn_min_level=2, rpn_max_level=6, roi_min_level=2, roi_max_level=5, post_nms_topN=600)
+    op.train()
+    inputs = [dev(g["rpn_rois_%d" % l]) for l in range(5)] + [dev(g["rpn_probs_%d" % l]) for l in range(5)]
+    roidb = [dict(boxes=g["gt_%d" % i], gt_classes=g["gt_classes_%d" % i]) for i in range(2)]
+    train = dict(BATCH_SIZE_PER_IM=128, FG_FRACTION=0.25, FG_THRESH=0.5, BG_THRESH_HI=0.5, BG_THRESH_LO=0.0, NUM_CLASSES=81,
+                 BBOX_REG_WEIGHTS=(10.0, 10.0, 5.0, 5.0), CLS_AGNOSTIC_BBOX_REG=False)
+    choices = [(g["fg_choice_%d" % i], g["bg_choice_%d" % i]) for i in range(2)]
+    blobs = op(inputs, roidb, g["im_info"], choices=choices, train=train)
+    for k in ("labels_int32", "rois", "bbox_inside_weights", "bbox_outside_weights", "rois_fpn2", "rois_fpn3", "rois_fpn4", "rois_fpn5",
+              "rois_idx_restore_int32"):
+        assert np.array_equal(blobs[k].cpu().numpy(), g["blob_" + k]), k
+    assert_targets_close(blobs["bbox_targets"].cpu().numpy(), g["blob_bbox_targets"])
+    op.eval()
+    assert "labels_int32" not in op(inputs)                                   # inference path unchanged
