@@ -406,7 +406,7 @@ int b200_roi_align_forward_fpn(int num_levels, const float* const* bottom_data_h
                                const float* spatial_scales_host, const int* level_roi_begin_host, int batch_size, int num_rois,
                                int channels, int aligned_height, int aligned_width, int sampling_ratio, const float* bottom_rois,
                                const int* top_rows, float* top_data, void* workspace, size_t workspace_bytes, b200_stream_t stream) {
-    if (num_levels < 1 || !bottom_data_host || !heights_host || !widths_host || !spatial_scales_host || !level_roi_begin_host)
+    if (num_levels < 1 || num_levels > 6 || !bottom_data_host || !heights_host || !widths_host || !spatial_scales_host || !level_roi_begin_host)
         return B200_ROI_EINVAL;
     if (batch_size <= 0 || num_rois <= 0 || channels <= 0 || aligned_height <= 0 || aligned_width <= 0 || !bottom_rois || !top_data)
         return B200_ROI_EINVAL;
@@ -414,16 +414,30 @@ int b200_roi_align_forward_fpn(int num_levels, const float* const* bottom_data_h
     for (int l = 0; l < num_levels; ++l)
         if (!bottom_data_host[l] || level_roi_begin_host[l + 1] < level_roi_begin_host[l]) return B200_ROI_EINVAL;
     int rc = 1000;
-    if (forward_path_mode() != 3)
-        rc = roi_align_forward_strip_fpn(num_levels, bottom_data_host, heights_host, widths_host, spatial_scales_host,
-                                         level_roi_begin_host, batch_size, num_rois, channels, aligned_height, aligned_width,
-                                         sampling_ratio, bottom_rois, top_data, top_rows, workspace, workspace_bytes,
-                                         (cudaStream_t)stream);
-    if (rc == 1000)
-        rc = roi_align_forward_stream_fpn(num_levels, bottom_data_host, heights_host, widths_host, spatial_scales_host,
-                                          level_roi_begin_host, batch_size, num_rois, channels, aligned_height, aligned_width,
-                                          sampling_ratio, bottom_rois, top_data, top_rows, workspace, workspace_bytes,
-                                          (cudaStream_t)stream);
+    if (forward_path_mode() != 3) {
+        // Levels that TMA can stage (W % 4 == 0, 16-byte aligned base) and levels that need the cp.async producers (FPN P5 of an
+        // 800 x 1333 image: W = 42) go to separate launch sequences: runs of consecutive levels of the same kind, each over its
+        // own contiguous range of the level-major RoIs.  The workspace is reused (stream order).
+        const int bins = aligned_height * aligned_width;
+        int l0 = 0;
+        rc = B200_ROI_OK;
+        while (l0 < num_levels && rc == B200_ROI_OK) {
+            auto tma_ok = [&](int l) { return (widths_host[l] & 3) == 0 && ((uintptr_t)bottom_data_host[l] & 15u) == 0; };
+            int l1 = l0 + 1;
+            while (l1 < num_levels && tma_ok(l1) == tma_ok(l0)) ++l1;
+            const int r0 = level_roi_begin_host[l0], r1 = level_roi_begin_host[l1];
+            if (r1 > r0) {
+                int begin[8];
+                for (int l = l0; l <= l1; ++l) begin[l - l0] = level_roi_begin_host[l] - r0;
+                rc = roi_align_forward_strip_fpn(l1 - l0, bottom_data_host + l0, heights_host + l0, widths_host + l0, spatial_scales_host + l0,
+                                                 begin, batch_size, r1 - r0, channels, aligned_height, aligned_width, sampling_ratio,
+                                                 bottom_rois + (size_t)5 * r0, top_rows ? top_data : top_data + (size_t)r0 * channels * bins,
+                                                 top_rows ? top_rows + r0 : nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+            }
+            l0 = l1;
+        }
+        if (rc != B200_ROI_OK && rc != 1000) return rc;
+    }
     return rc == 1000 ? B200_ROI_EWORKSPACE : rc;
 }
 

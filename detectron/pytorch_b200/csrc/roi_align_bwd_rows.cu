@@ -25,8 +25,10 @@
 //                                way out.
 //
 // Numerics: per tap the term is (dY / count) * (wy * wx) with count = sr^2 in {1, 4}: the division is an exact
-// scaling, so the term equals the reference's FMUL(dY, w) / count bit for bit (barring underflow); only the order
-// of the additions differs, as it does between two runs of the reference's atomicAdd.
+// scaling, so each addend equals the reference's FMUL(dY, w) / count up to the fused multiply-add's single rounding (the
+// product is not rounded separately inside fma2); the order of the additions differs as well, as it does between two runs of
+// the reference's atomicAdd.  Measured against the fp64 oracle: no further off than the reference kernel itself
+// (profiles/r04i_parity_spread.json).
 //
 // Semantics: lib/modeling/roi_xfrom/roi_align/src/roi_align_kernel.cu (reference) :150-193, :195-270.
 #include "roi_align_tiled.cuh"
@@ -179,7 +181,7 @@ template <int CPL> __host__ __device__ constexpr int rows_acc_bytes() {         
 template <int CPL, int NX> __host__ __device__ constexpr int rows_warp_smem() { return rows_acc_bytes<CPL>() + 2 * rows_stage_bytes<NX>(); }
 
 template <int PW, int SR, int CPL, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (CPL == 2) ? 2 : 1)
+__global__ void __launch_bounds__(WARPS * 32, (CPL == 2 && PW == 7) ? 2 : 1)     // PW = 14: ~117 KB per CTA, a second CTA never fits
 roi_align_bwd_rows(const BwdRoi* __restrict__ roi_in, const AxisEntry* __restrict__ xtab, int* __restrict__ zeroed,
                    const uint2* __restrict__ row_list, int row_cap, const uint4* __restrict__ ovf, const float* __restrict__ dyt,
                    float* __restrict__ dx, int N, int C, int H, int W, int PH, int tiles_x) {
