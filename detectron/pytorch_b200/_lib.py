@@ -69,6 +69,10 @@ _SIGNATURES = {
     # (top, top_counts_host, all, all_counts_host, P, thresh, scoring, beta, out, stream)
     "b200_box_voting_batched": (ctypes.c_int, [_c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
                                                ctypes.c_int, ctypes.c_float, _c_float_p, _stream_t]),
+    "b200_topk_batched_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    # (score_ptrs_host, A_host, HW_host, k_host, P, order_out, scores_out, workspace, workspace_bytes, stream)
+    "b200_topk_batched": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                         _c_float_p, ctypes.c_void_p, ctypes.c_size_t, _stream_t]),
     # (boxes, N, query, K, out, stream)
     "b200_bbox_overlaps": (ctypes.c_int, [_c_float_p, ctypes.c_int, _c_float_p, ctypes.c_int, _c_float_p, _stream_t]),
     # (boxes, N, gt, gt_classes, G, max_overlaps, argmax, max_classes, stream)

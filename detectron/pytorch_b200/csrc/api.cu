@@ -64,6 +64,8 @@ int roi_align_forward_strip_fpn(int, const float* const*, const int*, const int*
 int roi_align_forward_strip(const float*, float, int, int, int, int, int, int, int, int, const float*, float*, const int*, void*, size_t, cudaStream_t);
 void roi_align_strip_set_debug_buffer(unsigned long long*);
 
+size_t topk_batched_workspace_bytes(int);
+int topk_batched(const float* const*, const int*, const int*, const int*, int, long long*, float*, void*, size_t, cudaStream_t);
 int bbox_overlaps(const float*, int, const float*, int, float*, cudaStream_t);
 int roi_assign(const float*, int, const float*, const int*, int, float*, int*, int*, cudaStream_t);
 int roi_select(const float*, int, float, float, float, int*, int*, int*, cudaStream_t);
@@ -476,6 +478,23 @@ int b200_box_voting_batched(const float* top_dets_dev, const int* top_counts_hos
     if (scoring_method < 0 || scoring_method > 5) return B200_ROI_EINVAL;
     return box_voting_batched(top_dets_dev, top_counts_host, all_dets_dev, all_counts_host, num_problems, thresh, scoring_method, beta, out_dev,
                               (cudaStream_t)stream);
+}
+
+size_t b200_topk_batched_workspace_bytes(int num_problems) { return topk_batched_workspace_bytes(num_problems); }
+
+int b200_topk_batched(const float* const* scores_dev_ptrs_host, const int* num_anchors_host, const int* num_cells_host, const int* k_host,
+                      int num_problems, long long* order_out_dev, float* scores_out_dev, void* workspace, size_t workspace_bytes,
+                      b200_stream_t stream) {
+    if (num_problems < 1 || !scores_dev_ptrs_host || !num_anchors_host || !num_cells_host || !k_host) return B200_ROI_EINVAL;
+    long long total = 0;
+    for (int p = 0; p < num_problems && p < 64; ++p) {
+        if (!scores_dev_ptrs_host[p] || k_host[p] < 0) return B200_ROI_EINVAL;
+        total += k_host[p];
+    }
+    if (total > 0 && (!order_out_dev || !scores_out_dev)) return B200_ROI_EINVAL;
+    const int rc = topk_batched(scores_dev_ptrs_host, num_anchors_host, num_cells_host, k_host, num_problems, order_out_dev, scores_out_dev,
+                                workspace, workspace_bytes, (cudaStream_t)stream);
+    return rc == 1000 ? B200_ROI_EWORKSPACE : rc;
 }
 
 int b200_bbox_overlaps(const float* boxes_dev, int num_boxes, const float* query_boxes_dev, int num_query, float* overlaps_out_dev,

@@ -6,16 +6,18 @@ ndarray (R, 1))`.  The reference copies the score map, the deltas and im_info to
 generate_proposals.py:58-63), runs a 200 k-anchor numpy top-k, decode, clip, filter and the Cython NMS on one CPU
 thread, and the caller copies the RoIs back.  Here everything up to the final result stays on the device:
 
-    torch.topk / torch.sort (stable)  ->  b200_proposal_decode (anchor rebuild + bbox_transform + clip + filter, one
-    kernel)  ->  b200_nms (bitmask + on-device scan)  ->  ONE D2H of the kept rows per image
+    b200_topk_batched (radix select + in-CTA sort over every (level, image) score map of the step, read in place)  ->
+    b200_proposal_decode (anchor rebuild + bbox_transform + clip + filter, one kernel)  ->  b200_nms_batched (bitmask +
+    on-device scan)  ->  ONE D2H of the kept rows per image
+(torch.topk / torch.sort remain only as the fallback for k > 16384 candidates per map.)
 
 Configuration: the reference reads `cfg[TRAIN|TEST].RPN_{PRE,POST}_NMS_TOP_N, RPN_NMS_THRESH, RPN_MIN_SIZE` from its
 global config at call time; pass that object as `cfg=` to do the same, or give the four values per mode as keyword
 arguments (`train=dict(...)`, `test=dict(...)`); defaults are the reference's (lib/core/config.py:127-141, 200-214).
 
-Documented differences (see oracle/proposals.py): the order of EQUAL scores is unspecified, as in the reference
-(its argpartition/argsort, our torch.topk; only the full stable sort taken when pre_nms_topN covers every anchor orders
-ties by ascending (h, w, a) index), and NMS suppresses at IoU > thresh with the CUDA kernel's rounding (the reference's
+Documented differences (see oracle/proposals.py): the reference leaves the order of EQUAL scores unspecified (its
+argpartition/argsort); here they come out in ascending (h, w, a) index (which of several scores equal to the k-th survive the
+cut is decided in memory order), and NMS suppresses at IoU > thresh with the CUDA kernel's rounding (the reference's
 host NMS uses >=); results on the golden vectors are identical.  All images of a call -- and, through
 generate_proposals_batched, all FPN levels of a step -- share ONE batched NMS launch pair and ONE host read.
 """
@@ -61,8 +63,9 @@ class GenerateProposalsOp(nn.Module):
         device).  Returns numpy arrays like the reference: rois (R, 5) [batch, x1, y1, x2, y2], roi_probs (R, 1)."""
         return generate_proposals_batched([self], [rpn_cls_prob], [rpn_bbox_pred], im_info)[0]
 
-    def _decode_images(self, rpn_cls_prob, rpn_bbox_pred, info):
-        """top-k + decode for every image of this level: list of (dets (k, 5), valid (k,)) CUDA tensors, nothing synchronised."""
+    def _decode_images(self, rpn_cls_prob, rpn_bbox_pred, info, ranked=None):
+        """top-k + decode for every image of this level: list of (dets (k, 5), valid (k,)) CUDA tensors, nothing synchronised.
+        ranked: per image (order, top_scores) already selected by the batched device top-k (generate_proposals_batched)."""
         if not rpn_cls_prob.is_cuda:
             raise NotImplementedError("GenerateProposalsOp (B200) needs CUDA tensors; the host path is the reference's own")
         A = rpn_cls_prob.size(1)
@@ -72,19 +75,30 @@ class GenerateProposalsOp(nn.Module):
         scores = rpn_cls_prob.detach().float()
         deltas = rpn_bbox_pred.detach().float().contiguous()
         pre, post, thresh, min_size = self._mode_params()
-        return [self.proposals_for_one_image(info[i], deltas[i], scores[i], pre, post, thresh, min_size, run_nms=False)[:2]
+        return [self.proposals_for_one_image(info[i], deltas[i], scores[i], pre, post, thresh, min_size, run_nms=False,
+                                             ranked=None if ranked is None else ranked[i])[:2]
                 for i in range(scores.size(0))]
 
-    def proposals_for_one_image(self, im_info, bbox_deltas, scores, pre_nms_topN, post_nms_topN, nms_thresh, min_size, run_nms=True):
+    def num_candidates(self, A, H, W):
+        """How many candidates survive the pre-NMS top-k for an (A, H, W) score map in the current mode."""
+        pre = self._mode_params()[0]
+        total = A * H * W
+        return total if (pre <= 0 or pre >= total) else int(pre)
+
+    def proposals_for_one_image(self, im_info, bbox_deltas, scores, pre_nms_topN, post_nms_topN, nms_thresh, min_size, run_nms=True,
+                                ranked=None):
         """Device part for one image: returns (dets (k, 5), valid (k), keep indices, number kept) as CUDA tensors."""
         A, H, W = scores.shape
         dev = scores.device
-        flat = scores.permute(1, 2, 0).reshape(-1)                                  # (H, W, A) order, as the reference enumerates anchors
-        total = flat.numel()
-        if pre_nms_topN <= 0 or pre_nms_topN >= total:
-            top_scores, order = torch.sort(flat, descending=True, stable=True)
-        else:
-            top_scores, order = torch.topk(flat, int(pre_nms_topN), largest=True, sorted=True)
+        total = A * H * W
+        if ranked is not None:
+            order, top_scores = ranked
+        else:                                                                       # library fallback: k beyond the device top-k's 16384
+            flat = scores.permute(1, 2, 0).reshape(-1)                              # (H, W, A) order, as the reference enumerates anchors
+            if pre_nms_topN <= 0 or pre_nms_topN >= total:
+                top_scores, order = torch.sort(flat, descending=True, stable=True)
+            else:
+                top_scores, order = torch.topk(flat, int(pre_nms_topN), largest=True, sorted=True)
         k = int(order.numel())
         dets = torch.empty((k, 5), dtype=torch.float32, device=dev)
         valid = torch.empty((k,), dtype=torch.int32, device=dev)
@@ -111,7 +125,25 @@ def generate_proposals_batched(op_list, cls_probs, bbox_preds, im_info):
     Returns [(rois, roi_probs)] per level, exactly what op_list[l](cls_probs[l], bbox_preds[l], im_info) returns (numpy
     arrays, or CUDA tensors for ops built with return_tensors=True)."""
     info = im_info.detach().cpu().numpy().astype(np.float32) if torch.is_tensor(im_info) else np.asarray(im_info, np.float32)
-    per_level = [op._decode_images(p, d, info) for op, p, d in zip(op_list, cls_probs, bbox_preds)]
+    # ONE batched device top-k (b200_topk_batched) over every (level, image) score map whose k fits its limits
+    ranked = [None] * len(op_list)
+    problems = []
+    for l, (op, p) in enumerate(zip(op_list, cls_probs)):
+        if p.is_cuda and p.dim() == 4:
+            k = op.num_candidates(p.size(1), p.size(2), p.size(3))
+            if 0 < k <= ops.TOPK_MAX_K:
+                problems.extend((l, i, k) for i in range(p.size(0)))
+    for c0 in range(0, len(problems), ops.TOPK_MAX_PROBLEMS):
+        chunk = problems[c0:c0 + ops.TOPK_MAX_PROBLEMS]
+        maps = [cls_probs[l][i].detach().float() for l, i, _ in chunk]
+        order, top = ops.topk_batched_raw(maps, [k for _, _, k in chunk])
+        off = 0
+        for l, i, k in chunk:
+            if ranked[l] is None:
+                ranked[l] = [None] * cls_probs[l].size(0)
+            ranked[l][i] = (order[off:off + k], top[off:off + k])
+            off += k
+    per_level = [op._decode_images(p, d, info, ranked=r) for op, p, d, r in zip(op_list, cls_probs, bbox_preds, ranked)]
     params = [op._mode_params() for op in op_list]
     # problems that go through NMS, grouped by threshold (one batched call per distinct threshold; normally one)
     keep_of = {}

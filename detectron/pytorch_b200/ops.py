@@ -352,6 +352,43 @@ class _RoICrop(Function):
 # ------------------------------------------------------------------------------------------------
 # NMS
 # ------------------------------------------------------------------------------------------------
+TOPK_MAX_K = 16384
+TOPK_MAX_PROBLEMS = 64
+
+
+def topk_batched_raw(score_maps, ks):
+    """Top-k of several (A, H, W) float32 CUDA score maps in one batched call (b200_topk_batched: radix select + in-CTA sort,
+    no host read).  ks: host ints, k_p <= min(A*H*W, 16384); <= 64 problems.  Returns (order int64 (sum k,), scores float32
+    (sum k,)): problem p's slice holds, best first, the indices into its (H, W, A) flattening and the scores."""
+    import ctypes
+    P = len(score_maps)
+    if P < 1 or P > TOPK_MAX_PROBLEMS or len(ks) != P:
+        raise ValueError("topk_batched_raw: 1..64 problems with one k each")
+    maps = []
+    for m in score_maps:
+        _need_cuda_f32(m, "score map")
+        if m.dim() != 3:
+            raise ValueError("score maps must be (A, H, W), got %s" % (tuple(m.shape),))
+        maps.append(m.contiguous())
+    ks = [int(k) for k in ks]
+    dev = maps[0].device
+    total = sum(ks)
+    order = torch.empty((max(total, 1),), dtype=torch.int64, device=dev)
+    scores = torch.empty((max(total, 1),), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    ptrs = (ctypes.c_void_p * P)(*[m.data_ptr() for m in maps])
+    A = (ctypes.c_int * P)(*[m.size(0) for m in maps])
+    HW = (ctypes.c_int * P)(*[m.size(1) * m.size(2) for m in maps])
+    K = (ctypes.c_int * P)(*ks)
+    ws_bytes = int(lib.b200_topk_batched_workspace_bytes(P))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.b200_topk_batched(ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(A, ctypes.c_void_p), ctypes.cast(HW, ctypes.c_void_p),
+                                         ctypes.cast(K, ctypes.c_void_p), P, order.data_ptr(), scores.data_ptr(), ws.data_ptr(), ws_bytes,
+                                         _stream()), "b200_topk_batched")
+    return order[:total], scores[:total]
+
+
 def nms_batched_raw(dets, counts, thresh):
     """`len(counts)` independent NMS problems in one pair of launches.  dets: (sum(counts), >=4) rows of the problems back to
     back, each problem score-sorted; counts: host ints.  Returns (keep int32 (sum(counts),), num_out int32 (P,)) on the

@@ -234,6 +234,19 @@ B200_API int b200_proposal_decode(const float* bbox_deltas, const float* anchors
                          int num_candidates, int num_anchors, int height, int width, float feat_stride, float im_height,
                          float im_width, float min_size, float* dets_out, int* valid_out, b200_stream_t stream);
 
+/* ---- batched top-k of RPN score maps ----------------------------------------------------------
+ * replaces np.argpartition + np.argsort of lib/modeling/generate_proposals.py:118-131 (and the torch.topk / torch.sort the
+ * first device version used): problem p is one (A_p, H_p * W_p) float32 score map on the device, read where it lies;
+ * order_out receives, best first, the k_p indices into its (H, W, A) flattening (what b200_proposal_decode takes as
+ * `order`), scores_out the scores; problems are stored back to back.  <= 64 problems, k_p <= 16384 (else
+ * B200_ROI_EWORKSPACE: the caller sorts by other means).  Equal scores come out in ascending index; which of several
+ * scores EQUAL TO THE k-th are taken is deterministic (memory order), the reference leaves it unspecified.
+ * Radix select (3 histogram launches, chunk-parallel) + one collect-and-sort launch; no host read. */
+B200_API size_t b200_topk_batched_workspace_bytes(int num_problems);
+B200_API int b200_topk_batched(const float* const* scores_dev_ptrs_host, const int* num_anchors_host, const int* num_cells_host,
+                               const int* k_host, int num_problems, long long* order_out_dev, float* scores_out_dev, void* workspace,
+                               size_t workspace_bytes, b200_stream_t stream);
+
 /* ---- RoI label / regression-target generation on the device ---------------------------------
  * The per-image host work of the reference's training data path, for proposals that already live on the GPU.  Boxes are
  * float32 (x1, y1, x2, y2) rows in image pixels, exactly the roidb's `boxes`.

@@ -110,3 +110,33 @@ def test_collect_and_distribute_training_branch_vs_reference_op():
     assert_targets_close(blobs["bbox_targets"].cpu().numpy(), g["blob_bbox_targets"])
     op.eval()
     assert "labels_int32" not in op(inputs)                                   # inference path unchanged
+
+
+def test_topk_batched_vs_torch():
+    """b200_topk_batched (radix select + in-CTA sort) against torch.topk / a stable sort: several problems of different shapes in
+    one call, unique scores (indices must agree), heavy ties (values must agree, equal scores in ascending (h, w, a) index), k = n."""
+    from detectron.pytorch_b200 import ops
+    rng = np.random.RandomState(0)
+    shapes = [(3, 200, 336), (3, 100, 168), (15, 50, 84), (3, 13, 21), (1, 7, 9)]
+    ks = [2000, 2000, 12000, 3 * 13 * 21, 10]
+    maps = []
+    for (A, H, W) in shapes:
+        n = A * H * W
+        maps.append(dev(((rng.permutation(n) + 0.5) / n).astype(np.float32).reshape(A, H, W) * 2 - 1))       # unique, both signs
+    order, top = ops.topk_batched_raw(maps, ks)
+    off = 0
+    for m, k in zip(maps, ks):
+        flat = m.permute(1, 2, 0).reshape(-1)
+        ref_v, ref_i = torch.topk(flat, k, largest=True, sorted=True)
+        assert torch.equal(top[off:off + k], ref_v)
+        assert torch.equal(order[off:off + k], ref_i)
+        off += k
+    # ties: few distinct values
+    tie = dev(rng.randint(0, 7, (3, 40, 50)).astype(np.float32) / 7)
+    o, v = ops.topk_batched_raw([tie], [1500])
+    flat = tie.permute(1, 2, 0).reshape(-1)
+    assert torch.equal(v, torch.topk(flat, 1500).values)
+    assert torch.equal(flat[o], v)
+    same = v[1:] == v[:-1]
+    assert bool((o[1:][same] > o[:-1][same]).all())                   # equal scores: ascending index
+    assert o.unique().numel() == 1500
