@@ -109,6 +109,30 @@ def test_workspace_sizing_is_host_arithmetic(lib_option):
     assert lib.b200_roi_align_backward_ws(None, 0.25, 1, 4, 10, -1, 3, 7, 7, 2, None, None, None, 0, None) == -1
 
 
+def test_round2_entry_points_validate_arguments_without_gpu():
+    """Top-k, RoI targets, FPN forward: argument errors are reported before any CUDA call; workspace sizing is host arithmetic."""
+    lib = _lib.load()
+    EINVAL = -1
+    assert lib.b200_topk_batched_workspace_bytes(10) == 10 * 3 * 2048 * 4
+    assert lib.b200_topk_batched_workspace_bytes(0) == 0 and lib.b200_topk_batched_workspace_bytes(65) == 0
+    assert lib.b200_topk_batched(None, None, None, None, 3, None, None, None, 0, None) == EINVAL
+    assert lib.b200_bbox_overlaps(None, 5, None, 4, None, None) == EINVAL
+    assert lib.b200_bbox_overlaps(None, 0, None, 4, None, None) == 0                       # nothing to do
+    assert lib.b200_roi_assign(None, 3, None, None, 0, None, None, None, None) == EINVAL
+    assert lib.b200_roi_select(None, 5, ctypes.c_float(0.5), ctypes.c_float(0.5), ctypes.c_float(0.0), None, None, None, None) == EINVAL
+    w4 = (ctypes.c_float * 4)(10, 10, 5, 5)
+    assert lib.b200_fast_rcnn_targets(None, None, None, None, None, 4, 5, ctypes.cast(w4, ctypes.c_void_p), 81, 0, ctypes.c_float(1.0),
+                                      ctypes.c_float(0.0), None, None, None, None, None, None) == EINVAL      # num_fg > num_keep
+    # FPN workspace: the whole pyramid of an 800 x 1333 image (P5 is 25 x 42: staged by cp.async, P2..P4 by TMA)
+    H = (ctypes.c_int * 4)(200, 100, 50, 25); W = (ctypes.c_int * 4)(336, 168, 84, 42)
+    wf = lib.b200_roi_align_fpn_workspace_bytes(4, ctypes.cast(H, ctypes.c_void_p), ctypes.cast(W, ctypes.c_void_p), 2, 1000, 7, 7, 2)
+    assert wf > 1000 * 28 * 16 and wf % 256 == 0
+    assert lib.b200_roi_align_forward_fpn(7, None, None, None, None, None, 2, 1000, 256, 7, 7, 2, None, None, None, None, 0, None) == EINVAL
+    # single-map workspace covers the quad-strip path's tables, CSR records and temporary records
+    w = lib.b200_roi_align_workspace_bytes(1, 512, 200, 272, 7, 7, 2)
+    assert w >= 512 * 28 * 16 + 512 * 196 * 24
+
+
 def test_product_package_never_imports_oracle():
     pkg = os.path.join(ROOT, "detectron")
     for dirpath, _, files in os.walk(pkg):
