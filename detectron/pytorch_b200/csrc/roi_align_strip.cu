@@ -87,6 +87,7 @@ struct StripGeom {
     int SX, WX, K, cell;                                      // columns per slot (8 XO), strip core width, ring depth, bytes per cell
     int L, Q, keys, G, pieces, max_entries, cap_r;            // cap_r: fragments one RoI can have at most
     unsigned row_cost;
+    int stop_after;                                           // timing probe (B200_STREAM_PHASES=1|2): the prepass returns after that phase
     StripLevel lv[kMaxLevels];
     int colstart[kMaxCols + 1];
 };
@@ -268,6 +269,7 @@ strip_prep(const float* __restrict__ rois, StripGeom g, StripWs ws, float* __res
         }
         if (t == 0) ws.tmpcnt[r] = batch_ok ? n : -1;
     }
+    if (g.stop_after == 1) return;
     // ---- grid barrier (the grid is sized to be resident: see the launcher)
     __syncthreads();
     if (t == 0) {
@@ -322,11 +324,12 @@ strip_prep(const float* __restrict__ rois, StripGeom g, StripWs ws, float* __res
     __syncthreads();
     // row pointers for the main kernel: every CTA writes a slice
     for (int k = blockIdx.x * kPrepThreads + t; k <= keys; k += gridDim.x * kPrepThreads) ws.rowptr[k] = (int)s_pre[k];
-    // piece boundaries (CTA 0): piece p starts where the cumulative cost over the linear order (column, group, row) reaches p / pieces
-    if (blockIdx.x == 0) {
+    // piece boundaries: piece p starts where the cumulative cost over the linear order (column, group, row) reaches p / pieces.
+    // Every CTA holds the whole prefix, so the boundaries are spread over the grid (one per CTA, thread 0) instead of queueing in one
+    if (t == 0) {
         const unsigned total = s_cpre[keys];
         const u64 grand = (u64)total * (u64)g.G;
-        for (int p = t; p <= g.pieces; p += kPrepThreads) {
+        for (int p = blockIdx.x; p <= g.pieces; p += gridDim.x) {
             int L;
             if (p == 0) L = 0;
             else if (p == g.pieces) L = g.G * g.keys;
@@ -355,6 +358,7 @@ strip_prep(const float* __restrict__ rois, StripGeom g, StripWs ws, float* __res
             ws.piece_start[p] = L;
         }
     }
+    if (g.stop_after == 2) return;
     // ---- phase 3: fragment records into the CSR (position = row pointer + rank); zero-fill of the elements that are
     // accumulated with red.add (the bins of the fragments that hold a split bin's first sample)
     const int bins = g.PH * g.PW;
@@ -1018,6 +1022,7 @@ bool strip_geometry(int levels, const float* const* bottoms, const int* heights,
     g->cap_r = PH * PW * sr * sr;                              // worst case: every sample its own fragment
     g->max_entries = R * g->cap_r;
     g->row_cost = 44u;
+    g->stop_after = 0;
     size_t off = 0;
     lay->ytab_off = off; off = align_up_sz(off + (size_t)R * g->ny * 16, 256);
     lay->xtab_off = off; off = align_up_sz(off + (size_t)R * g->nx * 16, 256);
@@ -1137,6 +1142,7 @@ int roi_align_forward_strip_fpn(int levels, const float* const* bottoms, const i
     if (workspace_bytes < lay.ws_bytes) return 1000;
     const int rc_opt = option_get(kOptStripRowCost);
     if (rc_opt >= '0' && rc_opt <= '9') g.row_cost = 8u * (unsigned)(rc_opt - '0') + 4u;      // B200_STRIP_ROWCOST=0..9 (tuning)
+    if (option_get(kOptStreamPhases) == '1') g.stop_after = 1; else if (option_get(kOptStreamPhases) == '2') g.stop_after = 2;
     unsigned char* wsb = (unsigned char*)workspace;
     StripWs ws;
     ws.ytab = (uint4*)(wsb + lay.ytab_off);
@@ -1163,7 +1169,7 @@ int roi_align_forward_strip_fpn(int levels, const float* const* bottoms, const i
     if (err != cudaSuccess) return (int)err;
     if (sr == 1) strip_prep<1><<<prep_grid, kPrepThreads, prep_dyn, stream>>>(rois, g, ws, top, row_map);
     else         strip_prep<2><<<prep_grid, kPrepThreads, prep_dyn, stream>>>(rois, g, ws, top, row_map);
-    if (option_get(kOptStreamPhases) == 'p') return finish_launch(1);          // timing probe: prepass only (output undefined)
+    if (option_get(kOptStreamPhases) == 'p' || g.stop_after) return finish_launch(1);          // timing probe: prepass only (output undefined)
 
     StripArgs a;
     a.ytab = ws.ytab; a.xtab = ws.xtab; a.entries = ws.entries; a.rowptr = ws.rowptr; a.maxend = ws.maxend;

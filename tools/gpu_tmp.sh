@@ -1,3 +1,14 @@
-timeout 300 python -m pytest tests/test_gpu_targets.py -m gpu -q -p no:cacheprovider -k "topk" 2>&1 | tail -8
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k "proposal or device_chain" 2>&1 | tail -5
-echo "== proposals probe"; timeout 300 python tools/proposals_probe.py 2>&1 | tail -8
+mkdir -p gpurun_out/r04k
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r04k/prep.csv python tools/prep_probe.py > /dev/null 2>&1
+python - <<'PY'
+import csv
+rows=[r for r in csv.reader(open("gpurun_out/r04k/prep.csv")) if len(r)>5]
+hdr=None; v=[]
+for r in rows:
+    if r[0]=="ID": hdr=r; continue
+    if hdr is None: continue
+    d=dict(zip(hdr,r))
+    if "strip_prep" in d["Kernel Name"]: v.append(float(d["Metric Value"].replace(",",""))/1e3)
+print("strip_prep durations (us), 6 per phase setting [after phase 1 | after barrier+scan | whole]:")
+for i in range(0,len(v),6): print("  ", ["%.1f"%x for x in v[i:i+6]])
+PY
