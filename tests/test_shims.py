@@ -37,7 +37,8 @@ def test_reference_import_paths_and_signatures():
         from model.roi_crop.functions.gridgen import AffineGridGenFunction                       # helpers of the RoICrop mode
         from model.roi_crop.modules.gridgen import _AffineGridGen
         from model.roi_crop.functions.crop_resize import RoICropFunction as CropResize
-        assert CropResize is RoICropFunction and _AffineGridGen(3, 4).f.height == 3 and AffineGridGenFunction(3, 4).width == 4
+        assert issubclass(CropResize, RoICropFunction) and CropResize().device == -1          # the reference's second RoICrop front end (records its device)
+        assert _AffineGridGen(3, 4).f.height == 3 and AffineGridGenFunction(3, 4).width == 4
         assert "modeling.generate_proposals" not in sys.modules                                  # opt-in only
         pkg.install_reference_aliases(proposals=True)
         from modeling.generate_proposals import GenerateProposalsOp
