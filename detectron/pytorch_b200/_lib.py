@@ -47,6 +47,10 @@ _SIGNATURES = {
     "b200_roi_crop_forward": (ctypes.c_int, [_c_float_p, _c_float_p] + [ctypes.c_int] * 7 + [_c_float_p, _stream_t]),
     # (grad_output, grids, N, C, H, W, R, oh, ow, grad_image, grad_grids, stream)
     "b200_roi_crop_backward": (ctypes.c_int, [_c_float_p, _c_float_p] + [ctypes.c_int] * 7 + [_c_float_p, _c_float_p, _stream_t]),
+    "b200_roi_crop_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 7),
+    # (grad_output, grids, N, C, H, W, R, oh, ow, grad_image, grad_grids, workspace, workspace_bytes, stream)
+    "b200_roi_crop_backward_ws": (ctypes.c_int, [_c_float_p, _c_float_p] + [ctypes.c_int] * 7 + [_c_float_p, _c_float_p, ctypes.c_void_p,
+                                                                                              ctypes.c_size_t, _stream_t]),
     # (deltas, anchors, order, scores, k, A, H, W, stride, im_h, im_w, min_size, dets, valid, stream)
     "b200_proposal_decode": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p, _c_float_p] + [ctypes.c_int] * 4 +
                              [ctypes.c_float] * 4 + [_c_float_p, ctypes.c_void_p, _stream_t]),

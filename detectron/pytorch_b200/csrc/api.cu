@@ -44,7 +44,8 @@ int roi_align_legacy_backward(const float*, float, int, int, int, int, int, int,
 int roi_pool_forward(const float*, float, int, int, int, int, int, int, int, const float*, float*, int*, cudaStream_t);
 int roi_pool_backward(const float*, float, int, int, int, int, int, int, int, const float*, float*, const int*, cudaStream_t);
 int roi_crop_forward(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
-int roi_crop_backward(const float*, const float*, int, int, int, int, int, int, int, float*, float*, cudaStream_t);
+int roi_crop_backward(const float*, const float*, int, int, int, int, int, int, int, float*, float*, void*, size_t, cudaStream_t);
+size_t roi_crop_backward_workspace_bytes(int, int, int, int, int, int, int);
 size_t nms_workspace_bytes(int);
 int proposal_decode(const float*, const float*, const long long*, const float*, int, int, int, int, float, float, float, float, float*, int*, cudaStream_t);
 size_t roi_align_tiled_workspace_bytes(int, int, int, int, int, int, int);
@@ -380,7 +381,25 @@ int b200_roi_crop_backward(const float* grad_output, const float* grids, int bat
     if (!grad_image) return B200_ROI_EINVAL;
     if ((size_t)num_rois * out_height * out_width > 0 && (!grad_output || !grids)) return B200_ROI_EINVAL;
     return roi_crop_backward(grad_output, grids, batch_size, channels, height, width, num_rois, out_height, out_width,
-                             grad_image, grad_grids, (cudaStream_t)stream);
+                             grad_image, grad_grids, nullptr, 0, (cudaStream_t)stream);
+}
+
+size_t b200_roi_crop_backward_workspace_bytes(int batch_size, int channels, int height, int width, int num_rois, int out_height,
+                                              int out_width) {
+    if (batch_size <= 0 || channels <= 0 || height <= 0 || width <= 0 || num_rois <= 0 || out_height <= 0 || out_width <= 0) return 0;
+    return roi_crop_backward_workspace_bytes(batch_size, channels, height, width, num_rois, out_height, out_width);
+}
+
+int b200_roi_crop_backward_ws(const float* grad_output, const float* grids, int batch_size, int channels, int height, int width,
+                              int num_rois, int out_height, int out_width, float* grad_image, float* grad_grids, void* workspace,
+                              size_t workspace_bytes, b200_stream_t stream) {
+    if (batch_size < 0 || channels < 0 || height <= 0 || width <= 0 || num_rois < 0 || out_height < 0 || out_width < 0)
+        return B200_ROI_EINVAL;
+    if ((size_t)batch_size * channels == 0) return B200_ROI_OK;
+    if (!grad_image) return B200_ROI_EINVAL;
+    if ((size_t)num_rois * out_height * out_width > 0 && (!grad_output || !grids)) return B200_ROI_EINVAL;
+    return roi_crop_backward(grad_output, grids, batch_size, channels, height, width, num_rois, out_height, out_width,
+                             grad_image, grad_grids, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t b200_nms_workspace_bytes(int boxes_num) { return nms_workspace_bytes(boxes_num); }

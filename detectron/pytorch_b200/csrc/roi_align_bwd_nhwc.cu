@@ -132,6 +132,12 @@ nhwc_to_nchw_kernel(const float* __restrict__ scratch, float* __restrict__ dx, i
     }
 }
 
+// shared with the RoICrop backward (roi_crop.cu)
+void launch_nhwc_to_nchw(const float* scratch, float* dx, int N, int C, int HW, cudaStream_t stream) {
+    dim3 tgrid((HW + 31) / 32, (C + 31) / 32, N);
+    nhwc_to_nchw_kernel<<<tgrid, 256, 0, stream>>>(scratch, dx, C, HW);
+}
+
 size_t roi_align_bwd_nhwc_workspace_bytes(int N, int C, int H, int W) {
     return ((size_t)N * C * H * W * sizeof(float) + 255) / 256 * 256;
 }

@@ -327,10 +327,14 @@ def roi_crop_backward(grad_output, input2, input1_size):
     R, oh, ow, _ = input2.shape
     grad_input1 = torch.empty((N, C, H, W), dtype=torch.float32, device=grad_output.device)
     grad_input2 = torch.empty_like(input2)
+    lib = _lib.load()
+    ws_bytes = int(lib.b200_roi_crop_backward_workspace_bytes(N, C, H, W, R, oh, ow))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=grad_output.device) if ws_bytes else None
     with torch.cuda.device(grad_output.device):
-        _lib.check(_lib.load().b200_roi_crop_backward(grad_output.data_ptr(), input2.data_ptr(), N, C, H, W, R, oh, ow,
-                                                      grad_input1.data_ptr(), grad_input2.data_ptr(), _stream()),
-                   "b200_roi_crop_backward")
+        _lib.check(lib.b200_roi_crop_backward_ws(grad_output.data_ptr(), input2.data_ptr(), N, C, H, W, R, oh, ow,
+                                                 grad_input1.data_ptr(), grad_input2.data_ptr(),
+                                                 ws.data_ptr() if ws is not None else None, ws_bytes, _stream()),
+                   "b200_roi_crop_backward_ws")
     return grad_input1, grad_input2
 
 

@@ -145,6 +145,15 @@ B200_API int b200_roi_crop_forward(const float* image, const float* grids, int b
 B200_API int b200_roi_crop_backward(const float* grad_output, const float* grids, int batch_size, int channels,
                            int height, int width, int num_rois, int out_height, int out_width,
                            float* grad_image, float* grad_grids, b200_stream_t stream);
+/* Same with caller-supplied scratch (the Python layer takes it from torch's caching allocator): when the image gradient goes
+ * through the channel-innermost scratch image (vector reductions; C % 4 == 0 and enough taps) it needs
+ * b200_roi_crop_backward_workspace_bytes() bytes -- 0 when the scalar-atomic kernel is used.  b200_roi_crop_backward obtains
+ * the scratch with cudaMallocAsync / cudaFreeAsync on `stream`. */
+B200_API size_t b200_roi_crop_backward_workspace_bytes(int batch_size, int channels, int height, int width, int num_rois,
+                                                       int out_height, int out_width);
+B200_API int b200_roi_crop_backward_ws(const float* grad_output, const float* grids, int batch_size, int channels, int height,
+                                       int width, int num_rois, int out_height, int out_width, float* grad_image,
+                                       float* grad_grids, void* workspace, size_t workspace_bytes, b200_stream_t stream);
 
 /* ---- proposal NMS ------------------------------------------------------------------------------
  * replaces nms_cuda_compute, lib/model/nms/src/nms_cuda_kernel.cu:87-161 (header nms_cuda_kernel.h:5-6;

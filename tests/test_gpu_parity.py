@@ -496,6 +496,28 @@ def test_roi_crop_vs_oracle_reference_golden():
         assert np.array_equal(o, np.load(path)["out"])
 
 
+@pytest.mark.parametrize("shape,R", [((2, 32, 20, 24), 40), ((4, 256, 13, 17), 64), ((1, 48, 16, 16), 24)])
+def test_roi_crop_backward_vector_reduction_path(shape, R, lib_option):
+    """RoICrop image gradient through the channel-innermost scratch image (red.global.add.v4.f32, roi_crop.cu): against the fp64
+    oracle and against the scalar-atomic kernel (B200_ROI_ALIGN_BWD_PATH=generic), samples partly outside the image included."""
+    from detectron.pytorch_b200 import ops
+    img = S.make_features(shape, seed=7)
+    grid = S.make_crop_grid(R, 7, 7, seed=8).astype(np.float32)
+    grid[0, 0, 0] = (-1.0, -1.0); grid[1, 3, 3] = (-1.5, 0.2); grid[2, 6, 6] = (1.0, 1.0)
+    go = np.random.RandomState(9).standard_normal((R, shape[1], 7, 7)).astype(np.float32)
+    before = _lib.launch_count()
+    gi, gg = ops.roi_crop_backward(dev(go), dev(grid), shape)
+    assert _lib.launch_count() - before == 2                     # scatter + transpose (the scalar path counts 1)
+    ref = O.roi_crop_backward(go, grid, shape, acc64=True)
+    np.testing.assert_allclose(gi.cpu().numpy(), ref, **GRAD_TOL)
+    assert torch.count_nonzero(gg) == 0
+    lib_option("B200_ROI_ALIGN_BWD_PATH", "generic")
+    before = _lib.launch_count()
+    gi2, _ = ops.roi_crop_backward(dev(go), dev(grid), shape)
+    assert _lib.launch_count() - before == 1
+    np.testing.assert_allclose(gi.cpu().numpy(), gi2.cpu().numpy(), **GRAD_TOL)
+
+
 # -------------------------------------------------------------------------------------------- NMS
 @pytest.mark.parametrize("n", cases.NMS_SIZES)
 def test_nms_bit_exact(n):
