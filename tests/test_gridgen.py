@@ -46,5 +46,6 @@ def test_affine_grid_gen_helper_identity_roi_covers_the_map():
     torch.testing.assert_close(g2[0, -1, -1], torch.tensor([0.0, 0.0]), atol=1e-6, rtol=0)
 
 
-def test_crop_resize_is_the_same_function():
-    assert CropResizeFn is RoICropFunction
+def test_crop_resize_is_the_second_front_end_of_the_same_op():
+    """lib/model/roi_crop/functions/crop_resize.py: a second RoICropFunction over the same launchers that records its device."""
+    assert issubclass(CropResizeFn, RoICropFunction) and CropResizeFn().device == -1
