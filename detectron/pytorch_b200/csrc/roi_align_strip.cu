@@ -5,26 +5,35 @@
 // = fragments (<= 8 bins of one bin row of one RoI, keyed by the first feature row they read) -- but everything that cost
 // instructions there is organised differently:
 //
-//  * ring slot layout [column][32 channels] (cell = 128 B + 16 B pad = 144 B).  Compute mapping: lane = (bin b = lane / 8,
-//    channel quad q = lane % 8): ONE LDS.128 fetches one bilinear tap for FOUR channels, a quarter warp reads 128
-//    contiguous bytes (conflict-free for any cell), the arithmetic is packed fp32x2 (FMUL2 / FFMA2 / FADD2: both halves
-//    round like the scalar instruction, so the reference's operation order is kept bit for bit).  A pass evaluates 4 bins x
-//    32 channels in ~86 warp instructions; the lane = channel mapping of the first generation needs ~196 for the same.
-//  * staging: ONE producer warp, 4-byte cp.async (LDGSTS), lane = (8 consecutive columns x 4 channels): every request
-//    reads four full 32-byte sectors and the transposing write hits 32 distinct banks (bank = 4 x + c with the 36-word
-//    cell pitch).  Rows complete in order (cp.async groups of one thread), so residency is ONE monotonic counter
-//    (`ready` = rows of the CTA's row stream that have landed) instead of a parity-tracked mbarrier per slot;
+//  * ring slot layout [column][32 channels] (cell = 128 B; 144 B = 128 + 16 pad in cp.async mode).  Compute mapping:
+//    lane = (bin b = lane / 8, channel quad q = lane % 8): ONE LDS.128 fetches one bilinear tap for FOUR channels, a quarter
+//    warp reads 128 contiguous bytes (conflict-free for any cell), the arithmetic is packed fp32x2 (FMUL2 / FFMA2 / FADD2:
+//    both halves round like the scalar instruction, so the reference's operation order is kept bit for bit).  A pass
+//    evaluates 4 bins x 32 channels in ~90 warp instructions; the lane = channel mapping of the first generation needs ~196.
+//  * staging by TMA (default; W % 4 == 0 and a 16-byte aligned base): the map is described as the 4-D "x-quad" view
+//    (x mod 4, n C + c, x div 4, y) -- strides (4 B, H W 4, 16 B, W 4); a plain (x, y, c) box faults at strip starts that are
+//    not 16-byte aligned and cannot put the channel innermost -- and ONE cp.async.bulk.tensor.4d per row lands
+//    [quad][channel][4 floats] in the slot's own memory, issued by lane 0 of the issuer warp as soon as the slot is free;
+//    transposer warps (rows i mod T) wait for the slot's mbarrier, pull the row through registers (LDS.128, lane = channel)
+//    and rewrite it IN PLACE as [column][channel] (STS.32, lane = channel), then publish next[t] = their first stream row
+//    that has not landed.  128 shared-memory wavefronts per row instead of >= 512 LSU cycles for 64 four-byte cp.async;
+//  * staging by cp.async (fallback: any W, e.g. FPN P5 with W = 42; B200_STREAM_STAGE=async): every producer-side warp
+//    stages rows i mod kPW with 4-byte LDGSTS, lane = column (full 128-byte lines per request: the L1 tracks outstanding
+//    misses per line), the transposing write hits 8 distinct banks per returning sector (bank = 4 x + c with the 36-word
+//    pitch); a warp's rows land in order (cp.async groups of one thread) and it publishes the same next[] word;
+//  * residency is therefore min(next[]) -- one LDS.128 by a consumer warp whose fragment's last row is beyond what it has
+//    already seen -- instead of a parity-tracked mbarrier wait per row and warp;
 //  * slot release: every consumer warp publishes the stream index of the first row its current fragment reads (fragments
-//    are sorted by key, a warp's keys never decrease); the producer may overwrite row i - K once the minimum over the 16
-//    published words has passed it.  No per-row acquire / release by sixteen warps, no phase bits;
+//    are sorted by key, a warp's marks never decrease); row i - K may be overwritten once the minimum over the published
+//    words has passed it.  No per-row acquire / release, no phase bits;
 //  * results leave registers directly (lane = 4 channels of one bin: four stores per pass, 16-byte runs of 4 bins), axis
 //    tables are fetched per lane one fragment ahead straight into registers: no per-warp staging / table buffers, the
 //    whole shared memory is ring;
 //  * rows >= H are staged as zeros, and a sample clamped to the last row (low == high == H - 1, weights (1, 0)) reads
 //    that zero row with weight 0: no slot is ever read before it was written, so the ring needs no zero-initialisation;
-//  * prepass = ONE kernel (tables + fragment histogram, grid barrier, CSR scan in every CTA, fragment records, piece
-//    boundaries) instead of two kernels; the main kernel is launched with programmatic dependent launch so that its
-//    prologue overlaps the tail of the prepass.
+//  * prepass = ONE kernel (tables + fragment list, one returning atomic per fragment for its rank, grid barrier, CSR scan in
+//    every CTA, fragment records at row pointer + rank, piece boundaries spread over the CTAs) instead of two kernels; the
+//    main kernel is launched with programmatic dependent launch so that its prologue overlaps the tail of the prepass.
 //
 // Bit-exactness: every output element is computed by one lane in the reference's own operation order and written once;
 // only bins whose samples cannot be resident together are cut into per-sample fragments accumulated with red.global.add
