@@ -7,6 +7,14 @@ hyper-parameters and then *called* with the tensors -- `RoIAlignFunction(h, w, s
 rois)` (lib/modeling/model_builder.py:290-291).  torch >= 1.3 rejects non-static Functions, so this
 is a plain callable that delegates to a static Function; `.forward` / `.backward` remain usable
 directly and keep the reference's instance state (`rois`, `feature_size`).
+
+Numerics at this surface: the forward is deterministic and bit-identical to the reference kernel,
+except for bins whose samples cannot share a strip / the row ring (boxes wider than ~84 cells or taller than the ring at
+`sampling_ratio` 2): those are two partial sums, equal to the reference within 1e-7 and still run-to-run identical
+(`B200_ROI_ALIGN_PATH=generic` is the always-bit-exact switch).  A feature map that holds Inf / NaN can poison bins the
+reference would not let that cell reach: samples the reference skips are evaluated with weight 0.  The backward matches the
+reference within 1e-5 (fp32 accumulation order; the reference's atomicAdd order is itself undefined) and is not run-to-run
+bit-identical on the gather path (unit order comes from integer atomics).
 """
 from detectron.pytorch_b200 import ops as _ops
 
